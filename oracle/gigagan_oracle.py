@@ -1,0 +1,403 @@
+"""CPU/fp32 ORACLE for the GigaGAN G+D training hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a from-scratch *functional* restatement (plain torch ops on a
+``state_dict``) of the algorithm that lucidrains/gigagan-pytorch @ 0806433f runs
+for the unconditional generator / discriminator step.  It is the checker the
+CUDA product path is compared against; it is never imported by the product
+package ``gigagan_pytorch_b200`` (only ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may use it).
+
+Parity status: PINNED.  ``tests/test_oracle_vs_reference.py`` (runs in the build
+container where /root/reference exists) checks every function below against the
+unmodified reference modules on identical state_dicts/seeds, and
+``oracle/make_golden.py`` wrote the known-answer fixtures in ``tests/golden/``
+from the reference itself (the reference has no tests/golden vectors of its own,
+SURVEY.md section 4).
+
+All "ref:" citations are paths relative to /root/reference/gigagan_pytorch/.
+Tensors at this level are NCHW fp32, like the reference's.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------- #
+# configuration arithmetic (ref: gigagan_pytorch.py:1026-1040 G, :1565-1578 D)
+# --------------------------------------------------------------------------- #
+
+def generator_plan(image_size: int, dim_capacity: int = 16, dim_max: int = 2048, dim_latent: int = 512,
+                   num_skip_layers_excite: int = 0, self_attn_resolutions=(32, 16), num_conv_kernels: int = 2,
+                   self_attn_heads: int = 8, self_attn_dim_head: int = 64):
+    n = int(math.log2(image_size)) - 1
+    res = [image_size // (2 ** (n - 1 - i)) for i in range(n)]
+    dims = [min((2 ** (i + 1)) * dim_capacity, dim_max) for i in range(n)][::-1]
+    dims = [dim_latent] + dims
+    pairs = list(zip(dims[:-1], dims[1:]))
+    kmod = num_conv_kernels if num_conv_kernels > 1 else 0
+    split = [dim_latent, kmod]
+    layers = []
+    for i, ((ci, co), r) in enumerate(zip(pairs, res)):
+        split += [ci, kmod, co, kmod, co, 0]
+        layers.append(dict(index=i, dim_in=ci, dim_out=co, resolution=r, upsample=i > 0, upsample_rgb=i + 1 < n,
+                           squeeze_excite=num_skip_layers_excite > 0 and i + num_skip_layers_excite < n,
+                           self_attn=r in self_attn_resolutions))
+    return dict(layers=layers, split=split, num_skip_layers_excite=num_skip_layers_excite, dim_latent=dim_latent,
+                heads=self_attn_heads, dim_head=self_attn_dim_head)
+
+
+def discriminator_plan(image_size: int, dim_capacity: int = 16, dim_max: int = 2048, channels: int = 3,
+                       attn_resolutions=(32, 16), multiscale_input_resolutions=(64, 32, 16, 8),
+                       multiscale_output_skip_stages: int = 1, aux_recon_resolutions=(8,),
+                       aux_recon_patch_dims=(2,), aux_recon_frac_patches=(0.25,), num_skip_layers_excite: int = 0,
+                       attn_heads: int = 8, attn_dim_head: int = 64):
+    n = int(math.log2(image_size)) - 1
+    res = [image_size // (2 ** i) for i in range(n)]
+    dims = [min(d, dim_max) for d in [channels] + [(2 ** (i + 1)) * dim_capacity for i in range(n)]]
+    pairs = list(zip(dims[:-1], dims[1:]))
+    ms_in = [r for r in multiscale_input_resolutions if r < image_size]
+    ms_out = [r // (2 ** multiscale_output_skip_stages) for r in ms_in]
+    recon = {r: (p, f) for r, p, f in zip(aux_recon_resolutions, aux_recon_patch_dims, aux_recon_frac_patches)}
+    layers = []
+    for i, ((ci, co), r) in enumerate(zip(pairs, res)):
+        layers.append(dict(index=i, dim_in=ci, dim_out=co, resolution=r, downsample=i + 1 < n,
+                           squeeze_excite=i > 0 and num_skip_layers_excite > 0 and i + num_skip_layers_excite < n,
+                           attn=r in attn_resolutions, predictor=r in ms_out, recon=recon.get(r)))
+    return dict(layers=layers, ms_in=ms_in, ms_out=ms_out, num_skip_layers_excite=num_skip_layers_excite,
+                image_size=image_size, heads=attn_heads, dim_head=attn_dim_head)
+
+
+def _sub(sd: SD, prefix: str) -> SD:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# --------------------------------------------------------------------------- #
+# primitive blocks
+# --------------------------------------------------------------------------- #
+
+def leaky(x: Tensor) -> Tensor:
+    # ref: gigagan_pytorch.py:109-110 (negative slope 0.2 everywhere)
+    return torch.where(x >= 0, x, 0.2 * x)
+
+
+def channel_rmsnorm(x: Tensor, gamma: Tensor) -> Tensor:
+    # ref: gigagan_pytorch.py:224-232  F.normalize(dim=1) * sqrt(C) * gamma ; normalize eps 1e-12 on the norm
+    c = x.shape[1]
+    nrm = x.pow(2).sum(dim=1, keepdim=True).sqrt().clamp(min=1e-12)
+    return x / nrm * (c ** 0.5) * gamma.view(1, c, 1, 1)
+
+
+def blur3(x: Tensor) -> Tensor:
+    # ref: gigagan_pytorch.py:246-255 + kornia filter2d(normalized=True): [1,2,1]x[1,2,1]/16, reflect border
+    c = x.shape[1]
+    k1 = torch.tensor([1.0, 2.0, 1.0], dtype=x.dtype, device=x.device)
+    k = (k1[:, None] * k1[None, :]) / 16.0
+    xp = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    return F.conv2d(xp, k.expand(c, 1, 3, 3).contiguous(), groups=c)
+
+
+def upsample2x(x: Tensor) -> Tensor:
+    # ref: gigagan_pytorch.py:257-261  bilinear x2 (align_corners=False) then blur
+    return blur3(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False))
+
+
+def squeeze_excite(sd: SD, x: Tensor) -> Tensor:
+    # ref: gigagan_pytorch.py:297-307  mean -> Linear -> SiLU -> Linear -> Sigmoid -> (b c 1 1)
+    h = x.mean(dim=(2, 3))
+    h = F.linear(h, sd["1.weight"], sd["1.bias"])
+    h = h * torch.sigmoid(h)
+    h = torch.sigmoid(F.linear(h, sd["3.weight"], sd["3.bias"]))
+    return h[:, :, None, None]
+
+
+def adaptive_conv2d_mod(weights: Tensor, fmap: Tensor, mod: Tensor, kernel_mod: Optional[Tensor] = None,
+                        demod: bool = True, eps: float = 1e-8) -> Tensor:
+    """ref: gigagan_pytorch.py:344-409.  weights (n,o,i,k,k); fmap (b,i,h,w); mod (b',i); kernel_mod (b',n)."""
+    b = fmap.shape[0]
+    n, o, i, k, _ = weights.shape
+    if mod.shape[0] != b:                      # ref :365-366 scale-major repeat '(s b)'
+        mod = mod.repeat(b // mod.shape[0], 1)
+    if n > 1:
+        assert kernel_mod is not None and kernel_mod.numel() > 0
+        if kernel_mod.shape[0] != b:           # ref :373-374
+            kernel_mod = kernel_mod.repeat(b // kernel_mod.shape[0], 1)
+        attn = kernel_mod.softmax(dim=-1)      # ref :387
+        w = torch.einsum("bn,noikl->boikl", attn, weights)   # ref :390
+    else:
+        w = weights.expand(b, o, i, k, k) if weights.shape[0] == 1 else weights
+    w = w * (mod[:, None, :, None, None] + 1.0)              # ref :394-396
+    if demod:                                                # ref :398-400
+        inv = w.pow(2).sum(dim=(2, 3, 4), keepdim=True).clamp(min=eps).rsqrt()
+        w = w * inv
+    pad = (k - 1) // 2                                       # ref :312-313,406 (stride 1, dilation 1)
+    y = F.conv2d(fmap.reshape(1, b * i, *fmap.shape[2:]), w.reshape(b * o, i, k, k), padding=pad, groups=b)
+    return y.reshape(b, o, *y.shape[2:])
+
+
+def style_network(sd: SD, z: Tensor, depth: int, lr_mul: float = 0.1) -> Tensor:
+    # ref: gigagan_pytorch.py:871-887 EqualLinear, :910-921 StyleNetwork.forward
+    x = z / z.pow(2).sum(dim=1, keepdim=True).sqrt().clamp(min=1e-12)
+    for d in range(depth):
+        x = leaky(F.linear(x, sd[f"net.{2 * d}.weight"] * lr_mul, sd[f"net.{2 * d}.bias"] * lr_mul))
+    return x
+
+
+def self_attention(sd: SD, fmap: Tensor, heads: int = 8, dim_head: int = 64, dot_product: bool = False) -> Tensor:
+    """ref: gigagan_pytorch.py:538-594."""
+    b, _, hh, ww = fmap.shape
+    x = channel_rmsnorm(fmap, sd["norm.gamma"])
+    q = F.conv2d(x, sd["to_q.weight"])
+    v = F.conv2d(x, sd["to_v.weight"])
+    k = F.conv2d(x, sd["to_k.weight"]) if "to_k.weight" in sd else q      # ref :560 shared q/k space
+
+    def split(t):   # 'b (h d) x y -> (b h) (x y) d'
+        return t.reshape(b, heads, dim_head, hh * ww).permute(0, 1, 3, 2).reshape(b * heads, hh * ww, dim_head)
+
+    q, k, v = split(q), split(k), split(v)
+    nk = sd["null_kv"][0][None].expand(b, heads, dim_head).reshape(b * heads, 1, dim_head)   # ref :566
+    nv = sd["null_kv"][1][None].expand(b, heads, dim_head).reshape(b * heads, 1, dim_head)
+    k = torch.cat((nk, k), dim=1)
+    v = torch.cat((nv, v), dim=1)
+    if dot_product:
+        sim = q @ k.transpose(1, 2)                                          # ref :574
+    else:                                                                    # ref :577-580
+        sim = -((q * q).sum(-1)[:, :, None] + (k * k).sum(-1)[:, None, :] - 2.0 * (q @ k.transpose(1, 2)))
+    attn = (sim * dim_head ** -0.5).softmax(dim=-1)                          # ref :584-588
+    out = attn @ v
+    out = out.reshape(b, heads, hh * ww, dim_head).permute(0, 1, 3, 2).reshape(b, heads * dim_head, hh, ww)
+    return F.conv2d(out, sd["to_out.weight"])
+
+
+def self_attention_block(sd: SD, x: Tensor, dot_product: bool, heads: int = 8, dim_head: int = 64) -> Tensor:
+    # ref: gigagan_pytorch.py:744-760 (+ FeedForward :726-740, exact erf GELU)
+    x = self_attention(_sub(sd, "attn."), x, heads, dim_head, dot_product) + x
+    h = channel_rmsnorm(x, sd["ff.0.gamma"])
+    h = F.conv2d(h, sd["ff.1.weight"], sd["ff.1.bias"])
+    h = F.gelu(h)
+    h = F.conv2d(h, sd["ff.3.weight"], sd["ff.3.bias"])
+    return h + x
+
+
+# --------------------------------------------------------------------------- #
+# generator (ref: gigagan_pytorch.py:1140-1250)
+# --------------------------------------------------------------------------- #
+
+def generator_forward(sd: SD, plan: dict, noise: Tensor, style_depth: int = 4,
+                      layer_noises: Optional[Sequence[Tensor]] = None, return_all_rgbs: bool = False,
+                      self_attn_dot_product: bool = True):
+    """``layer_noises``: the 2*num_layers per-layer noise images (b,1,h,w); when None they are drawn with
+    torch.randn in the reference's order (ref :938) so that a shared manual_seed reproduces the reference."""
+    b = noise.shape[0]
+    styles = style_network(_sub(sd, "style_network."), noise, style_depth)
+    mods = F.linear(styles, sd["style_to_conv_modulations.weight"], sd["style_to_conv_modulations.bias"])
+    mods = list(mods.split(plan["split"], dim=-1))                 # ref :1184-1186
+
+    def nxt():
+        return mods.pop(0)
+
+    x = sd["init_block"][None].expand(b, -1, -1, -1)               # ref :1192
+    x = adaptive_conv2d_mod(sd["init_conv.weights"], x, nxt(), nxt())
+    rgb = torch.zeros(b, sd["layers.0.2.weights"].shape[1], 4, 4, dtype=x.dtype, device=x.device)
+    excitations: List[Optional[Tensor]] = [None] * plan["num_skip_layers_excite"]
+    rgbs = []
+    ln = list(layer_noises) if layer_noises is not None else None
+
+    def noise_img(t):
+        if ln is not None:
+            return ln.pop(0)
+        return torch.randn(t.shape[0], 1, t.shape[2], t.shape[3], device=t.device)   # ref :938
+
+    for L in plan["layers"]:
+        p = f"layers.{L['index']}."
+        if L["upsample"]:
+            x = upsample2x(x)                                      # ref :1209-1210
+        if L["squeeze_excite"]:
+            excitations.append(squeeze_excite(_sub(sd, p + "0."), x))   # ref :1212-1214
+        ex = excitations.pop(0) if excitations else None           # ref :1216-1218
+        if ex is not None:
+            x = x * ex
+        x = adaptive_conv2d_mod(sd[p + "1.0.weights"], x, nxt(), nxt())
+        x = leaky(x + sd[p + "1.1.weight"][None] * noise_img(x))   # ref :1221-1222, Noise :940
+        x = adaptive_conv2d_mod(sd[p + "1.3.weights"], x, nxt(), nxt())
+        x = leaky(x + sd[p + "1.4.weight"][None] * noise_img(x))
+        if L["self_attn"]:
+            x = self_attention_block(_sub(sd, p + "3."), x, self_attn_dot_product, plan["heads"], plan["dim_head"])
+        rgb = rgb + adaptive_conv2d_mod(sd[p + "2.weights"], x, nxt(), nxt(), demod=False)   # ref :1234-1236
+        rgbs.append(rgb)
+        if L["upsample_rgb"]:
+            rgb = upsample2x(rgb)
+    assert not mods
+    return (rgb, rgbs) if return_all_rgbs else rgb
+
+
+# --------------------------------------------------------------------------- #
+# discriminator (ref: gigagan_pytorch.py:1697-1838)
+# --------------------------------------------------------------------------- #
+
+def predictor(sd: SD, x: Tensor, depth: int = 2) -> Tensor:
+    # ref: gigagan_pytorch.py:1472-1498 (unconditional: plain convs)
+    residual = F.conv2d(x, sd["residual_fn.weight"], sd["residual_fn.bias"])
+    for d in range(depth):
+        inner = x
+        x = leaky(F.conv2d(x, sd[f"layers.{d}.0.weight"], sd[f"layers.{d}.0.bias"], padding=1))
+        x = leaky(F.conv2d(x, sd[f"layers.{d}.2.weight"], sd[f"layers.{d}.2.bias"], padding=1))
+        x = (x + inner) * (2 ** -0.5)
+    x = x + residual
+    return F.conv2d(x, sd["to_logits.weight"], sd["to_logits.bias"])
+
+
+def simple_decoder(sd: SD, fmap: Tensor, image: Tensor, patch_dim: int, frac: float,
+                   dropout_mask: Optional[Tensor] = None, patch_indices: Optional[Tensor] = None,
+                   training: bool = True, p_drop: float = 0.5) -> Tensor:
+    """ref: gigagan_pytorch.py:1290-1317.  dropout_mask is the keep-mask already scaled by 1/(1-p);
+    patch_indices (b, n_sel) long.  When None they are drawn like the reference (dropout on fmap's device,
+    permutation from a CPU randn argsort, ref :1310)."""
+    if training:
+        if dropout_mask is None:
+            fmap = F.dropout(fmap, p_drop, training=True)
+        else:
+            fmap = fmap * dropout_mask
+    if frac < 1.0:
+        b = fmap.shape[0]
+
+        def patches(t):   # 'b c (p1 h) (p2 w) -> b (p1 p2) c h w'
+            bb, c, hh, ww = t.shape
+            h, w = hh // patch_dim, ww // patch_dim
+            return t.reshape(bb, c, patch_dim, h, patch_dim, w).permute(0, 2, 4, 1, 3, 5).reshape(
+                bb, patch_dim * patch_dim, c, h, w)
+
+        fm, im = patches(fmap), patches(image)
+        total = patch_dim ** 2
+        nsel = max(int(frac * total), 1)
+        if patch_indices is None:
+            patch_indices = torch.randn((b, total)).sort(dim=-1).indices[:, :nsel]
+        idx = patch_indices.to(fmap.device)
+        ar = torch.arange(b, device=fmap.device)[:, None]
+        fmap = fm[ar, idx].flatten(0, 1)
+        image = im[ar, idx].flatten(0, 1)
+    x = F.conv2d(fmap, sd["net.0.weight"], sd["net.0.bias"], padding=1)
+    i = 1
+    while f"net.{i}.1.weight" in sd:
+        x = upsample2x(x)
+        x = leaky(F.conv2d(x, sd[f"net.{i}.1.weight"], sd[f"net.{i}.1.bias"], padding=1))
+        i += 1
+    return F.mse_loss(x, image)
+
+
+def real_images_to_rgbs(images: Tensor, plan: dict) -> List[Tensor]:
+    # ref: gigagan_pytorch.py:1683-1687 (bilinear, align_corners default False, no antialias)
+    return [F.interpolate(images, r, mode="bilinear") for r in plan["ms_in"]]
+
+
+def discriminator_forward(sd: SD, plan: dict, images: Tensor, rgbs: Sequence[Tensor],
+                          return_multiscale_outputs: bool = True, calc_aux_loss: bool = True,
+                          training: bool = True, recon_dropout_mask=None, recon_patch_indices=None):
+    x = images
+    batch = x.shape[0]
+    by_res = {t.shape[-1]: t for t in rgbs}
+    ms_out, aux = [], []
+    excitations: List[Optional[Tensor]] = [None] * (plan["num_skip_layers_excite"] + 1)   # ref :1754
+    for L in plan["layers"]:
+        p = f"layers.{L['index']}."
+        res = x.shape[-1]
+        if L["squeeze_excite"]:
+            excitations.append(squeeze_excite(_sub(sd, p + "0."), x))
+        ex = excitations.pop(0) if excitations else None
+        if ex is not None:
+            x = x * ex.repeat(x.shape[0] // ex.shape[0], 1, 1, 1)        # ref :1766 '(s b)'
+        prev = x.shape[0]
+        if res in plan["ms_in"]:                                           # ref :1772-1789
+            f = F.conv2d(by_res[res], sd[p + "1.weight"], sd[p + "1.bias"], padding=3)
+            f = f.repeat(x.shape[0] // f.shape[0], 1, 1, 1)
+            x = torch.cat((x + f, f), dim=0)
+        residual = F.conv2d(x, sd[p + "3.weight"], sd[p + "3.bias"], stride=2 if L["downsample"] else 1)
+        x = leaky(F.conv2d(x, sd[p + "2.0.weight"], sd[p + "2.0.bias"], padding=1))
+        x = leaky(F.conv2d(x, sd[p + "2.2.weight"], sd[p + "2.2.bias"], padding=1))
+        if L["attn"]:
+            x = self_attention_block(_sub(sd, p + "4."), x, False, plan["heads"], plan["dim_head"])
+        if L["predictor"] and return_multiscale_outputs:
+            ms_out.append(predictor(_sub(sd, p + "5."), x[:prev]))         # ref :1803-1804
+        if L["downsample"]:                                                # ref :289-293 pixel-unshuffle + 1x1
+            x = F.conv2d(F.pixel_unshuffle(x, 2), sd[p + "7.1.weight"], sd[p + "7.1.bias"])
+        x = (x + residual) * (2 ** -0.5)                                   # ref :1809-1810
+        if L["recon"] is not None and calc_aux_loss:                       # ref :1812-1827 (Q3: post-downsample x)
+            pd, fr = L["recon"]
+            aux.append(simple_decoder(_sub(sd, p + "6."), x[:batch], images, pd, fr,
+                                      recon_dropout_mask, recon_patch_indices, training))
+    x = F.conv2d(x, sd["to_logits.0.weight"], sd["to_logits.0.bias"], padding=1)   # ref :1655-1660
+    logits = F.linear(x.flatten(1), sd["to_logits.2.weight"], sd["to_logits.2.bias"])[:, 0]
+    return logits.reshape(-1, batch), ms_out, aux                          # ref :1836 '(s b) -> s b'
+
+
+# --------------------------------------------------------------------------- #
+# losses and the two step objectives (ref: gigagan_pytorch.py:120-163, :2227-2610)
+# --------------------------------------------------------------------------- #
+
+def generator_hinge_loss(fake: Tensor) -> Tensor:
+    return fake.mean()                                                      # ref :159-160
+
+
+def discriminator_hinge_loss(real: Tensor, fake: Tensor) -> Tensor:
+    return (F.relu(1 + real) + F.relu(1 - fake)).mean()                     # ref :162-163
+
+
+def gradient_penalty(images: Tensor, outputs: Sequence[Tensor], grad_output_weights: Sequence[float],
+                     weight: float = 10.0) -> Tensor:
+    # ref: gigagan_pytorch.py:120-155 (no GradScaler: bf16/fp32)
+    g, = torch.autograd.grad(outputs=list(outputs), inputs=images,
+                             grad_outputs=[torch.ones_like(o) * w for o, w in zip(outputs, grad_output_weights)],
+                             create_graph=True, retain_graph=True)
+    return weight * (g.flatten(1).norm(2, dim=1) ** 2).mean()
+
+
+def discriminator_step_loss(sd_d: SD, plan_d: dict, real: Tensor, fake: Tensor, fake_rgbs: Sequence[Tensor],
+                            apply_gradient_penalty: bool, ms_weight: float = 0.1, aux_weight: float = 1.0,
+                            calc_multiscale_loss: bool = True, recon_dropout_mask=None, recon_patch_indices=None):
+    """Loss of ref train_discriminator_step (:2320-2422), one micro-batch, unconditional, no VD.
+    ``real``/``fake``/``fake_rgbs`` must require grad when the penalty is on (ref :2275, :2311-2316)."""
+    real_rgbs = real_images_to_rgbs(real, plan_d)
+    f_logits, f_ms, _ = discriminator_forward(sd_d, plan_d, fake, fake_rgbs, calc_multiscale_loss, False)
+    r_logits, r_ms, aux = discriminator_forward(sd_d, plan_d, real, real_rgbs, calc_multiscale_loss, True,
+                                                recon_dropout_mask=recon_dropout_mask,
+                                                recon_patch_indices=recon_patch_indices)
+    div = discriminator_hinge_loss(r_logits, f_logits)
+    ms = sum((discriminator_hinge_loss(r, f) for f, r in zip(f_ms, r_ms)), torch.zeros((), device=real.device))
+    gp = torch.zeros((), device=real.device)
+    if apply_gradient_penalty:
+        w = [1.0] + [ms_weight] * len(r_ms)
+        gp = gradient_penalty(real, [r_logits, *r_ms], w) + gradient_penalty(fake, [f_logits, *f_ms], w)
+    aux_loss = sum(aux, torch.zeros((), device=real.device))
+    total = div + gp + ms * ms_weight + aux_loss * aux_weight
+    return total, dict(divergence=div, multiscale=ms, gradient_penalty=gp, aux_reconstruction=aux_loss)
+
+
+def generator_step_loss(sd_g: SD, plan_g: dict, sd_d: SD, plan_d: dict, noise: Tensor, style_depth: int = 4,
+                        layer_noises=None, ms_weight: float = 0.1, calc_multiscale_loss: bool = True):
+    """Loss of ref train_generator_step (:2518-2562), one micro-batch, unconditional, no VD."""
+    img, rgbs = generator_forward(sd_g, plan_g, noise, style_depth, layer_noises, return_all_rgbs=True)
+    logits, ms, _ = discriminator_forward(sd_d, plan_d, img, rgbs, calc_multiscale_loss, False)
+    div = generator_hinge_loss(logits)
+    msd = sum((generator_hinge_loss(m) for m in ms), torch.zeros((), device=noise.device))
+    return div + msd * ms_weight, dict(divergence=div, multiscale=msd), img
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=2e-4, b1=0.5, b2=0.9, eps=1e-8,
+               wd: Optional[float] = None):
+    """torch.optim.AdamW update as the reference configures it (ref optimizer.py:10-34; SURVEY Q2: wd=1e-2 on
+    ndim>=2 parameters, 0 otherwise).  In-place on p, m, v."""
+    if wd is None:
+        wd = 1e-2 if p.ndim >= 2 else 0.0
+    p.mul_(1 - lr * wd)
+    m.lerp_(g, 1 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1 - b2)
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-lr / bc1)

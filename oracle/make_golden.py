@@ -1,0 +1,106 @@
+"""Writes tests/golden/*.pt from the UNMODIFIED reference (run in the build container only):
+    python oracle/make_golden.py
+Each fixture holds a tiny model's state_dict, the seeded inputs and the reference's outputs /
+gradients, so that the GPU box (which has no /root/reference) can check oracle and CUDA path."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "ref_shims"))
+sys.path.insert(0, "/root/reference")
+import gigagan_pytorch as ref  # noqa: E402
+from gigagan_pytorch.gigagan_pytorch import (SelfAttentionBlock, discriminator_hinge_loss,  # noqa: E402
+                                             gradient_penalty)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def rn(k, *s):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(k))
+
+
+def sd_of(m):
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # ---- KA1: AdaptiveConv2DMod fwd+bwd (SURVEY 8c KA1 recipe)
+    torch.manual_seed(0)
+    m = ref.AdaptiveConv2DMod(8, 6, 3, num_conv_kernels=2)
+    x = rn(1, 2, 8, 5, 5).requires_grad_()
+    mod = rn(2, 2, 8).requires_grad_()
+    km = rn(3, 2, 2).requires_grad_()
+    y = m(x, mod=mod, kernel_mod=km)
+    (y ** 2).sum().backward()
+    torch.save(dict(weights=m.weights.detach().clone(), x=x.detach(), mod=mod.detach(), kernel_mod=km.detach(),
+                    y=y.detach(), dweights=m.weights.grad.clone(), dx=x.grad.clone(), dmod=mod.grad.clone(),
+                    dkernel_mod=km.grad.clone()), os.path.join(OUT, "ka1_adaptive_conv.pt"))
+    # ---- KA2: SelfAttentionBlock (L2 and dot)
+    for dot in (False, True):
+        torch.manual_seed(0)
+        blk = SelfAttentionBlock(16, dim_head=8, heads=2, dot_product=dot)
+        x = rn(1, 2, 16, 4, 4).requires_grad_()
+        y = blk(x)
+        (y ** 2).sum().backward()
+        torch.save(dict(sd=sd_of(blk), x=x.detach(), y=y.detach(), dx=x.grad.clone(),
+                        grads={k: p.grad.clone() for k, p in blk.named_parameters()}),
+                   os.path.join(OUT, f"ka2_attn_block_{'dot' if dot else 'l2'}.pt"))
+    # ---- KA3: StyleNetwork
+    torch.manual_seed(0)
+    sn = ref.StyleNetwork(dim=64, depth=4)
+    z = rn(1, 2, 64)
+    torch.save(dict(sd=sd_of(sn), z=z, y=sn(z).detach()), os.path.join(OUT, "ka3_style_network.pt"))
+    # ---- KA4: tiny Generator (image 32, capacity 2) fwd + grads of sum(rgb^2)
+    gcfg = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+                num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,),
+                self_attn_dim_head=8, self_attn_heads=2)
+    torch.manual_seed(0)
+    G = ref.Generator(**gcfg)
+    with torch.no_grad():
+        for n, p in G.named_parameters():
+            if n.endswith(".1.1.weight") or n.endswith(".1.4.weight"):
+                p.copy_(torch.randn_like(p) * 0.1)
+    z = rn(1, 2, 16)
+    torch.manual_seed(2)
+    rgb, rgbs = G(noise=z, return_all_rgbs=True)
+    (rgb ** 2).mean().backward()
+    torch.save(dict(cfg=gcfg, sd=sd_of(G), z=z, noise_seed=2, rgb=rgb.detach(), rgbs=[t.detach() for t in rgbs],
+                    grads={k: p.grad.clone() for k, p in G.named_parameters() if p.grad is not None}),
+               os.path.join(OUT, "ka4_generator.pt"))
+    # ---- KA5: tiny Discriminator (image 32) fwd, D-step objective with GP, param grads
+    dcfg = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8),
+                aux_recon_resolutions=(8,))
+    torch.manual_seed(0)
+    D = ref.Discriminator(**dcfg)
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    fake = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        D.eval()
+        logits, ms, _ = D(img, D.real_images_to_rgbs(img), calc_aux_loss=False)
+        D.train()
+    r = img.clone().requires_grad_()
+    f = fake.clone().requires_grad_()
+    frgbs = [t.detach().requires_grad_() for t in D.real_images_to_rgbs(f)]
+    fl, fm, _ = D(f, frgbs, calc_aux_loss=False)
+    rl, rm, _ = D(r, D.real_images_to_rgbs(r), calc_aux_loss=False)
+    div = discriminator_hinge_loss(rl, fl)
+    msl = sum(discriminator_hinge_loss(b, a) for a, b in zip(fm, rm))
+    w = [1.0] + [0.1] * len(rm)
+    gp = gradient_penalty(r, [rl, *rm], w) + gradient_penalty(f, [fl, *fm], w)
+    total = div + gp + 0.1 * msl
+    total.backward()
+    torch.save(dict(cfg=dcfg, sd=sd_of(D), img=img, fake=fake, logits=logits, ms=ms,
+                    loss=dict(total=total.detach(), divergence=div.detach(), multiscale=msl.detach(),
+                              gradient_penalty=gp.detach()),
+                    grads={k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}),
+               os.path.join(OUT, "ka5_discriminator.pt"))
+    for f_ in sorted(os.listdir(OUT)):
+        print(f_, os.path.getsize(os.path.join(OUT, f_)))
+
+
+if __name__ == "__main__":
+    main()
