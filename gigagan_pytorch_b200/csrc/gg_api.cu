@@ -1,0 +1,111 @@
+// extern "C" surface of libgigagan_sm100.so (declared in include/gigagan_sm100.h).
+#include <stdarg.h>
+#include <string.h>
+#include "../../include/gigagan_sm100.h"
+#include "gg_internal.h"
+
+static thread_local char g_err[512] = "";
+
+int gg_fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return -1;
+}
+int gg_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -2;
+}
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" {
+const char* gg_last_error(void) { return g_err; }
+int gg_version(void) { return 100; }
+int gg_has_tcgen05(void) {
+#ifdef GG_NO_TC
+  return 0;
+#else
+  return 1;
+#endif
+}
+
+int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
+                    int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                    float gain, int dtype, gg_stream_t stream) {
+#ifndef GG_NO_TC
+  if (dtype == GG_BF16) {
+    int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ST);
+    if (r <= 0) return r;
+  }
+#endif
+  return ggi_simt_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, dtype, ST);
+}
+int gg_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                    int KH, int KW, int stride, int pad, int per_sample_w, int dtype, gg_stream_t stream) {
+  return ggi_simt_conv_dgrad(dy, w, dx, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, dtype, ST);
+}
+int gg_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                    int KH, int KW, int stride, int pad, int per_sample_w, int dtype, gg_stream_t stream) {
+  return ggi_simt_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, dtype, ST);
+}
+int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
+           const int64_t* h_sa, const int64_t* h_sb, const int64_t* h_sc, float alpha, int dtype, gg_stream_t stream) {
+  return ggi_simt_bmm(A, B, bias, C, b1, b2, M, N, K, (const long*)h_sa, (const long*)h_sb, (const long*)h_sc, alpha, dtype, ST);
+}
+int gg_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, int64_t n, int dtype, gg_stream_t stream) {
+  return ggi_pw_unary(kind, level, x, a, b, out, n, dtype, ST);
+}
+int gg_pw_mul(const void* a, const void* b, void* out, int64_t n, int dtype, gg_stream_t stream) { return ggi_pw_mul(a, b, out, n, dtype, ST); }
+int gg_pw_axpby(float alpha, const void* x, float beta, const void* y, void* out, int64_t n, int dtype, gg_stream_t stream) {
+  return ggi_pw_axpby(alpha, x, beta, y, out, n, dtype, ST);
+}
+int gg_pw_bcast(const void* x, const float* s, void* out, int64_t R, int C, int P, int Ns, int mode, int op, int dtype, gg_stream_t stream) {
+  return ggi_pw_bcast(x, s, out, R, C, P, Ns, mode, op, dtype, ST);
+}
+int gg_red_rowdot(const void* a, const void* b, float* out, int64_t R, int C, int dtype, gg_stream_t stream) { return ggi_red_rowdot(a, b, out, R, C, dtype, ST); }
+int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype, gg_stream_t stream) {
+  return ggi_red_dot_sc(a, b, out, R, C, P, Ns, dtype, ST);
+}
+int gg_softmax_rows(const void* s, void* p, int64_t R, int C, int dtype, gg_stream_t stream) { return ggi_softmax_rows(s, p, R, C, dtype, ST); }
+int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
+                  int Ty, const int* ix, const float* wx, int Tx, int dtype, gg_stream_t stream) {
+  return ggi_resample2d(x, y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx, dtype, ST);
+}
+int gg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int HW, int Cpad, int dtype, gg_stream_t stream) { return ggi_nchw_to_nhwc(src, dst, N, C, HW, Cpad, dtype, ST); }
+int gg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, int Cpad, int dtype, gg_stream_t stream) { return ggi_nhwc_to_nchw(src, dst, N, C, HW, Cpad, dtype, ST); }
+int gg_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, int64_t R, int C, int dtype, gg_stream_t stream) {
+  return ggi_noise_act_fwd(x, noise, wn, y, R, C, dtype, ST);
+}
+int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, int64_t R, int C, int dtype, gg_stream_t stream) {
+  return ggi_noise_act_bwd(y, gy, noise, dx, dwn, R, C, dtype, ST);
+}
+int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
+                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, gg_stream_t stream) {
+  return ggi_adaconv_weights_fwd(bank, mod, kmod, w, attn, dinv, B, n, O, I, KK, demod, eps, dtype, ST);
+}
+int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
+                           float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
+                           int demod, float eps, gg_stream_t stream) {
+  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, ST);
+}
+int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, int B, int heads,
+                int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,
+                int dtype, gg_stream_t stream) {
+  return ggi_attn_fwd(q, k, v, null_kv, o, lse, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, dtype, ST);
+}
+int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
+                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, int B, int heads,
+                int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,
+                int dtype, gg_stream_t stream) {
+  return ggi_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, dtype, ST);
+}
+int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr, float lr,
+             float b1, float b2, float eps, float wd, float grad_scale, gg_stream_t stream) {
+  return ggi_adamw(p, g, m, v, chunks, nchunks, step_ptr, lr, b1, b2, eps, wd, grad_scale, ST);
+}
+int gg_incr(int* p, gg_stream_t stream) { return ggi_incr(p, ST); }
+}

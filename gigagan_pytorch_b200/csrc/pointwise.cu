@@ -1,0 +1,468 @@
+// Bandwidth-bound kernels: pointwise maps (3 derivative levels), broadcast multiplies/adds and their
+// partner reductions, row softmax, separable sparse resampling (bilinear x2 + binomial blur, bilinear resize),
+// NCHW<->NHWC, noise+activation, the AdaptiveConv2DMod weight builder, AdamW.
+// Reference call sites: gigagan_pytorch.py:224-261 (RMSNorm/Blur/Upsample), :297-307 (SqueezeExcite),
+// :378-400 (weight modulation/demodulation), :925-940 (Noise), :588 (softmax), optimizer.py:34 (AdamW).
+#include "gg_common.cuh"
+
+// ------------------------------------------------------------------ unary maps
+enum { U_LRELU = 0, U_RELU = 1, U_GELU = 2, U_SILU = 3, U_SIGMOID = 4, U_INVNORM = 5 };
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+template <int LEVEL>
+__device__ __forceinline__ float unary_eval(int kind, float x) {
+  switch (kind) {
+    case U_LRELU: return LEVEL == 0 ? (x > 0.f ? x : 0.2f * x) : LEVEL == 1 ? (x > 0.f ? 1.f : 0.2f) : 0.f;
+    case U_RELU: return LEVEL == 0 ? fmaxf(x, 0.f) : LEVEL == 1 ? (x > 0.f ? 1.f : 0.f) : 0.f;
+    case U_GELU: {
+      float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+      if (LEVEL == 0) return x * cdf;
+      float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+      return LEVEL == 1 ? cdf + x * pdf : pdf * (2.f - x * x);
+    }
+    case U_SILU: {
+      float s = sigmoidf_(x);
+      return LEVEL == 0 ? x * s : LEVEL == 1 ? s * (1.f + x * (1.f - s)) : s * (1.f - s) * (2.f + x * (1.f - 2.f * s));
+    }
+    case U_SIGMOID: {
+      float s = sigmoidf_(x);
+      return LEVEL == 0 ? s : LEVEL == 1 ? s * (1.f - s) : s * (1.f - s) * (1.f - 2.f * s);
+    }
+    case U_INVNORM: {   // 1 / max(sqrt(x), 1e-12)  (F.normalize's denominator), x = sum of squares
+      if (x <= 1e-24f) return LEVEL == 0 ? 1e12f : 0.f;
+      float r = rsqrtf(x);
+      return LEVEL == 0 ? r : LEVEL == 1 ? -0.5f * r * r * r : 0.75f * r * r * r * r * r;
+    }
+  }
+  return 0.f;
+}
+
+// level 0: out = f(x); level 1: out = a * f'(x); level 2: out = a * b * f''(x)
+template <typename T, int LEVEL>
+__global__ void unary_kernel(int kind, const T* __restrict__ x, const T* __restrict__ a, const T* __restrict__ b,
+                             T* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = unary_eval<LEVEL>(kind, ldf(x + i));
+    if (LEVEL >= 1) v *= ldf(a + i);
+    if (LEVEL >= 2) v *= ldf(b + i);
+    stf(out + i, v);
+  }
+}
+
+int ggi_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, long n, int dtype,
+                cudaStream_t st) {
+  int blocks = gg_blocks(n, 256);
+  GG_DISPATCH(dtype, {
+    if (level == 0) unary_kernel<T, 0><<<blocks, 256, 0, st>>>(kind, (const T*)x, nullptr, nullptr, (T*)out, n);
+    else if (level == 1) unary_kernel<T, 1><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, nullptr, (T*)out, n);
+    else unary_kernel<T, 2><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, (const T*)b, (T*)out, n);
+  });
+  return gg_check_launch("unary");
+}
+
+// ------------------------------------------------------------------ binary maps
+template <typename T>
+__global__ void mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    stf(out + i, ldf(a + i) * ldf(b + i));
+}
+template <typename T>
+__global__ void axpby_kernel(float alpha, const T* __restrict__ x, float beta, const T* __restrict__ y,
+                             T* __restrict__ out, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = alpha * ldf(x + i);
+    if (y) v += beta * ldf(y + i);
+    stf(out + i, v);
+  }
+}
+int ggi_pw_mul(const void* a, const void* b, void* out, long n, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (mul_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n)));
+  return gg_check_launch("mul");
+}
+int ggi_pw_axpby(float alpha, const void* x, float beta, const void* y, void* out, long n, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (axpby_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>(alpha, (const T*)x, beta, (const T*)y, (T*)out, n)));
+  return gg_check_launch("axpby");
+}
+
+// ------------------------------------------------------------------ broadcasts over a [R, C] view
+// mode 0 (ROWS): s[r].  mode 1 (SAMPLE_CH): s[((r / P) % Ns) * C + c]  (P rows per sample, scale-major repeat)
+// op 0: out = x * s ; op 1: out = x + s.   s is always fp32.
+template <typename T>
+__global__ void bcast_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ out, long R, int C,
+                             int P, int Ns, int mode, int op) {
+  long n = R * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    long r = i / C;
+    int c = (int)(i % C);
+    float sv = mode == 0 ? s[r] : s[((r / P) % Ns) * (long)C + c];
+    float xv = ldf(x + i);
+    stf(out + i, op == 0 ? xv * sv : xv + sv);
+  }
+}
+int ggi_pw_bcast(const void* x, const float* s, void* out, long R, int C, int P, int Ns, int mode, int op, int dtype,
+                cudaStream_t st) {
+  GG_DISPATCH(dtype, (bcast_kernel<T><<<gg_blocks(R * C, 256), 256, 0, st>>>((const T*)x, s, (T*)out, R, C, P, Ns, mode, op)));
+  return gg_check_launch("bcast");
+}
+
+// out[r] = sum_c a[r,c] * b[r,c]  (b may be null -> row sums); one warp per row
+template <typename T>
+__global__ void rowdot_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, long R, int C) {
+  long r = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  int lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int c = lane; c < C; c += 32) acc += ldf(a + r * C + c) * (b ? ldf(b + r * C + c) : 1.f);
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
+}
+int ggi_red_rowdot(const void* a, const void* b, float* out, long R, int C, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (rowdot_kernel<T><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)a, (const T*)b, out, R, C)));
+  return gg_check_launch("rowdot");
+}
+
+// out[n', c] = sum_{n == n' (mod Ns)} sum_{p < P} a[(n,p), c] * b[(n,p), c]   (fp32 out, zeroed here)
+template <typename T>
+__global__ void dot_sc_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, int C, int P,
+                              int Ns, long rows_per_out, int splits) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  int ns = blockIdx.y;
+  long chunk = (rows_per_out + splits - 1) / splits;
+  long j0 = blockIdx.z * chunk, j1 = min(rows_per_out, j0 + chunk);
+  float acc = 0.f;
+  if (c < C)
+    for (long j = j0 + threadIdx.y; j < j1; j += 8) {
+      long rep = j / P, pp = j % P;
+      long r = (rep * Ns + ns) * P + pp;
+      acc += ldf(a + r * C + c) * (b ? ldf(b + r * C + c) : 1.f);
+    }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(out + (long)ns * C + c, t);
+  }
+}
+int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int dtype, cudaStream_t st) {
+  long N = R / P;
+  long rows_per_out = (N / Ns) * P;
+  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Ns * C, st);
+  int base = gg_cdiv(C, 32) * Ns, splits = 1;
+  while (base * splits < 148 * 4 && rows_per_out / (splits * 2) >= 64) splits *= 2;
+  dim3 grid(gg_cdiv(C, 32), Ns, splits), block(32, 8);
+  GG_DISPATCH(dtype, (dot_sc_kernel<T><<<grid, block, 0, st>>>((const T*)a, (const T*)b, out, C, P, Ns, rows_per_out, splits)));
+  return gg_check_launch("dot_sc");
+}
+
+// ------------------------------------------------------------------ row softmax (one CTA per row)
+template <typename T>
+__global__ void softmax_rows_kernel(const T* __restrict__ s, T* __restrict__ p, int C) {
+  __shared__ float red[32];
+  long r = blockIdx.x;
+  const T* sr = s + r * C;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, ldf(sr + c));
+  m = warp_max(m);
+  if (lane == 0) red[wid] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sum += __expf(ldf(sr + c) - m);
+  sum = warp_sum(sum);
+  if (lane == 0) red[wid] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) stf(p + r * C + c, __expf(ldf(sr + c) - m) * inv);
+}
+int ggi_softmax_rows(const void* s, void* p, long R, int C, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (softmax_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)s, (T*)p, C)));
+  return gg_check_launch("softmax_rows");
+}
+
+// ------------------------------------------------------------------ separable sparse resampling (NHWC)
+// y[n,oy,ox,c] = sum_{a<Ty} sum_{b<Tx} wy[oy,a] wx[ox,b] x[n, iy[oy,a], ix[ox,b], c]
+template <typename T>
+__global__ void resample_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
+                                const int* __restrict__ iy, const float* __restrict__ wy, int Ty,
+                                const int* __restrict__ ix, const float* __restrict__ wx, int Tx) {
+  long n = (long)N * OH * OW * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long t = i / C;
+    int ox = (int)(t % OW); t /= OW;
+    int oy = (int)(t % OH);
+    int b = (int)(t / OH);
+    float acc = 0.f;
+    for (int a = 0; a < Ty; ++a) {
+      float wa = wy[oy * Ty + a];
+      if (wa == 0.f) continue;
+      const T* row = x + ((long)b * H + iy[oy * Ty + a]) * W * C + c;
+      float racc = 0.f;
+      for (int q = 0; q < Tx; ++q) {
+        float wq = wx[ox * Tx + q];
+        if (wq != 0.f) racc += wq * ldf(row + (long)ix[ox * Tx + q] * C);
+      }
+      acc += wa * racc;
+    }
+    stf(y + i, acc);
+  }
+}
+int ggi_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
+                  int Ty, const int* ix, const float* wx, int Tx, int dtype, cudaStream_t st) {
+  long n = (long)N * OH * OW * C;
+  GG_DISPATCH(dtype, (resample_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+  return gg_check_launch("resample2d");
+}
+
+// ------------------------------------------------------------------ layout: NCHW fp32 <-> NHWC T (channel pad)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int HW, int Cp) {
+  long n = (long)N * HW * Cp;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    long t = i / Cp;
+    int p = (int)(t % HW);
+    int b = (int)(t / HW);
+    stf(dst + i, c < C ? src[((long)b * C + c) * HW + p] : 0.f);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int N, int C, int HW, int Cp) {
+  long n = (long)N * C * HW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int p = (int)(i % HW);
+    long t = i / HW;
+    int c = (int)(t % C);
+    int b = (int)(t / C);
+    dst[i] = ldf(src + ((long)b * HW + p) * Cp + c);
+  }
+}
+int ggi_nchw_to_nhwc(const float* src, void* dst, int N, int C, int HW, int Cp, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (nchw_to_nhwc_kernel<T><<<gg_blocks((long)N * HW * Cp, 256), 256, 0, st>>>(src, (T*)dst, N, C, HW, Cp)));
+  return gg_check_launch("nchw_to_nhwc");
+}
+int ggi_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, int Cp, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (nhwc_to_nchw_kernel<T><<<gg_blocks((long)N * C * HW, 256), 256, 0, st>>>((const T*)src, dst, N, C, HW, Cp)));
+  return gg_check_launch("nhwc_to_nchw");
+}
+
+// ------------------------------------------------------------------ Noise + LeakyReLU (generator)
+// y = lrelu(x + wn[c] * noise[n,pixel])   x,y: [R=N*HW, C]; noise fp32 [R]; wn fp32 [C]
+template <typename T>
+__global__ void noise_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ noise,
+                                     const float* __restrict__ wn, T* __restrict__ y, long R, int C) {
+  long n = R * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    float v = ldf(x + i) + wn[i % C] * noise[i / C];
+    stf(y + i, v > 0.f ? v : 0.2f * v);
+  }
+}
+// dx = gy * lrelu'(y); dwn[c] += sum_r dx[r,c] * noise[r]
+template <typename T>
+__global__ void noise_act_bwd_kernel(const T* __restrict__ y, const T* __restrict__ gy,
+                                     const float* __restrict__ noise, T* __restrict__ dx, float* __restrict__ dwn,
+                                     long R, int C, int splits) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x;
+  long chunk = (R + splits - 1) / splits;
+  long r0 = blockIdx.y * chunk, r1 = min(R, r0 + chunk);
+  float acc = 0.f;
+  if (c < C)
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      float g = ldf(gy + r * C + c) * (ldf(y + r * C + c) > 0.f ? 1.f : 0.2f);
+      stf(dx + r * C + c, g);
+      acc += g * noise[r];
+    }
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    atomicAdd(dwn + c, t);
+  }
+}
+int ggi_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, long R, int C, int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (noise_act_fwd_kernel<T><<<gg_blocks(R * C, 256), 256, 0, st>>>((const T*)x, noise, wn, (T*)y, R, C)));
+  return gg_check_launch("noise_act_fwd");
+}
+int ggi_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, long R, int C, int dtype,
+                     cudaStream_t st) {
+  cudaMemsetAsync(dwn, 0, sizeof(float) * C, st);
+  int splits = 1;
+  while (gg_cdiv(C, 32) * splits < 148 * 4 && R / (splits * 2) >= 64) splits *= 2;
+  dim3 grid(gg_cdiv(C, 32), splits), block(32, 8);
+  GG_DISPATCH(dtype, (noise_act_bwd_kernel<T><<<grid, block, 0, st>>>((const T*)y, (const T*)gy, noise, (T*)dx, dwn, R, C, splits)));
+  return gg_check_launch("noise_act_bwd");
+}
+
+// ------------------------------------------------------------------ AdaptiveConv2DMod weight builder (K1)
+// bank [n][o][i][kk] fp32 (reference layout, kk = k*k); mod [B][I]; kmod [B][n] (null when n == 1)
+// out w [B][o][kk][i] (T, kernel layout), attn [B][n], dinv [B][o] (fp32 stats kept for backward)
+__global__ void adaconv_attn_kernel(const float* __restrict__ kmod, float* __restrict__ attn, int B, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (n == 1) { attn[b] = 1.f; return; }
+  float m = -INFINITY;
+  for (int j = 0; j < n; ++j) m = fmaxf(m, kmod[b * n + j]);
+  float s = 0.f;
+  for (int j = 0; j < n; ++j) s += expf(kmod[b * n + j] - m);
+  for (int j = 0; j < n; ++j) attn[b * n + j] = expf(kmod[b * n + j] - m) / s;
+}
+
+template <typename T>
+__global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+                                           const float* __restrict__ attn, T* __restrict__ w,
+                                           float* __restrict__ dinv, int n, int O, int I, int KK, int demod, float eps) {
+  __shared__ float red[32];
+  int b = blockIdx.y, o = blockIdx.x;
+  int E = I * KK;
+  float ss = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int i = e / KK;
+    float v = 0.f;
+    for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
+    float u = v * (mod[(long)b * I + i] + 1.f);
+    ss += u * u;
+  }
+  float d = 1.f;
+  if (demod) {
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    d = rsqrtf(fmaxf(t, eps));
+  }
+  if (threadIdx.x == 0) dinv[(long)b * O + o] = d;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int i = e / KK, kk = e % KK;
+    float v = 0.f;
+    for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
+    float u = v * (mod[(long)b * I + i] + 1.f);
+    stf(w + (((long)b * O + o) * KK + kk) * I + i, u * d);
+  }
+}
+
+// backward: gw [B][o][kk][i] fp32 -> dbank (atomic), dmod [B][I] (atomic), gattn [B][n] (atomic)
+__global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+                                           const float* __restrict__ attn, const float* __restrict__ dinv,
+                                           const float* __restrict__ gw, float* __restrict__ dbank,
+                                           float* __restrict__ dmod, float* __restrict__ gattn, int n, int O, int I,
+                                           int KK, int demod, float eps) {
+  __shared__ float red[32];
+  __shared__ float ga_sm[8];
+  int b = blockIdx.y, o = blockIdx.x;
+  int E = I * KK;
+  float d = dinv[(long)b * O + o];
+  float q = 0.f;
+  bool clamped = false;
+  if (demod) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      int i = e / KK, kk = e % KK;
+      float v = 0.f;
+      for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
+      float u = v * (mod[(long)b * I + i] + 1.f);
+      q += gw[(((long)b * O + o) * KK + kk) * I + i] * u;
+    }
+    q = warp_sum(q);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    q = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) q += red[i];
+    clamped = d * d * eps >= 0.999999f;   // d == rsqrt(eps)  <=>  sum u^2 <= eps: inv-norm is constant
+  }
+  if (threadIdx.x < 8) ga_sm[threadIdx.x] = 0.f;
+  __syncthreads();
+  float ga[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    int i = e / KK, kk = e % KK;
+    float v = 0.f;
+    for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
+    float s = mod[(long)b * I + i] + 1.f;
+    float u = v * s;
+    float g = gw[(((long)b * O + o) * KK + kk) * I + i];
+    float gu = d * g;
+    if (demod && !clamped) gu -= d * d * d * u * q;
+    atomicAdd(dmod + (long)b * I + i, gu * v);
+    float gv = gu * s;
+    for (int j = 0; j < n; ++j) {
+      atomicAdd(dbank + ((long)j * O + o) * E + e, attn[b * n + j] * gv);
+      ga[j] += gv * bank[((long)j * O + o) * E + e];
+    }
+  }
+  for (int j = 0; j < n; ++j) {
+    float t = warp_sum(ga[j]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&ga_sm[j], t);
+  }
+  __syncthreads();
+  if (threadIdx.x < n) atomicAdd(gattn + b * n + threadIdx.x, ga_sm[threadIdx.x]);
+}
+
+// dkmod = attn * (gattn - sum_j attn_j gattn_j)
+__global__ void adaconv_kmod_bwd_kernel(const float* __restrict__ attn, const float* __restrict__ gattn,
+                                        float* __restrict__ dkmod, int B, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float dot = 0.f;
+  for (int j = 0; j < n; ++j) dot += attn[b * n + j] * gattn[b * n + j];
+  for (int j = 0; j < n; ++j) dkmod[b * n + j] = attn[b * n + j] * (gattn[b * n + j] - dot);
+}
+
+int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
+                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, cudaStream_t st) {
+  if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
+  adaconv_attn_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(kmod, attn, B, n);
+  dim3 grid(O, B);
+  GG_DISPATCH(dtype, (adaconv_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(bank, mod, attn, (T*)w, dinv, n, O, I, KK, demod, eps)));
+  return gg_check_launch("adaconv_weights_fwd");
+}
+int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
+                           float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
+                           int demod, float eps, cudaStream_t st) {
+  cudaMemsetAsync(dbank, 0, sizeof(float) * (size_t)n * O * I * KK, st);
+  cudaMemsetAsync(dmod, 0, sizeof(float) * (size_t)B * I, st);
+  cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, st);
+  dim3 grid(O, B);
+  adaconv_weights_bwd_kernel<<<grid, 256, 0, st>>>(bank, mod, attn, dinv, gw, dbank, dmod, gattn_ws, n, O, I, KK, demod, eps);
+  if (n > 1 && dkmod) adaconv_kmod_bwd_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(attn, gattn_ws, dkmod, B, n);
+  return gg_check_launch("adaconv_weights_bwd");
+}
+
+// ------------------------------------------------------------------ AdamW over a flat fp32 buffer
+// chunk table: int4 {offset_lo, len, wd_flag, offset_hi}; one CTA per chunk.  step_ptr holds the 1-based step.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, const int4* __restrict__ chunks, const int* __restrict__ step_ptr,
+                             float lr, float b1, float b2, float eps, float wd, float grad_scale) {
+  int4 ch = chunks[blockIdx.x];
+  long off = ((long)ch.w << 31) | (unsigned)ch.x;
+  int step = *step_ptr;
+  float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  float decay = ch.z ? 1.f - lr * wd : 1.f;
+  float inv_sqrt_bc2 = rsqrtf(bc2), step_size = lr / bc1;
+  for (int i = threadIdx.x; i < ch.y; i += blockDim.x) {
+    long j = off + i;
+    float gi = g[j] * grad_scale, pi = p[j] * decay;
+    float mi = m[j] + (1.f - b1) * (gi - m[j]);
+    float vi = b2 * v[j] + (1.f - b2) * gi * gi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    p[j] = pi - step_size * (mi / denom);
+    m[j] = mi; v[j] = vi;
+  }
+}
+int ggi_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr,
+             float lr, float b1, float b2, float eps, float wd, float grad_scale, cudaStream_t st) {
+  adamw_kernel<<<nchunks, 256, 0, st>>>(p, g, m, v, (const int4*)chunks, step_ptr, lr, b1, b2, eps, wd, grad_scale);
+  return gg_check_launch("adamw");
+}
+__global__ void incr_kernel(int* p) { *p += 1; }
+int ggi_incr(int* p, cudaStream_t st) { incr_kernel<<<1, 1, 0, st>>>(p); return gg_check_launch("incr"); }

@@ -1,0 +1,617 @@
+"""Drop-in GigaGAN modules: same constructor keywords, parameter names/shapes/creation order (so state_dicts and
+seeded initialisation match lucidrains/gigagan-pytorch @ 0806433f), forward passes computed by the sm_100a kernels
+behind ``ops``.  Reference: gigagan_pytorch/gigagan_pytorch.py (line numbers cited per class).
+
+Internally feature maps are NHWC in the compute dtype; the public ``forward`` of every class takes and returns the
+reference's NCHW fp32 tensors.  ``forward_nhwc`` is the layout-preserving entry the trainer uses.
+"""
+from __future__ import annotations
+
+import math
+from functools import partial
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .ops import U_GELU, U_INVNORM, U_SIGMOID, U_SILU
+
+_COMPUTE = {"dtype": torch.float32, "fused_attention": True}
+
+
+def set_compute_dtype(dtype):
+    """fp32 (FFMA kernels, 1e-5 parity) or bf16 (tcgen05 where dense) for all modules created/run afterwards."""
+    assert dtype in (torch.float32, torch.bfloat16)
+    _COMPUTE["dtype"] = dtype
+
+
+def compute_dtype():
+    return _COMPUTE["dtype"]
+
+
+def exists(v):
+    return v is not None
+
+
+def is_power_of_two(n):
+    return math.log2(n).is_integer()
+
+
+def img_cpad(c):
+    return c
+
+
+# ----------------------------------------------------------------------------- small functional blocks (NHWC)
+def channel_rmsnorm(x, gamma):
+    """ref :224-232.  x NHWC; gamma (C,1,1)."""
+    c = x.shape[-1]
+    ss = ops.rowdot(x, x)
+    inv = ops.unary(U_INVNORM, ss)
+    y = ops.scale_rows(x, inv)
+    g = ops.axpby(c ** 0.5, gamma.reshape(1, c))
+    return ops.scale_channels(y, g, x.numel() // c, 1)
+
+
+def squeeze_excite(seq, x):
+    """ref :297-307 -> fp32 (N, C_out) gates."""
+    h = ops.mean_hw(x)
+    h = ops.linear(h, seq[1].weight, seq[1].bias)
+    h = ops.unary(U_SILU, h)
+    h = ops.linear(h, seq[3].weight, seq[3].bias)
+    return ops.unary(U_SIGMOID, h)
+
+
+def apply_excite(x, gates):
+    n, h, w, c = x.shape
+    return ops.scale_channels(x, gates, h * w, gates.shape[0])
+
+
+def SqueezeExciteParams(dim, dim_out, reduction=4, dim_min=32):
+    dim_hidden = max(dim_out // reduction, dim_min)
+    return nn.Sequential(nn.Identity(), nn.Linear(dim, dim_hidden), nn.SiLU(), nn.Linear(dim_hidden, dim_out),
+                         nn.Sigmoid(), nn.Identity())
+
+
+class Blur(nn.Module):
+    """Parameter-less; keeps the reference's ``f`` buffer for state_dict compatibility (ref :246-255)."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("f", torch.Tensor([1, 2, 1]))
+
+
+def UpsampleParams(*_):
+    return nn.Sequential(nn.Identity(), Blur())
+
+
+class ChannelRMSNorm(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(dim, 1, 1))
+
+    def forward_nhwc(self, x):
+        return channel_rmsnorm(x, self.gamma)
+
+
+# ----------------------------------------------------------------------------- AdaptiveConv2DMod (ref :315-409)
+class AdaptiveConv2DMod(nn.Module):
+    def __init__(self, dim, dim_out, kernel, *, demod=True, stride=1, dilation=1, eps=1e-8, num_conv_kernels=1):
+        super().__init__()
+        assert stride == 1 and dilation == 1, "the training hot path only uses stride 1 / dilation 1"
+        self.eps, self.dim_out, self.kernel = eps, dim_out, kernel
+        self.stride, self.dilation = stride, dilation
+        self.adaptive = num_conv_kernels > 1
+        self.weights = nn.Parameter(torch.randn((num_conv_kernels, dim_out, dim, kernel, kernel)))
+        self.demod = demod
+        nn.init.kaiming_normal_(self.weights, a=0, mode="fan_in", nonlinearity="leaky_relu")
+
+    def forward_nhwc(self, x, mod, kernel_mod=None):
+        b = x.shape[0]
+        if mod.shape[0] != b:                       # scale-major repeat, ref :365-366
+            mod = mod.repeat(b // mod.shape[0], 1)
+        if self.adaptive:
+            assert exists(kernel_mod) and kernel_mod.numel() > 0
+            if kernel_mod.shape[0] != b:
+                kernel_mod = kernel_mod.repeat(b // kernel_mod.shape[0], 1)
+        else:
+            assert not exists(kernel_mod) or kernel_mod.numel() == 0
+            kernel_mod = None
+        w = ops.AdaConvWeightsFn.apply(self.weights, mod, kernel_mod, self.demod, self.eps, x.dtype)
+        return ops.conv2d_prepared(x, w, pad=(self.kernel - 1) // 2, per_sample=True)
+
+    def forward(self, fmap, mod, kernel_mod=None):
+        x = ops.to_nhwc(fmap, fmap.shape[1], compute_dtype())
+        y = self.forward_nhwc(x, mod.float(), kernel_mod)
+        return ops.to_nchw(y, self.dim_out)
+
+
+# ----------------------------------------------------------------------------- attention (ref :513-594, :726-760)
+class SelfAttention(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, dot_product=False):
+        super().__init__()
+        self.heads, self.dim_head = heads, dim_head
+        self.scale = dim_head ** -0.5
+        dim_inner = dim_head * heads
+        self.dot_product = dot_product
+        self.norm = ChannelRMSNorm(dim)
+        self.to_q = nn.Conv2d(dim, dim_inner, 1, bias=False)
+        self.to_k = nn.Conv2d(dim, dim_inner, 1, bias=False) if dot_product else None
+        self.to_v = nn.Conv2d(dim, dim_inner, 1, bias=False)
+        self.null_kv = nn.Parameter(torch.randn(2, heads, dim_head))
+        self.to_out = nn.Conv2d(dim_inner, dim, 1, bias=False)
+
+    def forward_nhwc(self, x, residual=None, fused=None):
+        n, hh, ww, _ = x.shape
+        seq, heads, d = hh * ww, self.heads, self.dim_head
+        fused = _COMPUTE["fused_attention"] if fused is None else fused
+        xn = self.norm.forward_nhwc(x)
+        q = ops.conv2d(xn, self.to_q.weight)
+        v = ops.conv2d(xn, self.to_v.weight)
+        k = ops.conv2d(xn, self.to_k.weight) if exists(self.to_k) else q
+        if fused:
+            qv = q.view(n, seq, heads * d)
+            kv = k.view(n, seq, heads * d) if exists(self.to_k) else qv
+            o = ops.fused_attention(qv, kv, v.view(n, seq, heads * d), self.null_kv, heads, self.scale,
+                                    l2=not self.dot_product)
+            o = o.view(n, hh, ww, heads * d)
+        else:
+            o = self._composed(q, k, v, n, seq, heads, d).reshape(n, hh, ww, heads * d)
+        return ops.conv2d(o, self.to_out.weight, res=residual)
+
+    def _composed(self, q, k, v, n, seq, heads, d):
+        """Attention from closed-under-differentiation primitives (used inside the gradient penalty)."""
+        nk = self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d)
+        nv = self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d)
+        kf = torch.cat((nk, k.view(n, seq, heads, d)), dim=1)            # (n, seq+1, heads, d)
+        vf = torch.cat((nv, v.view(n, seq, heads, d)), dim=1)
+        q4 = q.view(n, seq, heads, d).permute(0, 2, 1, 3)                  # (n, heads, seq, d) view
+        kt = kf.permute(0, 2, 3, 1)                                        # (n, heads, d, seq+1) view
+        if self.dot_product:
+            s = ops.bmm(q4, kt, alpha=self.scale)
+        else:   # -|q-k|^2 * scale  ==  (2 q.k - |k|^2) * scale  up to a per-row constant (softmax-invariant)
+            s = ops.bmm(q4, kt, alpha=2.0 * self.scale)
+            ksq = ops.rowdot(kf, kf)                                        # (n, seq+1, heads) fp32
+            bias = ops.axpby(-self.scale, ksq.permute(0, 2, 1).contiguous())
+            s = ops.add_channels(s, bias.reshape(n * heads, seq + 1), seq, n * heads)
+        p = ops.softmax(s)
+        o = ops.bmm(p, vf.permute(0, 2, 1, 3), out_bmhn=True)             # physical (n, seq, heads, d)
+        return o.permute(0, 2, 1, 3)
+
+    def forward(self, fmap):
+        x = ops.to_nhwc(fmap, fmap.shape[1], compute_dtype())
+        return ops.to_nchw(self.forward_nhwc(x), fmap.shape[1])
+
+
+def FeedForwardParams(dim, mult=4):
+    dim_hidden = int(dim * mult)
+    return nn.Sequential(ChannelRMSNorm(dim), nn.Conv2d(dim, dim_hidden, 1), nn.GELU(), nn.Conv2d(dim_hidden, dim, 1))
+
+
+class SelfAttentionBlock(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, ff_mult=4, dot_product=False):
+        super().__init__()
+        self.attn = SelfAttention(dim=dim, dim_head=dim_head, heads=heads, dot_product=dot_product)
+        self.ff = FeedForwardParams(dim, ff_mult)
+
+    def forward_nhwc(self, x, fused=None):
+        x = self.attn.forward_nhwc(x, residual=x, fused=fused)
+        h = self.ff[0].forward_nhwc(x)
+        h = ops.conv2d(h, self.ff[1].weight, self.ff[1].bias)
+        h = ops.unary(U_GELU, h)
+        return ops.conv2d(h, self.ff[3].weight, self.ff[3].bias, res=x)
+
+    def forward(self, fmap):
+        x = ops.to_nhwc(fmap, fmap.shape[1], compute_dtype())
+        return ops.to_nchw(self.forward_nhwc(x), fmap.shape[1])
+
+
+# ----------------------------------------------------------------------------- style network (ref :871-921)
+class EqualLinear(nn.Module):
+    def __init__(self, dim, dim_out, lr_mul=1, bias=True):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(dim_out, dim))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(dim_out))
+        self.lr_mul = lr_mul
+
+
+class StyleNetwork(nn.Module):
+    def __init__(self, dim, depth, lr_mul=0.1, dim_text_latent=0):
+        super().__init__()
+        self.dim, self.dim_text_latent = dim, dim_text_latent
+        layers = []
+        for i in range(depth):
+            dim_in = (dim + dim_text_latent) if i == 0 else dim
+            layers.extend([EqualLinear(dim_in, dim, lr_mul), nn.LeakyReLU(0.2)])
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x, text_latent=None):
+        x = x.float()
+        inv = ops.unary(U_INVNORM, ops.rowdot(x, x))
+        x = ops.scale_rows(x, inv)
+        if self.dim_text_latent > 0:
+            assert exists(text_latent)
+            x = torch.cat((x, text_latent.float()), dim=-1)
+        for m in self.net:
+            if isinstance(m, EqualLinear):
+                x = ops.leaky_relu(ops.linear(x, m.weight, ops.axpby(m.lr_mul, m.bias), alpha=m.lr_mul))
+        return x
+
+
+class Noise(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(dim, 1, 1))
+
+
+# ----------------------------------------------------------------------------- generator (ref :947-1250)
+class BaseGenerator(nn.Module):
+    pass
+
+
+class Generator(BaseGenerator):
+    def __init__(self, *, image_size, dim_capacity=16, dim_max=2048, channels=3,
+                 style_network: StyleNetwork | Dict | None = None, style_network_dim=None, text_encoder=None,
+                 dim_latent=512, self_attn_resolutions: Tuple[int, ...] = (32, 16), self_attn_dim_head=64,
+                 self_attn_heads=8, self_attn_dot_product=True, self_attn_ff_mult=4,
+                 cross_attn_resolutions: Tuple[int, ...] = (32, 16), cross_attn_dim_head=64, cross_attn_heads=8,
+                 cross_attn_ff_mult=4, num_conv_kernels=2, num_skip_layers_excite=0, unconditional=False,
+                 pixel_shuffle_upsample=False):
+        super().__init__()
+        assert unconditional and text_encoder is None, \
+            "this build covers the unconditional training path (text conditioning: SURVEY.md 8f item 2)"
+        assert not pixel_shuffle_upsample, "pixel_shuffle_upsample is outside the hot path"
+        self.channels = channels
+        if isinstance(style_network, dict):
+            style_network = StyleNetwork(**style_network)
+        self.style_network = style_network
+        assert exists(style_network) ^ exists(style_network_dim)
+        if not exists(style_network_dim):
+            style_network_dim = style_network.dim
+        self.style_network_dim = style_network_dim
+        self.text_encoder = None
+        self.unconditional = unconditional
+        assert is_power_of_two(image_size)
+        num_layers = int(math.log2(image_size) - 1)
+        self.num_layers = num_layers
+        self.image_size = image_size
+
+        is_adaptive = num_conv_kernels > 1
+        dim_kernel_mod = num_conv_kernels if is_adaptive else 0
+        split = []
+        adaptive_conv = partial(AdaptiveConv2DMod, kernel=3, num_conv_kernels=num_conv_kernels)
+
+        self.init_block = nn.Parameter(torch.randn(dim_latent, 4, 4))
+        self.init_conv = adaptive_conv(dim_latent, dim_latent)
+        split.extend([dim_latent, dim_kernel_mod])
+
+        resolutions = [image_size // (2 ** (num_layers - 1 - i)) for i in range(num_layers)]
+        dims = [min((2 ** (i + 1)) * dim_capacity, dim_max) for i in range(num_layers)][::-1]
+        dims = [dim_latent] + dims
+        dim_pairs = list(zip(dims[:-1], dims[1:]))
+        self.num_skip_layers_excite = num_skip_layers_excite
+        self.layers = nn.ModuleList([])
+        for ind, ((dim_in, dim_out), resolution) in enumerate(zip(dim_pairs, resolutions)):
+            is_last, is_first = (ind + 1) == len(dim_pairs), ind == 0
+            se = None
+            if num_skip_layers_excite > 0 and (ind + num_skip_layers_excite) < len(dim_pairs):
+                se = SqueezeExciteParams(dim_in, dim_pairs[ind + num_skip_layers_excite][0])
+            resnet_block = nn.ModuleList([adaptive_conv(dim_in, dim_out), Noise(dim_out), nn.LeakyReLU(0.2),
+                                          adaptive_conv(dim_out, dim_out), Noise(dim_out), nn.LeakyReLU(0.2)])
+            to_rgb = AdaptiveConv2DMod(dim_out, channels, 1, num_conv_kernels=1, demod=False)
+            upsample = UpsampleParams(dim_in) if not is_first else None
+            rgb_upsample = UpsampleParams(channels) if not is_last else None
+            self_attn = None
+            if resolution in self_attn_resolutions:
+                self_attn = SelfAttentionBlock(dim_out, dim_head=self_attn_dim_head, heads=self_attn_heads,
+                                               ff_mult=self_attn_ff_mult, dot_product=self_attn_dot_product)
+            split.extend([dim_in, dim_kernel_mod, dim_out, dim_kernel_mod, dim_out, 0])
+            self.layers.append(nn.ModuleList([se, resnet_block, to_rgb, self_attn, None, upsample, rgb_upsample]))
+
+        self.style_to_conv_modulations = nn.Linear(style_network_dim, sum(split))
+        self.style_embed_split_dims = split
+        self.apply(self.init_)
+        nn.init.normal_(self.init_block, std=0.02)
+
+    def init_(self, m):
+        if type(m) in {nn.Conv2d, nn.Linear}:
+            nn.init.kaiming_normal_(m.weight, a=0, mode="fan_in", nonlinearity="leaky_relu")
+
+    @property
+    def total_params(self):
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def forward_nhwc(self, styles=None, noise=None, batch_size=1, layer_noises=None):
+        """-> (rgb NHWC, [rgbs NHWC]) in the compute dtype.  Per-layer noise images are drawn with torch.randn in
+        the reference's order (ref :938) unless ``layer_noises`` supplies them."""
+        dt = compute_dtype()
+        if not exists(styles):
+            assert exists(self.style_network)
+            if not exists(noise):
+                noise = torch.randn((batch_size, self.style_network_dim), device=self.device)
+            styles = self.style_network(noise)
+        mods = ops.linear(styles.float(), self.style_to_conv_modulations.weight, self.style_to_conv_modulations.bias)
+        mods = iter(mods.split(self.style_embed_split_dims, dim=-1))
+        b = styles.shape[0]
+        x = self.init_block.permute(1, 2, 0)[None].expand(b, -1, -1, -1).to(dt).contiguous()
+        x = self.init_conv.forward_nhwc(x, next(mods), next(mods))
+        rgb = None
+        excitations = [None] * self.num_skip_layers_excite
+        rgbs = []
+        ln = list(layer_noises) if layer_noises is not None else None
+
+        def noise_img(t):
+            if ln is not None:
+                return ln.pop(0)
+            return torch.randn(t.shape[0], 1, t.shape[1], t.shape[2], device=t.device)
+
+        for se, (conv1, noise1, _, conv2, noise2, _), to_rgb, self_attn, _, upsample, upsample_rgb in self.layers:
+            if exists(upsample):
+                x = ops.upsample2x_blur(x)
+            if exists(se):
+                excitations.append(squeeze_excite(se, x))
+            ex = excitations.pop(0) if excitations else None
+            if exists(ex):
+                x = apply_excite(x, ex)
+            x = conv1.forward_nhwc(x, next(mods), next(mods))
+            x = ops.NoiseActFn.apply(x, noise_img(x), noise1.weight)
+            x = conv2.forward_nhwc(x, next(mods), next(mods))
+            x = ops.NoiseActFn.apply(x, noise_img(x), noise2.weight)
+            if exists(self_attn):
+                x = self_attn.forward_nhwc(x)
+            layer_rgb = to_rgb.forward_nhwc(x, next(mods), next(mods))
+            rgb = layer_rgb if rgb is None else ops.add(rgb, layer_rgb)
+            rgbs.append(rgb)
+            if exists(upsample_rgb):
+                rgb = ops.upsample2x_blur(rgb)
+        assert next(mods, None) is None, "convolutions were incorrectly modulated"
+        return rgb, rgbs
+
+    def forward(self, styles=None, noise=None, texts=None, text_encodings=None, global_text_tokens=None,
+                fine_text_tokens=None, text_mask=None, batch_size=1, return_all_rgbs=False):
+        assert not any(map(exists, (texts, text_encodings, global_text_tokens, fine_text_tokens)))
+        rgb, rgbs = self.forward_nhwc(styles, noise, batch_size)
+        rgb = ops.to_nchw(rgb, self.channels)
+        if return_all_rgbs:
+            return rgb, [ops.to_nchw(t, self.channels) for t in rgbs]
+        return rgb
+
+
+# ----------------------------------------------------------------------------- discriminator (ref :1254-1838)
+class SimpleDecoder(nn.Module):
+    def __init__(self, dim, *, dims: Tuple[int, ...], patch_dim: int = 1, frac_patches: float = 1.,
+                 dropout: float = 0.5):
+        super().__init__()
+        assert 0 < frac_patches <= 1.
+        self.patch_dim, self.frac_patches = patch_dim, frac_patches
+        self.dropout = nn.Dropout(dropout)
+        dims = [dim, *dims]
+        layers = [nn.Conv2d(dim, dim, 3, padding=1)]
+        for dim_in, dim_out in zip(dims[:-1], dims[1:]):
+            layers.append(nn.Sequential(UpsampleParams(dim_in), nn.Conv2d(dim_in, dim_out, 3, padding=1),
+                                        nn.LeakyReLU(0.2)))
+        self.net = nn.Sequential(*layers)
+
+    def forward_nhwc(self, fmap, image_nhwc):
+        """fmap (B,h,w,C) compute dtype; image_nhwc (B,H,W,3).  RNG draws mirror ref :1295,:1310 (dropout on the
+        NCHW-shaped map on device, patch permutation from a CPU randn)."""
+        b, h, w, c = fmap.shape
+        if self.training and self.dropout.p > 0:
+            keep = F.dropout(torch.ones((b, c, h, w), device=fmap.device), self.dropout.p, True)
+            fmap = ops.mul(fmap, ops.to_nhwc(keep, c, fmap.dtype))
+        if self.frac_patches < 1.:
+            pd = self.patch_dim
+            total = pd * pd
+            nsel = max(int(self.frac_patches * total), 1)
+            perm = torch.randn((b, total)).sort(dim=-1).indices[:, :nsel]          # CPU, like the reference
+            onehot = torch.zeros((nsel, b, total))
+            onehot.scatter_(2, perm.t()[..., None], 1.0)
+            onehot = onehot.to(fmap.device, non_blocking=True)
+
+            def pick(t):   # '(b p) ...' selection as a one-hot weighted sum of the p1 x p2 sub-blocks
+                hh, ww = t.shape[1] // pd, t.shape[2] // pd
+                outs = []
+                for s in range(nsel):
+                    acc = None
+                    for pi in range(total):
+                        py, px = pi // pd, pi % pd
+                        blk = t[:, py * hh:(py + 1) * hh, px * ww:(px + 1) * ww, :]
+                        sel = onehot[s, :, pi].reshape(b, 1).expand(b, t.shape[-1]).contiguous()
+                        term = ops.scale_channels(blk, sel, hh * ww, b)
+                        acc = term if acc is None else ops.add(acc, term)
+                    outs.append(acc)
+                return outs[0] if nsel == 1 else torch.stack(outs, dim=1).flatten(0, 1)
+
+            fmap, image_nhwc = pick(fmap), pick(image_nhwc)
+        x = ops.conv2d(fmap, self.net[0].weight, self.net[0].bias, pad=1)
+        for blk in list(self.net)[1:]:
+            x = ops.upsample2x_blur(x)
+            x = ops.conv2d(x, blk[1].weight, blk[1].bias, pad=1, act=1)
+        d = ops.axpby(1.0, x, -1.0, image_nhwc)
+        return ops.axpby(1.0 / d.numel(), ops.sum_all(ops.mul(d, d)))
+
+
+class Predictor(nn.Module):
+    def __init__(self, dim, depth=4, num_conv_kernels=2, unconditional=False):
+        super().__init__()
+        assert unconditional, "text-conditioned predictors are outside this build (SURVEY.md 8f item 2)"
+        self.unconditional = unconditional
+        self.residual_fn = nn.Conv2d(dim, dim, 1)
+        self.residual_scale = 2 ** -0.5
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([nn.Conv2d(dim, dim, 3, padding=1), nn.LeakyReLU(0.2),
+                                              nn.Conv2d(dim, dim, 3, padding=1), nn.LeakyReLU(0.2)]))
+        self.to_logits = nn.Conv2d(dim, 1, 1)
+
+    def forward_nhwc(self, x):
+        residual = ops.conv2d(x, self.residual_fn.weight, self.residual_fn.bias)
+        for conv1, _, conv2, _ in self.layers:
+            inner = x
+            x = ops.conv2d(x, conv1.weight, conv1.bias, pad=1, act=1)
+            x = ops.conv2d(x, conv2.weight, conv2.bias, pad=1, act=1)
+            x = ops.axpby(self.residual_scale, x, self.residual_scale, inner)
+        x = ops.add(x, residual)
+        return ops.conv2d(x, self.to_logits.weight, self.to_logits.bias)
+
+
+def DownsampleParams(dim):
+    return nn.Sequential(nn.Identity(), nn.Conv2d(dim * 4, dim, 1))
+
+
+class Discriminator(nn.Module):
+    def __init__(self, *, dim_capacity=16, image_size, dim_max=2048, channels=3,
+                 attn_resolutions: Tuple[int, ...] = (32, 16), attn_dim_head=64, attn_heads=8,
+                 self_attn_dot_product=False, ff_mult=4, text_encoder=None, text_dim=None,
+                 filter_input_resolutions: bool = True,
+                 multiscale_input_resolutions: Tuple[int, ...] = (64, 32, 16, 8),
+                 multiscale_output_skip_stages: int = 1, aux_recon_resolutions: Tuple[int, ...] = (8,),
+                 aux_recon_patch_dims: Tuple[int, ...] = (2,), aux_recon_frac_patches: Tuple[float, ...] = (0.25,),
+                 aux_recon_fmap_dropout: float = 0.5, resize_mode="bilinear", num_conv_kernels=2,
+                 num_skip_layers_excite=0, unconditional=False, predictor_depth=2):
+        super().__init__()
+        assert unconditional and text_encoder is None, \
+            "this build covers the unconditional training path (text conditioning: SURVEY.md 8f item 2)"
+        assert resize_mode == "bilinear"
+        self.unconditional = unconditional
+        self.channels = channels
+        assert is_power_of_two(image_size)
+        if filter_input_resolutions:
+            multiscale_input_resolutions = [r for r in multiscale_input_resolutions if r < image_size]
+        assert len(set(multiscale_input_resolutions)) == len(multiscale_input_resolutions)
+        assert all(is_power_of_two(r) and r < image_size for r in multiscale_input_resolutions)
+        self.multiscale_input_resolutions = list(multiscale_input_resolutions)
+        assert multiscale_output_skip_stages > 0
+        ms_out = [r // (2 ** multiscale_output_skip_stages) for r in multiscale_input_resolutions]
+        assert all(r >= 4 for r in ms_out)
+        self.multiscale_output_resolutions = ms_out
+        assert len(aux_recon_resolutions) == len(aux_recon_patch_dims) == len(aux_recon_frac_patches)
+        self.aux_recon_resolutions_to_patches = dict(zip(aux_recon_resolutions,
+                                                         zip(aux_recon_patch_dims, aux_recon_frac_patches)))
+        self.resize_mode = resize_mode
+        num_layers = int(math.log2(image_size) - 1)
+        self.num_layers, self.image_size = num_layers, image_size
+        resolutions = [image_size // (2 ** i) for i in range(num_layers)]
+        dims = [min(d, dim_max) for d in [channels] + [(2 ** (i + 1)) * dim_capacity for i in range(num_layers)]]
+        dim_last = dims[-1]
+        dim_pairs = list(zip(dims[:-1], dims[1:]))
+        self.num_skip_layers_excite = num_skip_layers_excite
+        self.residual_scale = 2 ** -0.5
+        self.layers = nn.ModuleList([])
+        upsample_dims = []
+        for ind, ((dim_in, dim_out), resolution) in enumerate(zip(dim_pairs, resolutions)):
+            is_first, is_last = ind == 0, (ind + 1) == len(dim_pairs)
+            should_downsample = not is_last
+            upsample_dims.insert(0, dim_in)
+            se = None
+            if not is_first and num_skip_layers_excite > 0 and (ind + num_skip_layers_excite) < len(dim_pairs):
+                se = SqueezeExciteParams(dim_in, dim_pairs[ind + num_skip_layers_excite][0])
+            from_rgb = nn.Conv2d(channels, dim_in, 7, padding=3)
+            residual_conv = nn.Conv2d(dim_in, dim_out, 1, stride=(2 if should_downsample else 1))
+            resnet_block = nn.Sequential(nn.Conv2d(dim_in, dim_out, 3, padding=1), nn.LeakyReLU(0.2),
+                                         nn.Conv2d(dim_out, dim_out, 3, padding=1), nn.LeakyReLU(0.2))
+            predictor = None
+            if resolution in ms_out:
+                predictor = Predictor(dim_out, num_conv_kernels=num_conv_kernels, depth=2, unconditional=unconditional)
+            decoder = None
+            if resolution in aux_recon_resolutions:
+                patch_dim, frac = self.aux_recon_resolutions_to_patches[resolution]
+                decoder = SimpleDecoder(dim_out, dims=tuple(upsample_dims), patch_dim=patch_dim, frac_patches=frac,
+                                        dropout=aux_recon_fmap_dropout)
+            attn = None
+            if resolution in attn_resolutions:
+                attn = SelfAttentionBlock(dim_out, heads=attn_heads, dim_head=attn_dim_head, ff_mult=ff_mult,
+                                          dot_product=self_attn_dot_product)
+            self.layers.append(nn.ModuleList([se, from_rgb, resnet_block, residual_conv, attn, predictor, decoder,
+                                              DownsampleParams(dim_out) if should_downsample else None]))
+        self.to_logits = nn.Sequential(nn.Conv2d(dim_last, dim_last, 3, padding=1), nn.Identity(),
+                                       nn.Linear(dim_last * (4 ** 2), 1), nn.Identity())
+        self.text_encoder = None
+        self.apply(self.init_)
+
+    def init_(self, m):
+        if type(m) in {nn.Conv2d, nn.Linear}:
+            nn.init.kaiming_normal_(m.weight, a=0, mode="fan_in", nonlinearity="leaky_relu")
+
+    @property
+    def total_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    # -- reference :1683-1687: bilinear F.interpolate of NCHW images
+    def resize_image_to(self, images, resolution):
+        x = ops.to_nhwc(images, images.shape[1], torch.float32)
+        return ops.to_nchw(ops.resize_bilinear(x, resolution), images.shape[1])
+
+    def real_images_to_rgbs(self, images):
+        return [self.resize_image_to(images, r) for r in self.multiscale_input_resolutions]
+
+    def real_images_to_rgbs_nhwc(self, images_nhwc):
+        return [ops.resize_bilinear(images_nhwc, r) for r in self.multiscale_input_resolutions]
+
+    def forward_nhwc(self, images, rgbs: List[torch.Tensor], return_multiscale_outputs=True, calc_aux_loss=True,
+                     fused_attention=None):
+        """images (B,S,S,C) NHWC compute dtype; rgbs: NHWC maps.  -> (logits (s,B) fp32, [ms logits NHWC], [aux])."""
+        x = images
+        batch = x.shape[0]
+        assert x.shape[1] == x.shape[2] == self.image_size
+        by_res = {t.shape[2]: t for t in rgbs} if rgbs is not None else {}
+        missing = set(self.multiscale_input_resolutions) - set(by_res.keys())
+        assert not missing, f"rgbs of necessary resolution {self.multiscale_input_resolutions} were not passed in"
+        ms_outputs, aux_losses = [], []
+        excitations = [None] * (self.num_skip_layers_excite + 1)
+        for se, from_rgb, block, residual_fn, attn, predictor, decoder, downsample in self.layers:
+            resolution = x.shape[2]
+            if exists(se):
+                excitations.append(squeeze_excite(se, x))
+            ex = excitations.pop(0) if excitations else None
+            if exists(ex):
+                x = apply_excite(x, ex)
+            prev = x.shape[0]
+            if resolution in self.multiscale_input_resolutions:
+                rgb = by_res[resolution]
+                f = ops.conv2d(rgb, from_rgb.weight, from_rgb.bias, pad=3)
+                if x.shape[0] != f.shape[0]:
+                    f = f.repeat(x.shape[0] // f.shape[0], 1, 1, 1)
+                x = torch.cat((ops.add(x, f), f), dim=0)
+            stride = residual_fn.stride[0]
+            residual = ops.conv2d(x, residual_fn.weight, residual_fn.bias, stride=stride)
+            x = ops.conv2d(x, block[0].weight, block[0].bias, pad=1, act=1)
+            x = ops.conv2d(x, block[2].weight, block[2].bias, pad=1, act=1)
+            if exists(attn):
+                x = attn.forward_nhwc(x, fused=fused_attention)
+            if exists(predictor) and return_multiscale_outputs:
+                ms_outputs.append(predictor.forward_nhwc(x[:prev]))
+            if exists(downsample):     # pixel-unshuffle + 1x1 == 2x2 stride-2 conv (ref :289-293)
+                w = downsample[1].weight
+                w2 = w.view(w.shape[0], w.shape[1] // 4, 2, 2)
+                x = ops.conv2d(x, w2, downsample[1].bias, stride=2, res=residual, gain=self.residual_scale)
+            else:
+                x = ops.axpby(self.residual_scale, x, self.residual_scale, residual)
+            if exists(decoder) and calc_aux_loss:                 # ref :1812-1827 (post-downsample x, first B rows)
+                img3 = images if images.shape[-1] == self.channels else images[..., : self.channels].contiguous()
+                aux_losses.append(decoder.forward_nhwc(x[:batch], img3))
+        x = ops.conv2d(x, self.to_logits[0].weight, self.to_logits[0].bias, pad=1)
+        lw = self.to_logits[2].weight
+        logits = ops.conv2d(x, lw.view(1, x.shape[-1], 4, 4), self.to_logits[2].bias)      # flatten(c h w) @ W^T
+        logits = logits.float().reshape(-1, batch)
+        return logits, ms_outputs, aux_losses
+
+    def forward(self, images, rgbs: List[torch.Tensor], texts=None, text_encodings=None, text_embeds=None,
+                real_images=None, return_multiscale_outputs=True, calc_aux_loss=True):
+        assert not any(map(exists, (texts, text_encodings, text_embeds)))
+        dt = compute_dtype()
+        x = ops.to_nhwc(images, img_cpad(self.channels), dt)
+        r = [ops.to_nhwc(t, img_cpad(self.channels), dt) for t in rgbs]
+        logits, ms, aux = self.forward_nhwc(x, r, return_multiscale_outputs, calc_aux_loss)
+        return logits, [ops.to_nchw(m, 1) for m in ms], aux

@@ -1,0 +1,774 @@
+"""Differentiable operators over the C-ABI kernels (torch.autograd.Function wrappers).
+
+Design rule: the backward of every operator here is itself written with operators from this file (never raw
+kernels), so the graph built during a backward pass with ``create_graph=True`` is differentiable again.  That is
+what makes the discriminator's gradient penalty (reference gigagan_pytorch.py:120-155, a double backward through
+D) work on hand-written kernels.  Operators marked "first-order" (fused fast paths used outside the gradient
+penalty) are the only exception.
+
+Conventions: activations are NHWC tensors (N,H,W,C) in the compute dtype (fp32 or bf16); small statistic tensors
+(per-row / per-sample-channel) are fp32.  torch is used for memory only (allocation, views, cat/slice, casts).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ._lib import call
+
+U_LRELU, U_RELU, U_GELU, U_SILU, U_SIGMOID, U_INVNORM = range(6)
+ROWS, SAMPLE_CH = 0, 1
+MUL, ADD = 0, 1
+
+
+def _dt(t):
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _c(t):
+    if not t.is_cuda:
+        raise RuntimeError("gigagan_pytorch_b200 operators need CUDA tensors (there is no CPU path)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ============================================================================= convolution family
+class ConvGeom:
+    """Static description of one convolution (kernel size, stride, padding, fused epilogue)."""
+    __slots__ = ("kh", "kw", "stride", "pad", "per_sample", "act", "gain")
+
+    def __init__(self, kh, kw, stride=1, pad=0, per_sample=False, act=0, gain=1.0):
+        self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+        self.per_sample, self.act, self.gain = per_sample, act, gain
+
+    def out_hw(self, h, w):
+        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
+
+    def plain(self):
+        return ConvGeom(self.kh, self.kw, self.stride, self.pad, self.per_sample)
+
+
+def prep_weight(weight, cin, dtype):
+    """fp32 master (O,I,KH,KW) -> kernel layout (O,KH,KW,cin) in the compute dtype, zero-padding I up to cin."""
+    w = weight.detach().permute(0, 2, 3, 1)
+    if w.shape[-1] != cin:
+        w = torch.nn.functional.pad(w, (0, cin - w.shape[-1]))
+    return w.to(dtype).contiguous()
+
+
+def unprep_weight_grad(gk, like):
+    """kernel-layout fp32 gradient (O,KH,KW,cin) -> master layout (O,I,KH,KW)."""
+    return gk[..., : like.shape[1]].permute(0, 3, 1, 2).contiguous().to(like.dtype)
+
+
+def _conv_fprop_raw(x, wk, bias, res, g, out_c):
+    n, h, w, cin = x.shape
+    oh, ow = g.out_hw(h, w)
+    y = torch.empty((n, oh, ow, out_c), dtype=x.dtype, device=x.device)
+    call("gg_conv2d_fprop", _p(x), _p(wk), _p(bias), _p(res), _p(y), n, h, w, cin, oh, ow, out_c, g.kh, g.kw, g.stride,
+         g.pad, int(g.per_sample), g.act, float(g.gain), _dt(x), _st())
+    return y
+
+
+def _conv_dgrad_raw(gy, wk, g, in_shape):
+    n, h, w, cin = in_shape
+    _, oh, ow, cout = gy.shape
+    dx = torch.empty(in_shape, dtype=gy.dtype, device=gy.device)
+    call("gg_conv2d_dgrad", _p(gy), _p(wk), _p(dx), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
+         int(g.per_sample), _dt(gy), _st())
+    return dx
+
+
+def _conv_wgrad_raw(x, gy, g):
+    n, h, w, cin = x.shape
+    _, oh, ow, cout = gy.shape
+    shape = (n, cout, g.kh, g.kw, cin) if g.per_sample else (cout, g.kh, g.kw, cin)
+    dw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    call("gg_conv2d_wgrad", _p(x), _p(gy), _p(dw), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
+         int(g.per_sample), _dt(x), _st())
+    return dw
+
+
+class Conv2dFn(Function):
+    """y = (act(conv(x, W) + bias) + res) * gain.  ``weight`` is either the fp32 master (O,I,KH,KW) [master=True]
+    or an already prepared kernel-layout tensor ([N,]O,KH,KW,I) in x's dtype (per-sample AdaptiveConv weights)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, res, geom, master):
+        x = _c(x)
+        wk = prep_weight(weight, x.shape[-1], x.dtype) if master else _c(weight)
+        out_c = wk.shape[-4]
+        assert not (geom.act and (res is not None or geom.gain != 1.0)), "act and res/gain epilogues are exclusive"
+        y = _conv_fprop_raw(x, wk, bias, None if res is None else _c(res), geom, out_c)
+        ctx.geom, ctx.master, ctx.has_bias, ctx.has_res = geom, master, bias is not None, res is not None
+        ctx.save_for_backward(x, weight, y if geom.act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        g = ctx.geom
+        if g.gain != 1.0:
+            gy = axpby(g.gain, gy)
+        gres = gy if ctx.has_res else None
+        if g.act:
+            gy = Unary1Fn.apply(U_LRELU, y, gy)
+        gx = gw = gb = None
+        pg = g.plain()
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgradFn.apply(gy, weight, pg, tuple(x.shape), ctx.master)
+        if ctx.needs_input_grad[1] and not _skip_param_grads():
+            gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads():
+            gb = dot_sc(gy, None, gy.numel() // gy.shape[-1], 1).reshape(-1)
+        return gx, gw, gb, gres, None, None
+
+
+class ConvDgradFn(Function):
+    @staticmethod
+    def forward(ctx, gy, weight, geom, in_shape, master):
+        gy = _c(gy)
+        wk = prep_weight(weight, in_shape[-1], gy.dtype) if master else _c(weight)
+        ctx.geom, ctx.master = geom, master
+        ctx.save_for_backward(gy, weight)
+        return _conv_dgrad_raw(gy, wk, geom, in_shape)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        gy, weight = ctx.saved_tensors
+        g = ctx.geom
+        d_gy = d_w = None
+        if ctx.needs_input_grad[0]:
+            d_gy = Conv2dFn.apply(ggx, weight, None, None, g, ctx.master)
+        if ctx.needs_input_grad[1] and not _skip_param_grads():
+            d_w = ConvWgradFn.apply(ggx, gy, g, weight if ctx.master else None)
+        return d_gy, d_w, None, None, None
+
+
+class ConvWgradFn(Function):
+    """dW from (x, gy).  Returns master layout fp32 when ``like`` (the master weight) is given, else kernel layout
+    in x's dtype (per-sample prepared weights)."""
+
+    @staticmethod
+    def forward(ctx, x, gy, geom, like):
+        x, gy = _c(x), _c(gy)
+        ctx.geom, ctx.master = geom, like is not None
+        ctx.save_for_backward(x, gy)
+        ctx.like_shape = None if like is None else tuple(like.shape)
+        dw = _conv_wgrad_raw(x, gy, geom)
+        return unprep_weight_grad(dw, like) if like is not None else dw.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, gy = ctx.saved_tensors
+        g = ctx.geom
+        dx = dgy = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvDgradFn.apply(gy, ggw, g, tuple(x.shape), ctx.master)
+        if ctx.needs_input_grad[1]:
+            dgy = Conv2dFn.apply(x, ggw, None, None, g, ctx.master)
+        return dx, dgy, None, None
+
+
+_SKIP_PARAM_GRADS = [False]
+
+
+def _skip_param_grads():
+    return _SKIP_PARAM_GRADS[0]
+
+
+class skip_param_grads:
+    """Context: convolutions do not compute weight/bias gradients (used while taking d(outputs)/d(images) for the
+    gradient penalty, where autograd.grad only asks for the image gradient; ref gigagan_pytorch.py:138-145)."""
+
+    def __enter__(self):
+        self.prev = _SKIP_PARAM_GRADS[0]
+        _SKIP_PARAM_GRADS[0] = True
+
+    def __exit__(self, *a):
+        _SKIP_PARAM_GRADS[0] = self.prev
+
+
+def conv2d(x, weight, bias=None, *, stride=1, pad=0, act=0, res=None, gain=1.0):
+    """NHWC convolution with the fp32 master weight (O,I,KH,KW)."""
+    g = ConvGeom(weight.shape[2], weight.shape[3], stride, pad, False, act, gain)
+    return Conv2dFn.apply(x, weight, bias, res, g, True)
+
+
+def conv2d_prepared(x, wk, *, pad=0, per_sample=False):
+    g = ConvGeom(wk.shape[-3], wk.shape[-2], 1, pad, per_sample)
+    return Conv2dFn.apply(x, wk, None, None, g, False)
+
+
+# ============================================================================= batched GEMM
+def _strides4(t):
+    return (torch.tensor if False else list)(t.stride())
+
+
+class BmmFn(Function):
+    """C[b1,b2] = alpha * A[b1,b2] @ B[b1,b2] (+ bias over the last axis).  A (b1,b2,M,K), B (b1,b2,K,N): any
+    strides.  ``out_bmhn``: lay C out physically as (b1, M, b2, N) (returned view is still (b1,b2,M,N))."""
+
+    @staticmethod
+    def forward(ctx, a, b, bias, alpha, out_bmhn):
+        import ctypes
+        b1, b2, m, k = a.shape
+        n = b.shape[-1]
+        assert b.shape[:3] == (b1, b2, k) and a.dtype == b.dtype
+        if out_bmhn:
+            c = torch.empty((b1, m, b2, n), dtype=a.dtype, device=a.device).permute(0, 2, 1, 3)
+        else:
+            c = torch.empty((b1, b2, m, n), dtype=a.dtype, device=a.device)
+        sa = (ctypes.c_int64 * 4)(*a.stride())
+        sb = (ctypes.c_int64 * 4)(*b.stride())
+        sc = (ctypes.c_int64 * 3)(*c.stride()[:3])
+        assert c.stride(3) == 1
+        call("gg_bmm", _p(a), _p(b), _p(bias), _p(c), b1, b2, m, n, k, ctypes.cast(sa, ctypes.c_void_p),
+             ctypes.cast(sb, ctypes.c_void_p), ctypes.cast(sc, ctypes.c_void_p), float(alpha), _dt(a), _st())
+        ctx.alpha, ctx.has_bias = alpha, bias is not None
+        ctx.save_for_backward(a, b)
+        return c
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = gb = gbias = None
+        if ctx.needs_input_grad[0]:
+            ga = BmmFn.apply(g, b.transpose(-1, -2), None, ctx.alpha, False)
+        if ctx.needs_input_grad[1]:
+            gb = BmmFn.apply(a.transpose(-1, -2), g, None, ctx.alpha, False)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gc = _c(g)
+            gbias = dot_sc(gc, None, gc.numel() // gc.shape[-1], 1).reshape(-1)
+        return ga, gb, gbias, None, None
+
+
+def bmm(a, b, alpha=1.0, out_bmhn=False):
+    return BmmFn.apply(a, b, None, alpha, out_bmhn)
+
+
+def linear(x, weight, bias=None, alpha=1.0):
+    """x (R,K) @ weight(O,K)^T * alpha + bias  (fp32 small-tensor path; bias not scaled by alpha)."""
+    y = BmmFn.apply(x[None, None], weight.t()[None, None], bias, alpha, False)
+    return y[0, 0]
+
+
+# ============================================================================= pointwise with derivative levels
+class UnaryFn(Function):
+    @staticmethod
+    def forward(ctx, kind, x):
+        x = _c(x)
+        out = torch.empty_like(x)
+        call("gg_pw_unary", kind, 0, _p(x), None, None, _p(out), x.numel(), _dt(x), _st())
+        ctx.kind = kind
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return None, Unary1Fn.apply(ctx.kind, x, g)
+
+
+class Unary1Fn(Function):
+    """g * f'(x)"""
+
+    @staticmethod
+    def forward(ctx, kind, x, g):
+        x, g = _c(x), _c(g)
+        out = torch.empty_like(x)
+        call("gg_pw_unary", kind, 1, _p(x), _p(g), None, _p(out), x.numel(), _dt(x), _st())
+        ctx.kind = kind
+        ctx.save_for_backward(x, g)
+        return out
+
+    @staticmethod
+    def backward(ctx, gg):
+        x, g = ctx.saved_tensors
+        dx = dg = None
+        if ctx.needs_input_grad[1] and ctx.kind not in (U_LRELU, U_RELU):
+            dx = Unary2Fn.apply(ctx.kind, x, g, gg)
+        if ctx.needs_input_grad[2]:
+            dg = Unary1Fn.apply(ctx.kind, x, gg)
+        return None, dx, dg
+
+
+class Unary2Fn(Function):
+    """a * b * f''(x)  (terminal: third derivatives are never needed)"""
+
+    @staticmethod
+    def forward(ctx, kind, x, a, b):
+        x, a, b = _c(x), _c(a), _c(b)
+        out = torch.empty_like(x)
+        call("gg_pw_unary", kind, 2, _p(x), _p(a), _p(b), _p(out), x.numel(), _dt(x), _st())
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        raise RuntimeError("third-order derivatives are not implemented")
+
+
+def unary(kind, x):
+    return UnaryFn.apply(kind, x)
+
+
+def leaky_relu(x):
+    return UnaryFn.apply(U_LRELU, x)
+
+
+class MulFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        out = torch.empty_like(a)
+        call("gg_pw_mul", _p(a), _p(b), _p(out), a.numel(), _dt(a), _st())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        return (MulFn.apply(g, b) if ctx.needs_input_grad[0] else None,
+                MulFn.apply(g, a) if ctx.needs_input_grad[1] else None)
+
+
+def mul(a, b):
+    return MulFn.apply(a, b)
+
+
+class AxpbyFn(Function):
+    @staticmethod
+    def forward(ctx, alpha, x, beta, y):
+        x = _c(x)
+        y = None if y is None else _c(y)
+        out = torch.empty_like(x)
+        call("gg_pw_axpby", float(alpha), _p(x), float(beta), _p(y), _p(out), x.numel(), _dt(x), _st())
+        ctx.alpha, ctx.beta = alpha, beta
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        gx = AxpbyFn.apply(ctx.alpha, g, 0.0, None) if ctx.needs_input_grad[1] else None
+        gy = AxpbyFn.apply(ctx.beta, g, 0.0, None) if ctx.needs_input_grad[3] else None
+        return None, gx, None, gy
+
+
+def axpby(alpha, x, beta=0.0, y=None):
+    return AxpbyFn.apply(alpha, x, beta, y)
+
+
+def add(x, y):
+    return AxpbyFn.apply(1.0, x, 1.0, y)
+
+
+# ============================================================================= broadcasts and their reductions
+class BcastFn(Function):
+    """x viewed [R, C] (C = last dim) combined with an fp32 statistic tensor s.
+    mode ROWS: s has R entries.  mode SAMPLE_CH: s is (Ns, C); row r belongs to sample (r // P) % Ns."""
+
+    @staticmethod
+    def forward(ctx, x, s, P, Ns, mode, op):
+        x, s = _c(x), _c(s)
+        assert s.dtype == torch.float32
+        C = x.shape[-1]
+        R = x.numel() // C
+        assert s.numel() == (R if mode == ROWS else Ns * C), (s.shape, R, Ns, C)
+        out = torch.empty_like(x)
+        call("gg_pw_bcast", _p(x), _p(s), _p(out), R, C, P, Ns, mode, op, _dt(x), _st())
+        ctx.cfg = (P, Ns, mode, op)
+        ctx.save_for_backward(x, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        P, Ns, mode, op = ctx.cfg
+        gx = gs = None
+        if ctx.needs_input_grad[0]:
+            gx = BcastFn.apply(g, s, P, Ns, mode, MUL) if op == MUL else g
+        if ctx.needs_input_grad[1]:
+            other = x if op == MUL else None
+            if mode == ROWS:
+                gs = RowDotFn.apply(g, other if other is not None else _ones_like(g)).reshape(s.shape)
+            else:
+                gs = DotSCFn.apply(g, other, P, Ns).reshape(s.shape)
+        return gx, gs, None, None, None, None
+
+
+def _ones_like(t):
+    return torch.ones_like(t)
+
+
+def scale_rows(x, s):
+    return BcastFn.apply(x, s, 1, 1, ROWS, MUL)
+
+
+def scale_channels(x, s, rows_per_sample, num_samples):
+    """x * s[(sample % num_samples), c]  (s fp32 (num_samples, C))"""
+    return BcastFn.apply(x, s, rows_per_sample, num_samples, SAMPLE_CH, MUL)
+
+
+def add_channels(x, s, rows_per_sample, num_samples):
+    return BcastFn.apply(x, s, rows_per_sample, num_samples, SAMPLE_CH, ADD)
+
+
+class RowDotFn(Function):
+    """out[r] = sum_c a[r,c] b[r,c]   (fp32)"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _c(a), _c(b)
+        C = a.shape[-1]
+        R = a.numel() // C
+        out = torch.empty(a.shape[:-1], dtype=torch.float32, device=a.device)
+        call("gg_red_rowdot", _p(a), _p(b), _p(out), R, C, _dt(a), _st())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.float()
+        return (scale_rows(b, g) if ctx.needs_input_grad[0] else None,
+                scale_rows(a, g) if ctx.needs_input_grad[1] else None)
+
+
+def rowdot(a, b):
+    return RowDotFn.apply(a, b)
+
+
+class DotSCFn(Function):
+    """out[n', c] = sum over samples n == n' (mod Ns) and their P rows of a*b (b optional) -> fp32 (Ns, C)"""
+
+    @staticmethod
+    def forward(ctx, a, b, P, Ns):
+        a = _c(a)
+        b = None if b is None else _c(b)
+        C = a.shape[-1]
+        R = a.numel() // C
+        assert R % (P * Ns) == 0
+        out = torch.empty((Ns, C), dtype=torch.float32, device=a.device)
+        call("gg_red_dot_sc", _p(a), _p(b), _p(out), R, C, P, Ns, _dt(a), _st())
+        ctx.cfg = (P, Ns, b is None)
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        P, Ns, no_b = ctx.cfg
+        g = g.float()
+        if no_b:
+            ga = BcastFn.apply(torch.zeros_like(a), g, P, Ns, SAMPLE_CH, ADD) if ctx.needs_input_grad[0] else None
+            return ga, None, None, None
+        return (BcastFn.apply(b, g, P, Ns, SAMPLE_CH, MUL) if ctx.needs_input_grad[0] else None,
+                BcastFn.apply(a, g, P, Ns, SAMPLE_CH, MUL) if ctx.needs_input_grad[1] else None, None, None)
+
+
+def dot_sc(a, b, rows_per_sample, num_samples):
+    return DotSCFn.apply(a, b, rows_per_sample, num_samples)
+
+
+def mean_hw(x):
+    """(N,H,W,C) -> fp32 (N,C) spatial mean."""
+    n, h, w, c = x.shape
+    return axpby(1.0 / (h * w), dot_sc(x, None, h * w, n))
+
+
+def sum_all(x):
+    """scalar fp32 sum of any tensor"""
+    return dot_sc(x.reshape(-1, 1), None, x.numel(), 1).reshape(())
+
+
+class SoftmaxFn(Function):
+    @staticmethod
+    def forward(ctx, s):
+        s = _c(s)
+        C = s.shape[-1]
+        p = torch.empty_like(s)
+        call("gg_softmax_rows", _p(s), _p(p), s.numel() // C, C, _dt(s), _st())
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    def backward(ctx, gp):
+        (p,) = ctx.saved_tensors
+        # dS = P * (gP - rowdot(P, gP))
+        t = mul(p, gp)
+        r = rowdot(p, gp)
+        return axpby(1.0, t, -1.0, scale_rows(p, r))
+
+
+def softmax(s):
+    return SoftmaxFn.apply(s)
+
+
+# ============================================================================= resampling (separable, sparse)
+class ResampleOp:
+    """A separable linear map on the (H, W) axes given by dense 1-D matrices Ay (OH,H), Ax (OW,W); holds device
+    tap tables for the map and its transpose."""
+
+    def __init__(self, ay, ax, device):
+        self.shape_in = (ay.shape[1], ax.shape[1])
+        self.shape_out = (ay.shape[0], ax.shape[0])
+        self.fwd = (self._taps(ay, device), self._taps(ax, device))
+        self.bwd = (self._taps(ay.t(), device), self._taps(ax.t(), device))
+
+    @staticmethod
+    def _taps(a, device):
+        a = a.double()
+        nnz = int((a != 0).sum(dim=1).max().item())
+        idx = torch.zeros((a.shape[0], nnz), dtype=torch.int32)
+        wgt = torch.zeros((a.shape[0], nnz), dtype=torch.float32)
+        for r in range(a.shape[0]):
+            cols = torch.nonzero(a[r]).flatten()
+            idx[r, : len(cols)] = cols.to(torch.int32)
+            wgt[r, : len(cols)] = a[r, cols].float()
+        return idx.to(device).contiguous(), wgt.to(device).contiguous(), nnz
+
+
+def bilinear_matrix(n_in, n_out):
+    """1-D F.interpolate(mode='bilinear', align_corners=False) as an (n_out, n_in) matrix (torch semantics:
+    src = (dst + 0.5) * n_in / n_out - 0.5, clamped below at 0, right neighbour clamped to n_in - 1)."""
+    a = torch.zeros((n_out, n_in), dtype=torch.float64)
+    scale = n_in / n_out
+    for j in range(n_out):
+        src = max((j + 0.5) * scale - 0.5, 0.0)
+        i0 = min(int(math.floor(src)), n_in - 1)
+        i1 = min(i0 + 1, n_in - 1)
+        f = src - i0
+        a[j, i0] += 1.0 - f
+        a[j, i1] += f
+    return a
+
+
+def blur_matrix(n):
+    """1-D [1,2,1]/4 with reflect border (kornia filter2d default), (n, n)."""
+    a = torch.zeros((n, n), dtype=torch.float64)
+    for j in range(n):
+        for off, wt in ((-1, 0.25), (0, 0.5), (1, 0.25)):
+            i = j + off
+            if i < 0:
+                i = -i
+            if i >= n:
+                i = 2 * (n - 1) - i
+            a[j, i] += wt
+    return a
+
+
+_RESAMPLE_CACHE = {}
+
+
+def get_resample_op(kind, h, w, device, out=None):
+    key = (kind, h, w, str(device), out)
+    op = _RESAMPLE_CACHE.get(key)
+    if op is None:
+        if kind == "up2_blur":      # ref gigagan_pytorch.py:257-261
+            ay, ax = blur_matrix(2 * h) @ bilinear_matrix(h, 2 * h), blur_matrix(2 * w) @ bilinear_matrix(w, 2 * w)
+        elif kind == "bilinear":    # ref gigagan_pytorch.py:1683-1684
+            ay, ax = bilinear_matrix(h, out[0]), bilinear_matrix(w, out[1])
+        elif kind == "blur":
+            ay, ax = blur_matrix(h), blur_matrix(w)
+        else:
+            raise ValueError(kind)
+        op = _RESAMPLE_CACHE[key] = ResampleOp(ay, ax, device)
+    return op
+
+
+class ResampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, op, transposed):
+        x = _c(x)
+        n, h, w, c = x.shape
+        (ty, tx), (oh, ow) = (op.bwd, op.shape_in) if transposed else (op.fwd, op.shape_out)
+        assert (h, w) == (op.shape_out if transposed else op.shape_in)
+        y = torch.empty((n, oh, ow, c), dtype=x.dtype, device=x.device)
+        call("gg_resample2d", _p(x), _p(y), n, h, w, c, oh, ow, _p(ty[0]), _p(ty[1]), ty[2], _p(tx[0]), _p(tx[1]),
+             tx[2], _dt(x), _st())
+        ctx.op, ctx.transposed = op, transposed
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ResampleFn.apply(g, ctx.op, not ctx.transposed), None, None
+
+
+def upsample2x_blur(x):
+    return ResampleFn.apply(x, get_resample_op("up2_blur", x.shape[1], x.shape[2], x.device), False)
+
+
+def resize_bilinear(x, size):
+    return ResampleFn.apply(x, get_resample_op("bilinear", x.shape[1], x.shape[2], x.device, (size, size)), False)
+
+
+# ============================================================================= layout at the API edge
+class ToNHWCFn(Function):
+    """NCHW fp32 (reference layout) -> NHWC compute dtype, channels zero-padded to cpad."""
+
+    @staticmethod
+    def forward(ctx, x, cpad, dtype):
+        x = _c(x.float())
+        n, c, h, w = x.shape
+        y = torch.empty((n, h, w, cpad), dtype=dtype, device=x.device)
+        call("gg_nchw_to_nhwc", _p(x), _p(y), n, c, h * w, cpad, _dt(y), _st())
+        ctx.c = c
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNCHWFn.apply(g, ctx.c), None, None
+
+
+class ToNCHWFn(Function):
+    """NHWC (cpad channels) -> NCHW fp32 keeping the first c channels."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        x = _c(x)
+        n, h, w, cpad = x.shape
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call("gg_nhwc_to_nchw", _p(x), _p(y), n, c, h * w, cpad, _dt(x), _st())
+        ctx.cpad, ctx.dtype = cpad, x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return ToNHWCFn.apply(g, ctx.cpad, ctx.dtype), None
+
+
+def to_nhwc(x, cpad, dtype):
+    return ToNHWCFn.apply(x, cpad, dtype)
+
+
+def to_nchw(x, c):
+    return ToNCHWFn.apply(x, c)
+
+
+# ============================================================================= generator-only fused ops (first-order)
+class AdaConvWeightsFn(Function):
+    """Per-sample modulated / demodulated filter from the bank (ref gigagan_pytorch.py:378-400).
+    bank (n,O,I,k,k) fp32; mod (B,I) fp32; kmod (B,n) fp32 or None -> (B,O,k,k,I) kernel layout, compute dtype."""
+
+    @staticmethod
+    def forward(ctx, bank, mod, kmod, demod, eps, dtype):
+        bank, mod = _c(bank), _c(mod.float())
+        n, O, I, k, _ = bank.shape
+        B = mod.shape[0]
+        if n > 1:
+            assert kmod is not None and kmod.numel() > 0
+            kmod = _c(kmod.float())
+        else:
+            kmod = None
+        w = torch.empty((B, O, k, k, I), dtype=dtype, device=bank.device)
+        attn = torch.empty((B, n), dtype=torch.float32, device=bank.device)
+        dinv = torch.empty((B, O), dtype=torch.float32, device=bank.device)
+        call("gg_adaconv_weights_fwd", _p(bank), _p(mod), _p(kmod), _p(w), _p(attn), _p(dinv), B, n, O, I, k * k,
+             int(demod), float(eps), _dt(w), _st())
+        ctx.cfg = (demod, eps, kmod is not None)
+        ctx.save_for_backward(bank, mod, attn, dinv)
+        return w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gw):
+        bank, mod, attn, dinv = ctx.saved_tensors
+        demod, eps, has_kmod = ctx.cfg
+        n, O, I, k, _ = bank.shape
+        B = mod.shape[0]
+        gw = _c(gw.float())
+        dbank = torch.empty_like(bank)
+        dmod = torch.empty_like(mod)
+        dkmod = torch.empty((B, n), dtype=torch.float32, device=bank.device) if has_kmod else None
+        ws = torch.empty((B, n), dtype=torch.float32, device=bank.device)
+        call("gg_adaconv_weights_bwd", _p(bank), _p(mod), _p(attn), _p(dinv), _p(gw), _p(dbank), _p(dmod), _p(dkmod),
+             _p(ws), B, n, O, I, k * k, int(demod), float(eps), _st())
+        return dbank, dmod, dkmod, None, None, None
+
+
+class NoiseActFn(Function):
+    """lrelu(x + weight[c] * noise[n,h,w])  (ref gigagan_pytorch.py:925-940 + :1222)"""
+
+    @staticmethod
+    def forward(ctx, x, noise, weight):
+        x, noise, weight = _c(x), _c(noise.float()), _c(weight.float())
+        C = x.shape[-1]
+        y = torch.empty_like(x)
+        call("gg_noise_act_fwd", _p(x), _p(noise), _p(weight), _p(y), x.numel() // C, C, _dt(x), _st())
+        ctx.save_for_backward(y, noise)
+        ctx.wshape = weight.shape
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        y, noise = ctx.saved_tensors
+        gy = _c(gy)
+        C = y.shape[-1]
+        dx = torch.empty_like(y)
+        dw = torch.empty(C, dtype=torch.float32, device=y.device)
+        call("gg_noise_act_bwd", _p(y), _p(gy), _p(noise), _p(dx), _p(dw), y.numel() // C, C, _dt(y), _st())
+        return dx, None, dw.reshape(ctx.wshape)
+
+
+class FusedAttnFn(Function):
+    """softmax(logits) V with online softmax; q,k,v (B, n, heads*d) rows (views into NHWC conv outputs allowed:
+    last dim contiguous).  First-order only (the gradient-penalty path uses the composed attention)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, null_kv, heads, scale, l2, shared_qk):
+        B, nq, hd = q.shape
+        nk, d = k.shape[1], hd // heads
+        assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+        assert q.stride(0) == nq * q.stride(1) and k.stride(0) == nk * k.stride(1) and v.stride(0) == nk * v.stride(1)
+        nkv = None if null_kv is None else _c(null_kv.float())
+        o = torch.empty((B, nq, hd), dtype=q.dtype, device=q.device)
+        lse = torch.empty((B * heads, nq), dtype=torch.float32, device=q.device)
+        call("gg_attn_fwd", _p(q), _p(k), _p(v), _p(nkv), _p(o), _p(lse), B, heads, nq, nk, d, q.stride(1), k.stride(1),
+             v.stride(1), o.stride(1), float(scale), int(l2), _dt(q), _st())
+        ctx.cfg = (heads, scale, l2, shared_qk)
+        ctx.save_for_backward(q, k, v, nkv, o, lse)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, go):
+        q, k, v, nkv, o, lse = ctx.saved_tensors
+        heads, scale, l2, shared = ctx.cfg
+        B, nq, hd = q.shape
+        nk, d = k.shape[1], hd // heads
+        go = _c(go)
+        dq = torch.empty((B, nq, hd), dtype=q.dtype, device=q.device)
+        dk = torch.empty((B, nk, hd), dtype=q.dtype, device=q.device)
+        dv = torch.empty((B, nk, hd), dtype=q.dtype, device=q.device)
+        dnull = None if nkv is None else torch.empty_like(nkv)
+        delta = torch.empty_like(lse)
+        # the backward kernel indexes dq/dk/dv with the strides of q/k/v: give it dense copies' strides
+        assert go.stride(1) == o.stride(1)
+        qc, kc, vc = _c(q), _c(k), _c(v)
+        call("gg_attn_bwd", _p(qc), _p(kc), _p(vc), _p(nkv), _p(o), _p(go), _p(lse), _p(dq), _p(dk), _p(dv), _p(dnull),
+             _p(delta), B, heads, nq, nk, d, qc.stride(1), kc.stride(1), vc.stride(1), o.stride(1), float(scale),
+             int(l2), _dt(q), _st())
+        if shared:
+            dq = add(dq, dk)
+            dk = None
+        return dq, dk, dv, dnull, None, None, None, None
+
+
+def fused_attention(q, k, v, null_kv, heads, scale, l2=False):
+    shared = k is q
+    return FusedAttnFn.apply(q, k, v, null_kv, heads, scale, l2, shared)

@@ -1,0 +1,442 @@
+"""GigaGAN trainer with the reference's public surface (ctor keywords, ``set_dataloader``, ``__call__(steps=,
+grad_accum_every=)``, ``generate``, ``train_discriminator_step`` / ``train_generator_step``), running the G and D
+passes on the sm_100a kernels, AdamW as one fused kernel over flat parameter buffers and the data-parallel
+gradient exchange as NCCL all-reduces of those flat buffers (one per optimiser step per model).
+
+Reference: gigagan_pytorch/gigagan_pytorch.py:1858-2750 (GigaGAN), :120-163 (losses), optimizer.py:10-34.
+Differences that are deliberate: no ``.item()`` host syncs inside a step (losses stay on device
+until logged), D's weight gradients are not computed/reduced during the generator step (Q12), and HF accelerate
+is replaced by torch.distributed directly (``accelerator=`` / ``accelerate_kwargs=`` are accepted and ignored).
+"""
+from __future__ import annotations
+
+import copy
+import math
+import os
+from collections import namedtuple
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+from ._lib import call
+from .modules import BaseGenerator, Discriminator, Generator, compute_dtype, img_cpad, set_compute_dtype
+from .ops import U_RELU, _p, _st
+
+__version__ = "0.1.0"
+
+TrainDiscrLosses = namedtuple("TrainDiscrLosses", ["divergence", "multiscale_divergence", "vision_aided_divergence",
+                                                   "total_matching_aware_loss", "gradient_penalty",
+                                                   "aux_reconstruction"])
+TrainGenLosses = namedtuple("TrainGenLosses", ["divergence", "multiscale_divergence", "total_vd_divergence",
+                                               "contrastive_loss"])
+
+
+def exists(v):
+    return v is not None
+
+
+def cycle(dl):
+    while True:
+        for data in dl:
+            yield data
+
+
+# ----------------------------------------------------------------------------- losses (ref :120-163)
+_CONST = {}
+
+
+def _const(val, device):
+    key = (float(val), str(device))
+    t = _CONST.get(key)
+    if t is None:
+        t = _CONST[key] = torch.full((1, 1), float(val), dtype=torch.float32, device=device)
+    return t
+
+
+def _mean_relu_affine(x, a, b):
+    """mean(relu(b + a*x)) as a 0-dim fp32 tensor."""
+    x = x.float().reshape(-1, 1)
+    t = ops.add_channels(ops.axpby(a, x), _const(b, x.device), x.shape[0], 1)
+    return ops.axpby(1.0 / x.shape[0], ops.sum_all(ops.unary(U_RELU, t)))
+
+
+def _mean(x):
+    x = x.float()
+    return ops.axpby(1.0 / x.numel(), ops.sum_all(x))
+
+
+def generator_hinge_loss(fake):
+    return _mean(fake)
+
+
+def discriminator_hinge_loss(real, fake):
+    return ops.add(_mean_relu_affine(real, 1.0, 1.0), _mean_relu_affine(fake, -1.0, 1.0))
+
+
+def gradient_penalty(images, outputs, grad_output_weights=None, weight=10, center=0., scaler=None, eps=1e-4):
+    """weight * mean_b ||d(sum_k w_k out_k)/d images_b||^2  (ref :120-155; center must be 0, no GradScaler)."""
+    assert center == 0. and scaler is None
+    if not isinstance(outputs, (list, tuple)):
+        outputs = [outputs]
+    if grad_output_weights is None:
+        grad_output_weights = (1,) * len(outputs)
+    gos = [torch.full_like(o, float(w)) for o, w in zip(outputs, grad_output_weights)]
+    with ops.skip_param_grads():
+        g, = torch.autograd.grad(outputs=list(outputs), inputs=images, grad_outputs=gos, create_graph=True,
+                                 retain_graph=True)
+    b = g.shape[0]
+    per = g.numel() // b
+    c = 64 if per % 64 == 0 else (g.shape[-1] if per % g.shape[-1] == 0 else 1)
+    g2 = g.reshape(-1, c)
+    t = ops.dot_sc(g2, g2, per // c, b)                          # (b, c) partial sums of squares
+    return ops.axpby(float(weight) / b, ops.sum_all(t))
+
+
+# ----------------------------------------------------------------------------- flat parameters + fused AdamW
+class FlatAdamW:
+    """All parameters of a module live in one fp32 buffer (and their .grad in another); AdamW is one kernel launch
+    over a chunk table.  Semantics = torch.optim.AdamW as the reference builds it (optimizer.py:10-34 called from
+    gigagan_pytorch.py:1982-1983): lr, betas, eps, decoupled weight decay 1e-2 on ndim>=2 tensors only (Q2)."""
+
+    CHUNK = 1 << 16
+
+    def __init__(self, module: nn.Module, lr=2e-4, betas=(0.5, 0.9), eps=1e-8, wd=1e-2):
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params
+        dev = params[0].device
+        assert dev.type == "cuda", "move the model to the GPU before building the optimiser"
+        total = sum(p.numel() for p in params)
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        chunks, off = [], 0
+        for p in params:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + n].view(p.shape)
+            p.grad = self.grad[off:off + n].view(p.shape)
+            decay = 1 if p.ndim >= 2 else 0
+            for s in range(0, n, self.CHUNK):
+                o = off + s
+                chunks.append((o & 0x7FFFFFFF, min(self.CHUNK, n - s), decay, o >> 31))
+            off += n
+        self.chunks = torch.tensor(chunks, dtype=torch.int32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, wd
+        self.scaler = None
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+        for p, off in zip(self.params, self._offsets()):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * off:
+                p.grad = self.grad[off:off + p.numel()].view(p.shape)
+
+    def _offsets(self):
+        off = 0
+        for p in self.params:
+            yield off
+            off += p.numel()
+
+    def step(self, grad_scale=1.0):
+        call("gg_incr", _p(self.step_t), _st())
+        call("gg_adamw", _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.chunks), self.chunks.shape[0],
+             _p(self.step_t), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, float(grad_scale), _st())
+
+    def all_reduce_grads(self, group=None):
+        """SUM all-reduce of the flat gradient; the 1/world scaling is folded into the AdamW kernel."""
+        dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+
+    def state_dict(self):
+        return dict(m=self.m, v=self.v, step=self.step_t, lr=self.lr, betas=self.betas, eps=self.eps, wd=self.wd)
+
+    def load_state_dict(self, sd):
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"])
+
+
+def get_optimizer(module_or_params, lr=1e-4, wd=1e-2, betas=(0.9, 0.99), eps=1e-8, **_):
+    assert isinstance(module_or_params, nn.Module), "pass the module (flat-buffer optimiser)"
+    return FlatAdamW(module_or_params, lr=lr, betas=betas, eps=eps, wd=wd)
+
+
+# ----------------------------------------------------------------------------- trainer
+class GigaGAN(nn.Module):
+    def __init__(self, *, generator: BaseGenerator | Dict, discriminator: Discriminator | Dict,
+                 vision_aided_discriminator=None, diff_augment=None, learning_rate=2e-4, betas=(0.5, 0.9),
+                 weight_decay=0., discr_aux_recon_loss_weight=1., multiscale_divergence_loss_weight=0.1,
+                 vision_aided_divergence_loss_weight=0.5, generator_contrastive_loss_weight=0.1,
+                 matching_awareness_loss_weight=0.1, calc_multiscale_loss_every=1, apply_gradient_penalty_every=4,
+                 resize_image_mode="bilinear", train_upsampler=False, log_steps_every=20,
+                 create_ema_generator_at_init=True, save_and_sample_every=1000, early_save_thres_steps=2500,
+                 early_save_and_sample_every=100, num_samples=25, model_folder="./gigagan-models",
+                 results_folder="./gigagan-results", sample_upsampler_dl=None, accelerator=None,
+                 accelerate_kwargs: dict = {}, find_unused_parameters=True, amp=False, mixed_precision_type="fp16"):
+        super().__init__()
+        assert vision_aided_discriminator is None, "VisionAidedDiscriminator needs CLIP weights (out of scope)"
+        assert diff_augment is None, "DiffAugment is host-side and not part of this build yet"
+        assert not train_upsampler, "UnetUpsampler training is the next SURVEY 8 row (not in this build)"
+        if amp:
+            assert mixed_precision_type == "bf16", "B200 path computes in bf16 (set mixed_precision_type='bf16')"
+            set_compute_dtype(torch.bfloat16)
+        self.train_upsampler = train_upsampler
+        self.apply_gradient_penalty_every = apply_gradient_penalty_every
+        self.calc_multiscale_loss_every = calc_multiscale_loss_every
+        if isinstance(generator, dict):
+            generator = Generator(**generator)
+        if isinstance(discriminator, dict):
+            discriminator = Discriminator(**discriminator)
+        self.G, self.D, self.VD = generator, discriminator, None
+        self.diff_augment = None
+        assert generator.unconditional == discriminator.unconditional
+        self.unconditional = generator.unconditional
+        self.learning_rate, self.betas = learning_rate, betas
+        self.G_opt = self.D_opt = None          # built lazily once the parameters are on the GPU
+        self.has_ema_generator = False
+        self._want_ema = create_ema_generator_at_init
+        self.discr_aux_recon_loss_weight = discr_aux_recon_loss_weight
+        self.multiscale_divergence_loss_weight = multiscale_divergence_loss_weight
+        self.vision_aided_divergence_loss_weight = vision_aided_divergence_loss_weight
+        self.generator_contrastive_loss_weight = generator_contrastive_loss_weight
+        self.matching_awareness_loss_weight = matching_awareness_loss_weight
+        self.resize_image_mode = resize_image_mode
+        self.log_steps_every = log_steps_every
+        self.register_buffer("steps", torch.ones(1, dtype=torch.long))
+        self._host_steps = 1
+        self.save_and_sample_every = save_and_sample_every
+        self.early_save_thres_steps = early_save_thres_steps
+        self.early_save_and_sample_every = early_save_and_sample_every
+        self.num_samples = num_samples
+        self.train_dl = None
+        self.results_folder, self.model_folder = Path(results_folder), Path(model_folder)
+        self.print(f"Generator: {generator.total_params:,}  Discriminator: {discriminator.total_params:,}")
+
+    # ---- process-group helpers (accelerate replaced by torch.distributed)
+    @property
+    def is_distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    @property
+    def world_size(self):
+        return dist.get_world_size() if self.is_distributed else 1
+
+    @property
+    def is_main(self):
+        return not self.is_distributed or dist.get_rank() == 0
+
+    @property
+    def device(self):
+        return self.steps.device
+
+    def print(self, msg):
+        if self.is_main:
+            print(msg)
+
+    @property
+    def unwrapped_G(self):
+        return self.G
+
+    @property
+    def unwrapped_D(self):
+        return self.D
+
+    def _ensure_optimizers(self):
+        if self.G_opt is None:
+            if self.is_distributed:          # identical initial weights on every rank, like DDP's broadcast
+                for p in list(self.G.parameters()) + list(self.D.parameters()):
+                    dist.broadcast(p.data, src=0)
+            if self._want_ema and self.is_main and not self.has_ema_generator:
+                self.create_ema_generator()          # before flattening: deepcopy of flat views would copy storages
+            self.G_opt = FlatAdamW(self.G, lr=self.learning_rate, betas=self.betas)
+            self.D_opt = FlatAdamW(self.D, lr=self.learning_rate, betas=self.betas)
+
+    def create_ema_generator(self, update_every=10, update_after_step=100, decay=0.995):
+        if not self.is_main:
+            return
+        assert not self.has_ema_generator
+        self.G_ema = copy.deepcopy(self.G).requires_grad_(False)
+        self._ema_cfg = (update_every, update_after_step, decay)
+        self._ema_step = 0
+        self.has_ema_generator = True
+
+    @torch.no_grad()
+    def _ema_update(self):
+        every, after, decay = self._ema_cfg
+        step = self._ema_step
+        self._ema_step += 1
+        if step % every != 0:
+            return
+        if step <= after:
+            for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
+                pe.copy_(p)
+            return
+        for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
+            pe.copy_(ops.axpby(decay, pe, 1.0 - decay, p))
+
+    def set_dataloader(self, dl):
+        assert not exists(self.train_dl), "training dataloader has already been set"
+        self.train_dl = dl
+        self.train_dl_batch_size = dl.batch_size
+
+    @torch.inference_mode()
+    def generate(self, *args, **kwargs):
+        model = self.G_ema if self.has_ema_generator else self.G
+        model.eval()
+        return model(*args, **kwargs)
+
+    def save(self, path, overwrite=True):
+        path = Path(path)
+        path.parents[0].mkdir(exist_ok=True, parents=True)
+        assert overwrite or not path.exists()
+        self._ensure_optimizers()
+        pkg = dict(G=self.G.state_dict(), D=self.D.state_dict(), G_opt=self.G_opt.state_dict(),
+                   D_opt=self.D_opt.state_dict(), steps=self._host_steps, version=__version__)
+        if self.has_ema_generator:
+            pkg["G_ema"] = self.G_ema.state_dict()
+        torch.save(pkg, str(path))
+
+    def load(self, path, strict=False):
+        pkg = torch.load(str(path), map_location=self.device, weights_only=False)
+        self.G.load_state_dict(pkg["G"], strict=strict)
+        self.D.load_state_dict(pkg["D"], strict=strict)
+        self._ensure_optimizers()
+        for opt, key in ((self.G_opt, "G_opt"), (self.D_opt, "D_opt")):
+            if key in pkg and isinstance(pkg[key], dict) and "m" in pkg[key]:
+                opt.load_state_dict(pkg[key])
+        if "steps" in pkg:
+            self._host_steps = int(pkg["steps"])
+            self.steps.fill_(self._host_steps)
+
+    # ---- one micro-batch of each objective (device tensors in, 0-dim loss tensors out)
+    def _d_objective(self, real, noise, apply_gradient_penalty, calc_multiscale_loss):
+        D, G, dt = self.D, self.G, compute_dtype()
+        gp_on = apply_gradient_penalty
+        real = real.float()
+        if gp_on:
+            real.requires_grad_()
+        real_n = ops.to_nhwc(real, img_cpad(D.channels), dt)
+        real_rgbs = D.real_images_to_rgbs_nhwc(real_n)
+        with torch.no_grad():
+            fake, rgbs = G.forward_nhwc(noise=noise)
+        fake = fake.detach().requires_grad_(gp_on)
+        rgbs = [t.detach().requires_grad_(gp_on) for t in rgbs]
+        fused = not gp_on
+        fl, fm, _ = D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False, fused_attention=fused)
+        rl, rm, aux = D.forward_nhwc(real_n, real_rgbs, calc_multiscale_loss, True, fused_attention=fused)
+        div = discriminator_hinge_loss(rl, fl)
+        total = div
+        zero = torch.zeros((), device=real.device)
+        ms = zero
+        if self.multiscale_divergence_loss_weight > 0. and len(fm) > 0:
+            ms = None
+            for a, b in zip(fm, rm):
+                t = discriminator_hinge_loss(b, a)
+                ms = t if ms is None else ops.add(ms, t)
+            total = ops.axpby(1.0, total, self.multiscale_divergence_loss_weight, ms)
+        gp = zero
+        if gp_on:
+            w = [1.] + [self.multiscale_divergence_loss_weight] * len(rm)
+            gp = ops.add(gradient_penalty(real, [rl, *rm], w), gradient_penalty(fake, [fl, *fm], w))
+            total = ops.add(total, gp)
+        aux_loss = zero
+        if self.discr_aux_recon_loss_weight > 0. and len(aux) > 0:
+            aux_loss = aux[0]
+            for a in aux[1:]:
+                aux_loss = ops.add(aux_loss, a)
+            total = ops.axpby(1.0, total, self.discr_aux_recon_loss_weight, aux_loss)
+        return total, (div, ms, gp, aux_loss)
+
+    def _g_objective(self, noise, calc_multiscale_loss):
+        fake, rgbs = self.G.forward_nhwc(noise=noise)
+        logits, ms, _ = self.D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False)
+        div = generator_hinge_loss(logits)
+        total, msd = div, torch.zeros((), device=noise.device)
+        if self.multiscale_divergence_loss_weight > 0. and len(ms) > 0:
+            msd = None
+            for m in ms:
+                t = generator_hinge_loss(m)
+                msd = t if msd is None else ops.add(msd, t)
+            total = ops.axpby(1.0, total, self.multiscale_divergence_loss_weight, msd)
+        return total, (div, msd)
+
+    def _next_images(self, dl_iter):
+        batch = next(dl_iter)
+        if isinstance(batch, (tuple, list)):
+            batch = batch[0]
+        return batch.to(self.device, non_blocking=True)
+
+    def train_discriminator_step(self, dl_iter: Iterable, grad_accum_every=1, apply_gradient_penalty=False,
+                                 calc_multiscale_loss=True):
+        self._ensure_optimizers()
+        self.G.train(); self.D.train()
+        self.D_opt.zero_grad()
+        acc = None
+        for _ in range(grad_accum_every):
+            real = self._next_images(dl_iter)
+            noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
+            total, parts = self._d_objective(real, noise, apply_gradient_penalty, calc_multiscale_loss)
+            ops.axpby(1.0 / grad_accum_every, total).backward()
+            parts = [p.detach() / grad_accum_every for p in parts]
+            acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
+        if self.is_distributed:
+            self.D_opt.all_reduce_grads()
+        self.D_opt.step(grad_scale=1.0 / self.world_size)
+        div, ms, gp, aux = acc
+        return TrainDiscrLosses(div, ms if calc_multiscale_loss else None, 0., 0., gp, aux)
+
+    def train_generator_step(self, batch_size=None, dl_iter: Optional[Iterable] = None, grad_accum_every=1,
+                             calc_multiscale_loss=True):
+        self._ensure_optimizers()
+        self.G.train(); self.D.train()
+        self.G_opt.zero_grad()
+        d_params = list(self.D.parameters())
+        for p in d_params:                   # Q12: D's weight gradients are discarded by the reference; skip them
+            p.requires_grad_(False)
+        acc = None
+        try:
+            for _ in range(grad_accum_every):
+                noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
+                total, parts = self._g_objective(noise, calc_multiscale_loss)
+                ops.axpby(1.0 / grad_accum_every, total).backward()
+                parts = [p.detach() / grad_accum_every for p in parts]
+                acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
+        if self.is_distributed:
+            self.G_opt.all_reduce_grads()
+        self.G_opt.step(grad_scale=1.0 / self.world_size)
+        if self.is_main and self.has_ema_generator:
+            self._ema_update()
+        div, msd = acc
+        return TrainGenLosses(div, msd if calc_multiscale_loss else None, 0., 0.)
+
+    def forward(self, *, steps, grad_accum_every=1):
+        assert exists(self.train_dl), "you need to set the dataloader by running .set_dataloader(dl: Dataloader)"
+        batch_size = self.train_dl_batch_size
+        dl_iter = cycle(self.train_dl)
+        last_gp = last_msd = last_msg = 0.
+        for _ in range(steps):
+            step = self._host_steps
+            gp_on = self.apply_gradient_penalty_every > 0 and step % self.apply_gradient_penalty_every == 0
+            ms_on = self.calc_multiscale_loss_every > 0 and step % self.calc_multiscale_loss_every == 0
+            d = self.train_discriminator_step(dl_iter=dl_iter, grad_accum_every=grad_accum_every,
+                                              apply_gradient_penalty=gp_on, calc_multiscale_loss=ms_on)
+            g = self.train_generator_step(dl_iter=dl_iter, batch_size=batch_size, grad_accum_every=grad_accum_every,
+                                          calc_multiscale_loss=ms_on)
+            if gp_on:
+                last_gp = d.gradient_penalty
+            if exists(d.multiscale_divergence):
+                last_msd = d.multiscale_divergence
+            if exists(g.multiscale_divergence):
+                last_msg = g.multiscale_divergence
+            if step == 1 or step % self.log_steps_every == 0:
+                losses = (("G", g.divergence), ("MSG", last_msg), ("VG", 0.), ("D", d.divergence), ("MSD", last_msd),
+                          ("VD", 0.), ("GP", last_gp), ("SSL", d.aux_reconstruction), ("CL", 0.), ("MAL", 0.))
+                self.print(" | ".join(f"{n}: {float(v):.2f}" for n, v in losses))
+            self._host_steps += 1
+            self.steps += 1
+        self.print(f"complete {steps} training steps")

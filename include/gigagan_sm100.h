@@ -1,0 +1,114 @@
+/* libgigagan_sm100.so — C ABI of the B200 (sm_100a) GigaGAN training hot path.
+ *
+ * Conventions (SURVEY.md 8b "lower boundary"):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named `h_*`;
+ *   - the library never allocates and never synchronises; the caller owns every buffer (outputs and
+ *     workspaces) and passes the stream to launch on;
+ *   - returns 0 on success, negative on error; gg_last_error() gives the thread-local message;
+ *   - dtype: 0 = fp32 (FFMA kernels, 1e-5 parity path), 1 = bf16 storage / fp32 accumulate (tcgen05 where the
+ *     shape is dense enough, FFMA otherwise).  Small statistic tensors are always fp32.
+ *   - activations are NHWC (pixel rows x channels); conv weights are "kernel layout" [Cout][KH][KW][Cin].
+ *
+ * Each entry point names the reference interface it replaces; paths are relative to
+ * lucidrains/gigagan-pytorch @ 0806433f, gigagan_pytorch/.
+ */
+#ifndef GIGAGAN_SM100_H
+#define GIGAGAN_SM100_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gg_stream_t; /* cudaStream_t */
+
+const char* gg_last_error(void);
+int gg_version(void);
+/* 1 when this build contains the tcgen05/TMA kernels (always, for sm_100a). */
+int gg_has_tcgen05(void);
+
+/* ---- convolution family (replaces F.conv2d / nn.Conv2d: gigagan_pytorch.py:402-409 grouped per-sample conv of
+ * AdaptiveConv2DMod; :1608-1620, :292, :1454-1470, :1656 discriminator convs; unet_upsampler.py:82-160).
+ * x [N,H,W,Cin], w [G][Cout][KH][KW][Cin] (G = N when per_sample_w else 1), y [N,OH,OW,Cout].
+ * y = (act(conv + bias) + res) * gain ; act 0 none / 1 leaky-relu(0.2); bias fp32 or NULL; res like y or NULL. */
+int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y,
+                    int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad,
+                    int per_sample_w, int act, float gain, int dtype, gg_stream_t stream);
+/* dx [N,H,W,Cin] = conv-transpose(dy [N,OH,OW,Cout], w)  (autograd of the calls above, data gradient) */
+int gg_conv2d_dgrad(const void* dy, const void* w, void* dx,
+                    int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad,
+                    int per_sample_w, int dtype, gg_stream_t stream);
+/* dw [G][Cout][KH][KW][Cin] fp32 (overwritten) = sum over pixels of dy (x) x  (weight gradient) */
+int gg_conv2d_wgrad(const void* x, const void* dy, float* dw,
+                    int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad,
+                    int per_sample_w, int dtype, gg_stream_t stream);
+
+/* ---- strided batched GEMM (replaces torch.einsum/bmm at gigagan_pytorch.py:574,:579,:590,:643,:651 and
+ * nn.Linear / F.linear at :302-304,:887,:1121,:1658).  C[z1,z2][m,n] = alpha * sum_k A[m,k] B[k,n] (+ bias[n]).
+ * h_sa/h_sb = {batch1 stride, batch2 stride, row stride, col stride} (elements, host arrays); h_sc = {s1,s2,row}. */
+int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
+           const int64_t* h_sa, const int64_t* h_sb, const int64_t* h_sc, float alpha, int dtype, gg_stream_t stream);
+
+/* ---- pointwise maps with explicit derivative levels (replaces nn.LeakyReLU :109, F.relu :163, nn.GELU :738,
+ * nn.SiLU/nn.Sigmoid :303-305, F.normalize's 1/max(||x||,eps) :231).  kind: 0 lrelu 1 relu 2 gelu 3 silu
+ * 4 sigmoid 5 invnorm.  level 0: out=f(x); 1: out=a*f'(x); 2: out=a*b*f''(x). */
+int gg_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, int64_t n, int dtype,
+                gg_stream_t stream);
+int gg_pw_mul(const void* a, const void* b, void* out, int64_t n, int dtype, gg_stream_t stream);
+int gg_pw_axpby(float alpha, const void* x, float beta, const void* y /*nullable*/, void* out, int64_t n, int dtype,
+                gg_stream_t stream);
+/* x viewed [R,C]; s fp32.  mode 0: s[r]; mode 1: s[((r/P)%Ns)*C+c] (per-sample-channel, scale-major repeat as in
+ * gigagan_pytorch.py:1766).  op 0 multiply, 1 add.  (SqueezeExcite scaling :1218,:1767; RMSNorm gamma :232) */
+int gg_pw_bcast(const void* x, const float* s, void* out, int64_t R, int C, int P, int Ns, int mode, int op, int dtype,
+                gg_stream_t stream);
+/* out[r] = sum_c a*b (b nullable) ; out[n',c] = sum over samples n==n' (mod Ns) and their P rows of a*b */
+int gg_red_rowdot(const void* a, const void* b, float* out, int64_t R, int C, int dtype, gg_stream_t stream);
+int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype,
+                  gg_stream_t stream);
+/* row softmax over the last axis of [R,C]  (gigagan_pytorch.py:588, :649; attend.py:104) */
+int gg_softmax_rows(const void* s, void* p, int64_t R, int C, int dtype, gg_stream_t stream);
+
+/* ---- separable sparse resampling of NHWC maps: bilinear x2 + [1,2,1]^2/16 reflect blur (:246-261), bilinear
+ * F.interpolate (:1683-1687) and their transposes.  Tap tables: iy/wy [OH][Ty], ix/wx [OW][Tx]. */
+int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
+                  int Ty, const int* ix, const float* wx, int Tx, int dtype, gg_stream_t stream);
+
+/* ---- layout at the API edge: reference tensors are NCHW fp32 (images, rgbs) */
+int gg_nchw_to_nhwc(const float* src, void* dst, int N, int C, int HW, int Cpad, int dtype, gg_stream_t stream);
+int gg_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, int Cpad, int dtype, gg_stream_t stream);
+
+/* ---- generator Noise + LeakyReLU (gigagan_pytorch.py:925-940 then :1222) */
+int gg_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, int64_t R, int C, int dtype,
+                     gg_stream_t stream);
+int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, int64_t R, int C,
+                     int dtype, gg_stream_t stream);
+
+/* ---- AdaptiveConv2DMod weight builder (gigagan_pytorch.py:378-400): softmax over the filter bank, (mod+1)
+ * modulation, demodulation.  bank [n][O][I][KK] fp32; mod [B][I]; kmod [B][n] (NULL if n==1);
+ * w [B][O][KK][I]; attn [B][n], dinv [B][O] saved for backward. */
+int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
+                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, gg_stream_t stream);
+int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
+                           float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
+                           int demod, float eps, gg_stream_t stream);
+
+/* ---- fused attention (gigagan_pytorch.py:562-592 with null key/value and L2-distance logits; attend.py:64-110)
+ * q,k,v,o: [B, n, heads, d] rows with the given row strides (elements); null_kv [2][heads][d] fp32 or NULL.
+ * mode 0 dot-product, 1 shared-QK L2 distance.  lse [B*heads][nq] fp32 saved for backward. */
+int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse,
+                int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
+                float scale, int mode, int dtype, gg_stream_t stream);
+int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
+                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws,
+                int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
+                float scale, int mode, int dtype, gg_stream_t stream);
+
+/* ---- AdamW on a flat fp32 parameter buffer (optimizer.py:10-34 as GigaGAN configures it: betas (0.5,0.9),
+ * decoupled wd on ndim>=2 tensors).  chunks: int4 {offset_lo31, len, wd_flag, offset_hi}. */
+int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr,
+             float lr, float b1, float b2, float eps, float wd, float grad_scale, gg_stream_t stream);
+int gg_incr(int* p, gg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

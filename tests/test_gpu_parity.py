@@ -1,0 +1,282 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle / golden fixtures on identical inputs.
+fp32 kernels: tolerance 1e-5 relative for forwards (1e-4 of the tensor's max for gradients, which pass through
+atomics and double backward); bf16: 1e-2 of the tensor's max (north_star tolerance)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import gigagan_pytorch_b200 as g
+    g.set_compute_dtype(torch.float32)
+    yield
+    g.set_compute_dtype(torch.float32)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relmax(a, b):
+    return (a.float() - b.float()).abs().max().item() / (b.float().abs().max().item() + 1e-20)
+
+
+def load(n):
+    return torch.load(os.path.join(GOLD, n), weights_only=False)
+
+
+def rn(k, *s):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(k))
+
+
+# ------------------------------------------------------------------ primitives
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("cfg", [
+    dict(n=2, h=9, w=7, ci=5, co=6, k=3, s=1, p=1), dict(n=3, h=8, w=8, ci=16, co=8, k=1, s=2, p=0),
+    dict(n=2, h=8, w=8, ci=4, co=8, k=2, s=2, p=0), dict(n=2, h=12, w=12, ci=3, co=10, k=7, s=1, p=3),
+    dict(n=1, h=4, w=4, ci=32, co=1, k=4, s=1, p=0), dict(n=2, h=16, w=16, ci=64, co=96, k=3, s=1, p=1),
+])
+def test_conv_family(cfg, dtype, tol):
+    from gigagan_pytorch_b200 import ops
+    c = cfg
+    x = rn(1, c["n"], c["ci"], c["h"], c["w"]).to(dev())
+    w = (rn(2, c["co"], c["ci"], c["k"], c["k"]) * 0.2).to(dev()).requires_grad_()
+    b = rn(3, c["co"]).to(dev()).requires_grad_()
+    xr = x.clone().requires_grad_()
+    ref = F.leaky_relu(F.conv2d(xr, w, b, stride=c["s"], padding=c["p"]), 0.2)
+    gy = torch.randn_like(ref)
+    gx_ref, gw_ref, gb_ref = torch.autograd.grad(ref, (xr, w, b), gy)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(dtype).requires_grad_()
+    y = ops.conv2d(xn, w, b, stride=c["s"], pad=c["p"], act=1)
+    gx, gw, gb = torch.autograd.grad(y, (xn, w, b), gy.permute(0, 2, 3, 1).contiguous().to(dtype))
+    assert relmax(y.permute(0, 3, 1, 2), ref) < tol
+    assert relmax(gx.permute(0, 3, 1, 2), gx_ref) < tol * 2
+    assert relmax(gw, gw_ref) < tol * 2
+    assert relmax(gb, gb_ref) < tol * 2
+
+
+def test_conv_double_backward_fp32():
+    """gradient-penalty shaped check: d/dw of |d y / d x|^2 through Conv2dFn/ConvDgradFn/ConvWgradFn."""
+    from gigagan_pytorch_b200 import ops
+    x = rn(1, 2, 4, 6, 6).to(dev())
+    w1 = (rn(2, 8, 4, 3, 3) * 0.3).to(dev()).requires_grad_()
+    w2 = (rn(3, 1, 8, 3, 3) * 0.3).to(dev()).requires_grad_()
+
+    def penalty(conv, xin, to_out):
+        h = conv(xin, w1, 1, True)
+        o = conv(h, w2, 1, False)
+        g, = torch.autograd.grad(o.sum(), xin, create_graph=True)
+        return (g.float() ** 2).sum()
+
+    xr = x.clone().requires_grad_()
+    pr = penalty(lambda t, w, p, a: F.leaky_relu(F.conv2d(t, w, padding=p), 0.2) if a else F.conv2d(t, w, padding=p), xr, None)
+    gr = torch.autograd.grad(pr, (w1, w2))
+    xn = x.permute(0, 2, 3, 1).contiguous().requires_grad_()
+    h = ops.conv2d(xn, w1, pad=1, act=1)
+    o = ops.conv2d(h, w2, pad=1)
+    g, = torch.autograd.grad(ops.sum_all(o), xn, create_graph=True)
+    pm = ops.sum_all(ops.mul(g, g))
+    gm = torch.autograd.grad(pm, (w1, w2))
+    assert relmax(pm, pr) < 1e-4
+    for a, b in zip(gm, gr):
+        assert relmax(a, b) < 1e-4
+
+
+def test_bmm_and_linear():
+    from gigagan_pytorch_b200 import ops
+    a = rn(1, 2, 3, 17, 9).to(dev()).requires_grad_()
+    b = rn(2, 2, 3, 9, 21).to(dev()).requires_grad_()
+    c = ops.bmm(a, b, alpha=0.5)
+    ref = 0.5 * (a @ b)
+    assert relmax(c, ref) < 1e-5
+    g = torch.randn_like(ref)
+    for m, r in zip(torch.autograd.grad(c, (a, b), g), torch.autograd.grad(ref, (a, b), g)):
+        assert relmax(m, r) < 1e-5
+    at = rn(3, 2, 9, 3, 17).to(dev()).permute(0, 2, 3, 1)          # strided view
+    assert relmax(ops.bmm(at, b, out_bmhn=True), at @ b) < 1e-5
+    x, w, bias = rn(4, 5, 7).to(dev()), rn(5, 11, 7).to(dev()), rn(6, 11).to(dev())
+    assert relmax(ops.linear(x, w, bias), F.linear(x, w, bias)) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["lrelu", "relu", "gelu", "silu", "sigmoid", "invnorm"])
+def test_unary_levels(kind):
+    from gigagan_pytorch_b200 import ops
+    fns = dict(lrelu=(ops.U_LRELU, lambda t: F.leaky_relu(t, 0.2)), relu=(ops.U_RELU, F.relu),
+               gelu=(ops.U_GELU, F.gelu), silu=(ops.U_SILU, F.silu), sigmoid=(ops.U_SIGMOID, torch.sigmoid),
+               invnorm=(ops.U_INVNORM, lambda t: 1.0 / t.sqrt().clamp(min=1e-12)))
+    k, f = fns[kind]
+    x = rn(1, 64, 33).to(dev())
+    if kind == "invnorm":
+        x = x.abs() + 0.1
+    x1, x2 = x.clone().requires_grad_(), x.clone().requires_grad_()
+    y1, y2 = ops.unary(k, x1), f(x2)
+    assert relmax(y1, y2) < 1e-5
+    g1, = torch.autograd.grad(y1.sum() if False else ops.sum_all(ops.mul(y1, y1)), x1, create_graph=True)
+    g2, = torch.autograd.grad((y2 * y2).sum(), x2, create_graph=True)
+    assert relmax(g1, g2) < 1e-4
+    h1, = torch.autograd.grad(ops.sum_all(ops.mul(g1, g1)), x1)
+    h2, = torch.autograd.grad((g2 * g2).sum(), x2)
+    assert relmax(h1, h2) < 1e-3
+
+
+def test_broadcasts_reductions_softmax():
+    from gigagan_pytorch_b200 import ops
+    x = rn(1, 6, 5, 5, 12).to(dev()).requires_grad_()             # (N,H,W,C): 2 samples x 3 scales
+    s = rn(2, 2, 12).to(dev()).requires_grad_()
+    y = ops.scale_channels(x, s, 25, 2)
+    ref = x * s.repeat(3, 1)[:, None, None, :]
+    assert relmax(y, ref) < 1e-6
+    g = torch.randn_like(ref)
+    for m, r in zip(torch.autograd.grad(y, (x, s), g), torch.autograd.grad(ref, (x, s), g)):
+        assert relmax(m, r) < 1e-5
+    assert relmax(ops.mean_hw(x), x.mean(dim=(1, 2))) < 1e-5
+    assert relmax(ops.rowdot(x, x), (x * x).sum(-1)) < 1e-5
+    sm = rn(3, 7, 4, 33).to(dev()).requires_grad_()
+    p = ops.softmax(sm)
+    pr = sm.softmax(-1)
+    assert relmax(p, pr) < 1e-5
+    gp = torch.randn_like(pr)
+    assert relmax(torch.autograd.grad(p, sm, gp)[0], torch.autograd.grad(pr, sm, gp)[0]) < 1e-5
+
+
+def test_resample_and_layout():
+    from gigagan_pytorch_b200 import ops
+    from oracle import gigagan_oracle as O
+    x = rn(1, 2, 5, 8, 8).to(dev()).requires_grad_()
+    xn = ops.to_nhwc(x, 5, torch.float32)
+    y = ops.to_nchw(ops.upsample2x_blur(xn), 5)
+    ref = O.upsample2x(x)
+    assert relmax(y, ref) < 1e-5
+    g = torch.randn_like(ref)
+    assert relmax(torch.autograd.grad(y, x, g)[0], torch.autograd.grad(ref, x, g)[0]) < 1e-5
+    img = torch.rand(2, 3, 32, 32, device=dev())
+    r = ops.to_nchw(ops.resize_bilinear(ops.to_nhwc(img, 3, torch.float32), 8), 3)
+    assert relmax(r, F.interpolate(img, 8, mode="bilinear")) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_ka1_adaptive_conv(dtype, tol):
+    import gigagan_pytorch_b200 as g
+    fx = load("ka1_adaptive_conv.pt")
+    g.set_compute_dtype(dtype)
+    m = g.AdaptiveConv2DMod(8, 6, 3, num_conv_kernels=2).to(dev())
+    with torch.no_grad():
+        m.weights.copy_(fx["weights"])
+    x, mod, km = (fx[k].to(dev()).requires_grad_() for k in ("x", "mod", "kernel_mod"))
+    y = m(x, mod=mod, kernel_mod=km)
+    (y ** 2).sum().backward()
+    assert relmax(y, fx["y"].to(dev())) < tol
+    for t, k in ((m.weights, "dweights"), (x, "dx"), (mod, "dmod"), (km, "dkernel_mod")):
+        assert relmax(t.grad, fx[k].to(dev())) < tol * 3, k
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name,dot", [("l2", False), ("dot", True)])
+def test_ka2_attention_block(name, dot, fused):
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    fx = load(f"ka2_attn_block_{name}.pt")
+    blk = g.SelfAttentionBlock(16, dim_head=8, heads=2, dot_product=dot).to(dev())
+    blk.load_state_dict(fx["sd"])
+    x = fx["x"].to(dev()).requires_grad_()
+    xn = ops.to_nhwc(x, 16, torch.float32)
+    y = ops.to_nchw(blk.forward_nhwc(xn, fused=fused), 16)
+    (y ** 2).sum().backward()
+    assert relmax(y, fx["y"].to(dev())) < 1e-4
+    assert relmax(x.grad, fx["dx"].to(dev())) < 2e-4
+    for k, v in fx["grads"].items():
+        assert relmax(dict(blk.named_parameters())[k].grad, v.to(dev())) < 2e-4, k
+
+
+def test_ka3_style_network():
+    import gigagan_pytorch_b200 as g
+    fx = load("ka3_style_network.pt")
+    sn = g.StyleNetwork(dim=64, depth=4).to(dev())
+    sn.load_state_dict(fx["sd"])
+    assert relmax(sn(fx["z"].to(dev())), fx["y"].to(dev())) < 1e-5
+
+
+# ------------------------------------------------------------------ whole models vs fixtures from the reference
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 4e-2)])
+def test_ka4_generator(dtype, tol):
+    import gigagan_pytorch_b200 as g
+    fx = load("ka4_generator.pt")
+    g.set_compute_dtype(dtype)
+    G = g.Generator(**fx["cfg"]).to(dev())
+    G.load_state_dict(fx["sd"])
+    # the fixture drew its layer noises from CPU randn under manual_seed(noise_seed); reproduce them exactly
+    torch.manual_seed(fx["noise_seed"])
+    res = [4, 8, 16, 32]
+    noises = []
+    for r in res:
+        for _ in range(2):
+            noises.append(torch.randn(2, 1, r, r).to(dev()))
+    rgb, rgbs = G.forward_nhwc(noise=fx["z"].to(dev()), layer_noises=noises)
+    from gigagan_pytorch_b200 import ops
+    out = ops.to_nchw(rgb, 3)
+    assert relmax(out, fx["rgb"].to(dev())) < tol
+    for a, b in zip(rgbs, fx["rgbs"]):
+        assert relmax(ops.to_nchw(a, 3), b.to(dev())) < tol
+    (out ** 2).mean().backward()
+    named = dict(G.named_parameters())
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["grads"].items())
+    assert worst[0] < tol * 5, worst
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 4e-2)])
+def test_ka5_discriminator_step_with_gradient_penalty(dtype, tol):
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    from gigagan_pytorch_b200.trainer import discriminator_hinge_loss, gradient_penalty
+    fx = load("ka5_discriminator.pt")
+    g.set_compute_dtype(dtype)
+    D = g.Discriminator(**fx["cfg"]).to(dev())
+    D.load_state_dict(fx["sd"])
+    D.eval()
+    with torch.no_grad():
+        lo, ms, _ = D(fx["img"].to(dev()), D.real_images_to_rgbs(fx["img"].to(dev())), calc_aux_loss=False)
+    assert relmax(lo, fx["logits"].to(dev())) < tol
+    for a, b in zip(ms, fx["ms"]):
+        assert relmax(a, b.to(dev())) < tol
+    D.train()
+    r = fx["img"].to(dev()).requires_grad_()
+    f = fx["fake"].to(dev()).requires_grad_()
+    frgbs = [t.detach().requires_grad_() for t in D.real_images_to_rgbs(f)]
+    # gradient penalty needs the composed (any-order differentiable) attention
+    dt = dtype
+    fn = ops.to_nhwc(f, 3, dt)
+    rn_ = ops.to_nhwc(r, 3, dt)
+    fl, fm, _ = D.forward_nhwc(fn, [ops.to_nhwc(t, 3, dt) for t in frgbs], True, False, fused_attention=False)
+    rl, rm, _ = D.forward_nhwc(rn_, D.real_images_to_rgbs_nhwc(rn_), True, False, fused_attention=False)
+    div = discriminator_hinge_loss(rl, fl)
+    msl = sum(discriminator_hinge_loss(b, a) for a, b in zip(fm, rm))
+    w = [1.0] + [0.1] * len(rm)
+    gp = gradient_penalty(r, [rl, *rm], w) + gradient_penalty(f, [fl, *fm], w)
+    total = div + gp + 0.1 * msl
+    total.backward()
+    assert relmax(gp, fx["loss"]["gradient_penalty"].to(dev())) < tol * 5
+    assert relmax(total, fx["loss"]["total"].to(dev())) < tol * 5
+    named = dict(D.named_parameters())
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["grads"].items())
+    assert worst[0] < tol * 10, worst
+
+
+def test_fused_attention_matches_composed_large():
+    """size beyond the oracle's reach: fused (online softmax) vs composed (materialised) on 32x32 tokens."""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    torch.manual_seed(0)
+    blk = g.SelfAttentionBlock(64, dim_head=64, heads=2, dot_product=False).to(dev())
+    x = torch.randn(2, 32, 32, 64, device=dev())
+    a = blk.forward_nhwc(x, fused=True)
+    b = blk.forward_nhwc(x, fused=False)
+    assert relmax(a, b) < 1e-4
