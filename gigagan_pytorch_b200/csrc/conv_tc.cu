@@ -1,0 +1,586 @@
+// tcgen05 / TMA implicit-GEMM convolution for NHWC bf16 (sm_100a only).
+//
+//   D[128 pixels x Ntile] (fp32, TMEM)  +=  A_tap[128 pixels x chunk] (smem, K-major)  *  W_tap[Ntile x chunk]^T
+//
+// * one M tile = a (Wt x Ht x Nt) box of output pixels; for every filter tap the SAME TMA tensor map is read at
+//   the box origin shifted by (kx - pad, ky - pad): the hardware's out-of-bounds zero fill is the padding, so there
+//   is no im2col buffer and no boundary code.  stride-2 convolutions use one map per tap over a strided view.
+// * weights are the kernel-layout tensor [Cout][taps][Cin] (optionally per sample) read by a second map.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane, tcgen05.mma cta_group::1 kind::f16, M=128),
+//   warps 2..5 = epilogue (tcgen05.ld -> bias / LeakyReLU / residual / gain -> bf16 -> global).  smem ring of
+//   `stages` (A,B) slabs with full/empty mbarriers; two TMEM accumulator stages so the epilogue of tile i overlaps
+//   the MMAs of tile i+1; persistent CTAs stride over tiles (N-tile fastest so neighbours share the A tile in L2).
+// Replaces: cuDNN conv under nn.Conv2d / F.conv2d, gigagan_pytorch.py:402-409, :1454-1470, :1608-1620, :1656.
+#include <cuda.h>
+#include "gg_internal.h"
+
+#define TC_THREADS 192
+#define TC_MAX_STAGES 8
+
+struct TcP {
+  int N, OH, OW, Cout;
+  int Wt, Ht, Nt, tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles;
+  int Ntile, chunk, cchunks, KH, KW, pad, stride, per_sample;
+  int stages, stage_bytes, a_bytes, b_bytes;
+  int act;
+  float gain;
+  uint32_t idesc, sbo, layout_type, tmem_cols;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a pipeline bug must not hang the GPU
+      printf("conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride between 8-row groups
+  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                     const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+                     const __grid_constant__ CUtensorMap tmB, const TcP p, const float* __restrict__ bias,
+                     const bf16* __restrict__ res, bf16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;                  // SWIZZLE_128B slabs need 1024 B alignment
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bars = base + p.stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(gen_base + p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int kblocks = p.KH * p.KW * p.cchunks;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+        int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+        int ox0 = tw * p.Wt, oy0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Ntile;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
+          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
+          if (p.stride == 1) {
+            int ky = tap / p.KW, kx = tap - ky * p.KW;
+            tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
+          } else {
+            const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
+            tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0, oy0, n0);
+          }
+          tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0 : 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
+          uint64_t da = make_smem_desc(sa, p.sbo, p.layout_type), db = make_smem_desc(sb, p.sbo, p.layout_type);
+          int ksteps = p.chunk >> 4;
+          for (int k = 0; k < ksteps; ++k)
+            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(empty_bar(stage));
+          if (kb == kblocks - 1) tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ww = m % p.Wt, hh = (m / p.Wt) % p.Ht, nn = m / (p.Wt * p.Ht);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
+      int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      int n = tn * p.Nt + nn, co0 = nt * p.Ntile;
+      long pix = ((long)n * p.OH + th * p.Ht + hh) * p.OW + tw * p.Wt + ww;
+      bool live = n < p.N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ntile);
+      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        if (live) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          if (bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + co0 + c0 + j);
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+          }
+          bf16* dst = y + pix * p.Cout + co0 + c0;
+          if (res) {
+            const uint4* rp = (const uint4*)(res + pix * p.Cout + co0 + c0);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const bf16* rb0 = (const bf16*)&r0; const bf16* rb1 = (const bf16*)&r1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(rb0[j]); v[8 + j] += __bfloat162float(rb1[j]); }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* ob0 = (__nv_bfloat162*)&o0; __nv_bfloat162* ob1 = (__nv_bfloat162*)&o1;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ob0[j] = __floats2bfloat162_rn(v[2 * j] * p.gain, v[2 * j + 1] * p.gain);
+            ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j] * p.gain, v[8 + 2 * j + 1] * p.gain);
+          }
+          ((uint4*)dst)[0] = o0;
+          ((uint4*)dst)[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess) fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+static int make_map4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4], int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return gg_fail("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return gg_fail("cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// returns 1 if the shape is not eligible for the tensor-core path
+int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
+                      int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                      float gain, cudaStream_t st) {
+  // ---- eligibility
+  int chunk = Cin >= 64 ? 64 : Cin;
+  if (!(chunk == 16 || chunk == 32 || chunk == 64) || Cin % chunk) return 1;
+  if (Cout % 16 || Cout < 16) return 1;
+  int Ntile = Cout > 256 ? 256 : Cout;
+  if (Cout % Ntile || (Ntile & (Ntile - 1))) return 1;
+  if (stride == 1) { if (OH != H + 2 * pad - KH + 1 || OW != W + 2 * pad - KW + 1) return 1; }
+  else if (stride == 2) { if (pad != 0 || KH != KW || KH > 2 || H != 2 * OH || W != 2 * OW) return 1; }
+  else return 1;
+  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 4 || OH < 4) return 1;
+  int Wt = OW < 16 ? OW : 16;
+  int Ht = OH < 128 / Wt ? OH : 128 / Wt;
+  int Nt = 128 / (Wt * Ht);
+  if (Wt * Ht * Nt != 128) return 1;
+  if (per_sample_w && Nt != 1) return 1;
+  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)res) & 15) return 1;
+
+  TcP p;
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout;
+  p.Wt = Wt; p.Ht = Ht; p.Nt = Nt;
+  p.tiles_w = OW / Wt; p.tiles_h = OH / Ht; p.tiles_n = (N + Nt - 1) / Nt;
+  p.Ntile = Ntile; p.n_tiles_n = Cout / Ntile;
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
+  p.chunk = chunk; p.cchunks = Cin / chunk; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
+  p.per_sample = per_sample_w;
+  p.a_bytes = 128 * chunk * 2; p.b_bytes = Ntile * chunk * 2;
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
+  int stages = (200 * 1024) / p.stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) return 1;
+  p.stages = stages;
+  p.act = act; p.gain = gain;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.sbo = 8 * chunk * 2;                                   // 8 rows of (chunk*2) bytes
+  p.layout_type = chunk == 64 ? 2u : chunk == 32 ? 4u : 6u;
+  uint32_t cols = 2 * Ntile;
+  p.tmem_cols = cols < 32 ? 32 : cols;
+
+  // ---- tensor maps
+  CUtensorMap tmA[4], tmB;
+  int nmaps = stride == 1 ? 1 : KH * KW;
+  for (int t = 0; t < 4; ++t) {
+    int tt = t < nmaps ? t : 0;
+    const bf16* basep = (const bf16*)x;
+    uint64_t dims[4], strides[3];
+    if (stride == 1) {
+      dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = N;
+      strides[0] = (uint64_t)Cin * 2; strides[1] = (uint64_t)W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
+    } else {
+      int ky = tt / KW, kx = tt % KW;
+      basep += ((long)ky * W + kx) * Cin;
+      dims[0] = Cin; dims[1] = OW; dims[2] = OH; dims[3] = N;
+      strides[0] = (uint64_t)2 * Cin * 2; strides[1] = (uint64_t)2 * W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
+    }
+    uint32_t box[4] = {(uint32_t)chunk, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
+    if (make_map4(&tmA[t], basep, dims, strides, box, chunk * 2)) return -1;
+  }
+  {
+    int taps = KH * KW;
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, (uint64_t)(per_sample_w ? N : 1)};
+    uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
+    uint32_t box[4] = {(uint32_t)chunk, 1, (uint32_t)Ntile, 1};
+    if (make_map4(&tmB, w, dims, strides, box, chunk * 2)) return -1;
+  }
+  size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  conv_fprop_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p, bias, (const bf16*)res, (bf16*)y);
+  return gg_check_launch("conv_fprop_tc");
+}
+
+// =================================================================================================
+// Weight gradient on tcgen05:  dW[co, tap, ci] += sum_pixels dY[p, co] * X[p + tap, ci]
+//   D[128 co x Ntile ci] (TMEM) += A[co x 16 pixels] * B[ci x 16 pixels]^T, both operands MN-major: the TMA boxes
+//   (64 channels x Pw x Ph x Pn pixels, 128 B rows, SWIZZLE_128B) are consumed directly with the pixel axis as K.
+//   Work item = (co block, ci block, tap, [image], pixel-range split); partial sums are reduced with fp32 red.add.
+// =================================================================================================
+#define WG_PIX 64     // pixels per pipeline stage (4 UMMA K-steps of 16)
+
+struct WgP {
+  int N, OH, OW, Cout, Cin, taps, KW, pad, stride;
+  int Wt, Ht, Nt, tiles_w, tiles_h, tiles_n, pix_tiles;   // pixel tiling of the OUTPUT grid
+  int co_blocks, ci_blocks, Ntile, nsub_a, nsub_b, splits, per_sample, tiles_per_image, total_items;
+  int stages, stage_bytes, a_bytes, b_bytes;
+  uint32_t idesc, tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;          // stride between 64-element blocks of the MN axis
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride between 8-row (K) groups
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
+                     const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ CUtensorMap tmX3,
+                     const __grid_constant__ CUtensorMap tmDY, const WgP p, float* __restrict__ dw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (base - raw);
+  const uint32_t bars = base + p.stages * p.stage_bytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (TC_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(gen_base + p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item -> (split, image, tap, ci block, co block);  pixel tiles [t0, t1) of the image (or of the whole batch)
+  auto decode = [&](int item, int& cob, int& cib, int& tap, int& img, int& t0, int& t1) {
+    int sp = item % p.splits; item /= p.splits;
+    cib = item % p.ci_blocks; item /= p.ci_blocks;
+    cob = item % p.co_blocks; item /= p.co_blocks;
+    tap = item % p.taps; item /= p.taps;
+    img = item;                                         // 0 unless per_sample
+    int ntiles = p.per_sample ? p.tiles_per_image : p.pix_tiles;
+    int per = (ntiles + p.splits - 1) / p.splits;
+    t0 = sp * per; t1 = min(ntiles, t0 + per);
+    if (p.per_sample) { t0 += img * p.tiles_per_image; t1 += img * p.tiles_per_image; }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        int cob, cib, tap, img, t0, t1;
+        decode(item, cob, cib, tap, img, t0, t1);
+        int ky = tap / p.KW, kx = tap - ky * p.KW;
+        for (int t = t0; t < t1; ++t) {
+          int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, tn = t / (p.tiles_w * p.tiles_h);
+          int ox0 = tw * p.Wt, oy0 = th * p.Ht, n0 = tn * p.Nt;
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
+          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
+          for (int s = 0; s < p.nsub_a; ++s)
+            tma_load_4d(sa + s * (WG_PIX * 128), &tmDY, full_bar(stage), cob * 128 + s * 64, ox0, oy0, n0);
+          for (int s = 0; s < p.nsub_b; ++s) {
+            int c0 = cib * p.Ntile + s * 64;
+            if (p.stride == 1) tma_load_4d(sb + s * (WG_PIX * 128), &tmX0, full_bar(stage), c0, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
+            else {
+              const CUtensorMap* m = tap == 0 ? &tmX0 : tap == 1 ? &tmX1 : tap == 2 ? &tmX2 : &tmX3;
+              tma_load_4d(sb + s * (WG_PIX * 128), m, full_bar(stage), c0, ox0, oy0, n0);
+            }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t lbo_a = p.nsub_a > 1 ? WG_PIX * 128 : 0, lbo_b = WG_PIX * 128;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int cob, cib, tap, img, t0, t1;
+      decode(item, cob, cib, tap, img, t0, t1);
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
+#pragma unroll
+          for (int k = 0; k < WG_PIX / 16; ++k) {
+            uint64_t da = make_smem_desc_mn(sa + k * 2048, lbo_a, 1024), db = make_smem_desc_mn(sb + k * 2048, lbo_b, 1024);
+            tc_mma_f16(d_tmem, da, db, p.idesc, (t > t0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));
+          if (t == t1 - 1) tc_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+      if (t1 > t0) { if (++acc == 2) { acc = 0; acc_phase ^= 1u; } }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      int cob, cib, tap, img, t0, t1;
+      decode(item, cob, cib, tap, img, t0, t1);
+      if (t1 <= t0) continue;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      int co = cob * 128 + row;
+      bool live = co < p.Cout;
+      float* dst = dw + (((long)img * p.Cout + co) * p.taps + tap) * p.Cin + cib * p.Ntile;
+      uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ntile);
+      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
+        uint32_t r[16];
+        tc_ld16(taddr + c0, r);
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// dw must be zero-filled by the caller of this launcher (done here with a memset on the stream).
+int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                      int KH, int KW, int stride, int pad, int per_sample_w, cudaStream_t st) {
+  if (Cin % 16 || Cout % 16 || Cin < 16 || Cout < 16) return 1;
+  if (Cin > 256 && Cin % 256) return 1;
+  if (Cin > 64 && Cin % 64) return 1;
+  if (Cout > 64 && Cout % 64) return 1;
+  if (stride == 1) { if (OH != H + 2 * pad - KH + 1 || OW != W + 2 * pad - KW + 1) return 1; }
+  else if (stride == 2) { if (pad != 0 || KH != KW || KH > 2 || H != 2 * OH || W != 2 * OW) return 1; }
+  else return 1;
+  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 4 || OH < 4) return 1;
+  int Wt = OW < 16 ? OW : 16;
+  int Ht = OH < WG_PIX / Wt ? OH : WG_PIX / Wt;
+  int Nt = WG_PIX / (Wt * Ht);
+  if (Wt * Ht * Nt != WG_PIX) return 1;
+  if (per_sample_w && Nt != 1) return 1;
+  if (N % Nt) return 1;                               // zero-filled phantom images would be harmless, keep it exact
+  if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return 1;
+  WgP p;
+  p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.Cin = Cin; p.taps = KH * KW; p.KW = KW; p.pad = pad; p.stride = stride;
+  p.Wt = Wt; p.Ht = Ht; p.Nt = Nt; p.tiles_w = OW / Wt; p.tiles_h = OH / Ht; p.tiles_n = N / Nt;
+  p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_per_image = p.tiles_w * p.tiles_h;
+  p.co_blocks = (Cout + 127) / 128;
+  p.Ntile = Cin > 256 ? 256 : Cin;
+  p.ci_blocks = Cin / p.Ntile;
+  p.nsub_a = Cout > 64 ? 2 : 1;
+  p.nsub_b = (p.Ntile + 63) / 64;
+  p.per_sample = per_sample_w;
+  int base_items = p.co_blocks * p.ci_blocks * p.taps * (per_sample_w ? N : 1);
+  int ntiles = per_sample_w ? p.tiles_per_image : p.pix_tiles;
+  int splits = 1;
+  while (base_items * splits < 3 * num_sms() && ntiles / (splits * 2) >= 8) splits *= 2;
+  p.splits = splits;
+  p.total_items = base_items * splits;
+  p.a_bytes = p.nsub_a * WG_PIX * 128; p.b_bytes = p.nsub_b * WG_PIX * 128;
+  p.stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (200 * 1024) / p.stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  p.stages = stages;
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  uint32_t cols = 2 * p.Ntile;
+  p.tmem_cols = cols < 32 ? 32 : cols;
+
+  CUtensorMap tmX[4], tmDY;
+  int nmaps = stride == 1 ? 1 : KH * KW;
+  for (int t = 0; t < 4; ++t) {
+    int tt = t < nmaps ? t : 0;
+    const bf16* basep = (const bf16*)x;
+    uint64_t dims[4], strides[3];
+    if (stride == 1) {
+      dims[0] = Cin; dims[1] = W; dims[2] = H; dims[3] = N;
+      strides[0] = (uint64_t)Cin * 2; strides[1] = (uint64_t)W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
+    } else {
+      int ky = tt / KW, kx = tt % KW;
+      basep += ((long)ky * W + kx) * Cin;
+      dims[0] = Cin; dims[1] = OW; dims[2] = OH; dims[3] = N;
+      strides[0] = (uint64_t)2 * Cin * 2; strides[1] = (uint64_t)2 * W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
+    }
+    uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
+    if (make_map4(&tmX[t], basep, dims, strides, box, 128)) return -1;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
+    uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)OW * Cout * 2, (uint64_t)OH * OW * Cout * 2};
+    uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
+    if (make_map4(&tmDY, dy, dims, strides, box, 128)) return -1;
+  }
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(per_sample_w ? N : 1) * Cout * KH * KW * Cin, st);
+  size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+  conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmX[0], tmX[1], tmX[2], tmX[3], tmDY, p, dw);
+  return gg_check_launch("conv_wgrad_tc");
+}

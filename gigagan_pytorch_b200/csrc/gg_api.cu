@@ -33,11 +33,14 @@ int gg_has_tcgen05(void) {
 #endif
 }
 
+static int g_flags = 0;
+int gg_set_flags(int flags) { int o = g_flags; g_flags = flags; return o; }
+
 int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                     int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
                     float gain, int dtype, gg_stream_t stream) {
 #ifndef GG_NO_TC
-  if (dtype == GG_BF16) {
+  if (dtype == GG_BF16 && !(g_flags & 1)) {
     int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ST);
     if (r <= 0) return r;
   }
@@ -50,6 +53,12 @@ int gg_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W
 }
 int gg_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                     int KH, int KW, int stride, int pad, int per_sample_w, int dtype, gg_stream_t stream) {
+#ifndef GG_NO_TC
+  if (dtype == GG_BF16 && !(g_flags & 1)) {
+    int r = ggi_tc_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, ST);
+    if (r <= 0) return r;
+  }
+#endif
   return ggi_simt_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, dtype, ST);
 }
 int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,

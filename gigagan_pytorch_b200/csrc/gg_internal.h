@@ -44,3 +44,5 @@ int ggi_incr(int* p, cudaStream_t st);
 int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                       int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
                       float gain, cudaStream_t st);
+int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                      int KH, int KW, int stride, int pad, int per_sample_w, cudaStream_t st);

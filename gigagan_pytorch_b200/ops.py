@@ -87,6 +87,13 @@ def _conv_fprop_raw(x, wk, bias, res, g, out_c):
 def _conv_dgrad_raw(gy, wk, g, in_shape):
     n, h, w, cin = in_shape
     _, oh, ow, cout = gy.shape
+    if g.stride == 1:
+        # data gradient of a stride-1 convolution == convolution of dy with the spatially flipped, in/out-swapped
+        # filter and padding k-1-pad: reuse the forward kernel (tcgen05 when eligible).
+        wt = wk.flip((-3, -2)).transpose(-4, -1).contiguous()          # ([N,]Cin,KH,KW,Cout)
+        gt = ConvGeom(g.kh, g.kw, 1, g.kh - 1 - g.pad, g.per_sample)
+        assert g.kh == g.kw
+        return _conv_fprop_raw(gy, wt, None, None, gt, cin)
     dx = torch.empty(in_shape, dtype=gy.dtype, device=gy.device)
     call("gg_conv2d_dgrad", _p(gy), _p(wk), _p(dx), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
          int(g.per_sample), _dt(gy), _st())

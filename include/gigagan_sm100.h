@@ -25,6 +25,8 @@ const char* gg_last_error(void);
 int gg_version(void);
 /* 1 when this build contains the tcgen05/TMA kernels (always, for sm_100a). */
 int gg_has_tcgen05(void);
+/* bit 0: route every convolution to the FFMA kernels (testing the tcgen05 path against them). Returns old flags. */
+int gg_set_flags(int flags);
 
 /* ---- convolution family (replaces F.conv2d / nn.Conv2d: gigagan_pytorch.py:402-409 grouped per-sample conv of
  * AdaptiveConv2DMod; :1608-1620, :292, :1454-1470, :1656 discriminator convs; unet_upsampler.py:82-160).

@@ -48,12 +48,13 @@ def rn(k, *s):
 def test_conv_family(cfg, dtype, tol):
     from gigagan_pytorch_b200 import ops
     c = cfg
-    x = rn(1, c["n"], c["ci"], c["h"], c["w"]).to(dev())
-    w = (rn(2, c["co"], c["ci"], c["k"], c["k"]) * 0.2).to(dev()).requires_grad_()
+    rd = (lambda t: t.to(dtype).float())          # the reference sees the same storage rounding as the kernel
+    x = rd(rn(1, c["n"], c["ci"], c["h"], c["w"])).to(dev())
+    w = rd(rn(2, c["co"], c["ci"], c["k"], c["k"]) * 0.2).to(dev()).requires_grad_()
     b = rn(3, c["co"]).to(dev()).requires_grad_()
     xr = x.clone().requires_grad_()
     ref = F.leaky_relu(F.conv2d(xr, w, b, stride=c["s"], padding=c["p"]), 0.2)
-    gy = torch.randn_like(ref)
+    gy = rd(torch.randn_like(ref))
     gx_ref, gw_ref, gb_ref = torch.autograd.grad(ref, (xr, w, b), gy)
     xn = x.permute(0, 2, 3, 1).contiguous().to(dtype).requires_grad_()
     y = ops.conv2d(xn, w, b, stride=c["s"], pad=c["p"], act=1)
@@ -62,6 +63,55 @@ def test_conv_family(cfg, dtype, tol):
     assert relmax(gx.permute(0, 3, 1, 2), gx_ref) < tol * 2
     assert relmax(gw, gw_ref) < tol * 2
     assert relmax(gb, gb_ref) < tol * 2
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=4, h=16, w=16, ci=64, co=64, k=3, s=1, p=1, ps=False), dict(n=2, h=32, w=32, ci=128, co=256, k=3, s=1, p=1, ps=False),
+    dict(n=16, h=4, w=4, ci=512, co=512, k=3, s=1, p=1, ps=False), dict(n=3, h=8, w=8, ci=64, co=128, k=1, s=1, p=0, ps=False),
+    dict(n=2, h=64, w=64, ci=16, co=16, k=3, s=1, p=1, ps=False), dict(n=2, h=32, w=32, ci=32, co=64, k=3, s=1, p=1, ps=False),
+    dict(n=2, h=16, w=16, ci=64, co=128, k=2, s=2, p=0, ps=False), dict(n=2, h=16, w=16, ci=64, co=128, k=1, s=2, p=0, ps=False),
+    dict(n=3, h=16, w=16, ci=64, co=32, k=3, s=1, p=1, ps=True), dict(n=2, h=8, w=8, ci=256, co=1024, k=1, s=1, p=0, ps=False),
+])
+def test_tcgen05_conv_matches_ffma(cfg):
+    """bf16 tensor-core implicit GEMM (TMA taps, TMEM accumulators) vs the FFMA kernel on identical bf16 inputs;
+    both accumulate in fp32, so they agree to accumulation-order noise (bit-exactness is not defined for fp)."""
+    from gigagan_pytorch_b200 import ops, _lib
+    c = cfg
+    dt = torch.bfloat16
+    x = rn(1, c["n"], c["h"], c["w"], c["ci"]).to(dev()).to(dt)
+    wshape = ((c["n"],) if c["ps"] else ()) + (c["co"], c["k"], c["k"], c["ci"])
+    w = (rn(2, *wshape) * (c["ci"] * c["k"] * c["k"]) ** -0.5).to(dev()).to(dt)
+    bias = rn(3, c["co"]).to(dev())
+    g = ops.ConvGeom(c["k"], c["k"], c["s"], c["p"], c["ps"], act=1)
+    L = _lib.lib()
+    y_tc = ops._conv_fprop_raw(x, w, bias, None, g, c["co"])
+    old = L.gg_set_flags(1)
+    try:
+        y_ff = ops._conv_fprop_raw(x, w, bias, None, g, c["co"])
+    finally:
+        L.gg_set_flags(old)
+    torch.cuda.synchronize()
+    assert relmax(y_tc, y_ff) < 2e-2 and (y_tc.float() - y_ff.float()).abs().mean().item() < 2e-3 * y_ff.float().abs().mean().item()
+    # residual + gain epilogue
+    res = rn(4, *y_ff.shape).to(dev()).to(dt)
+    g2 = ops.ConvGeom(c["k"], c["k"], c["s"], c["p"], c["ps"], act=0, gain=2 ** -0.5)
+    a = ops._conv_fprop_raw(x, w, bias, res, g2, c["co"])
+    old = L.gg_set_flags(1)
+    try:
+        b = ops._conv_fprop_raw(x, w, bias, res, g2, c["co"])
+    finally:
+        L.gg_set_flags(old)
+    assert relmax(a, b) < 2e-2
+    # weight gradient (MN-major tcgen05 operands, split over pixel ranges, fp32 red.add)
+    gy = rn(5, *y_ff.shape).to(dev()).to(dt)
+    gp = ops.ConvGeom(c["k"], c["k"], c["s"], c["p"], c["ps"])
+    dw_tc = ops._conv_wgrad_raw(x, gy, gp)
+    old = L.gg_set_flags(1)
+    try:
+        dw_ff = ops._conv_wgrad_raw(x, gy, gp)
+    finally:
+        L.gg_set_flags(old)
+    assert relmax(dw_tc, dw_ff) < 1e-3, relmax(dw_tc, dw_ff)
 
 
 def test_conv_double_backward_fp32():
