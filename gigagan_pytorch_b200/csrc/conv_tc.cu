@@ -11,11 +11,7 @@
 //   `stages` (A,B) slabs with full/empty mbarriers; two TMEM accumulator stages so the epilogue of tile i overlaps
 //   the MMAs of tile i+1; persistent CTAs stride over tiles (N-tile fastest so neighbours share the A tile in L2).
 // Replaces: cuDNN conv under nn.Conv2d / F.conv2d, gigagan_pytorch.py:402-409, :1454-1470, :1608-1620, :1656.
-#include <cuda.h>
-#include "gg_internal.h"
-
-#define TC_THREADS 192
-#define TC_MAX_STAGES 8
+#include "tc_common.cuh"
 
 struct TcP {
   int N, OH, OW, Cout;
@@ -24,63 +20,9 @@ struct TcP {
   int stages, stage_bytes, a_bytes, b_bytes;
   int act;
   float gain;
+  long y_off, y_sn, y_sh, y_sw;          // output addressing (elements): y_off + n*y_sn + oy*y_sh + ox*y_sw + co
   uint32_t idesc, sbo, layout_type, tmem_cols;
 };
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long t0 = clock64();
-  while (true) {
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a pipeline bug must not hang the GPU
-      printf("conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride between 8-row groups
-  d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
 
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -174,7 +116,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
       int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
       int n = tn * p.Nt + nn, co0 = nt * p.Ntile;
-      long pix = ((long)n * p.OH + th * p.Ht + hh) * p.OW + tw * p.Wt + ww;
+      long pix = p.y_off + (long)n * p.y_sn + (long)(th * p.Ht + hh) * p.y_sh + (long)(tw * p.Wt + ww) * p.y_sw;
       bool live = n < p.N;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -194,9 +136,9 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
           }
-          bf16* dst = y + pix * p.Cout + co0 + c0;
+          bf16* dst = y + pix + co0 + c0;
           if (res) {
-            const uint4* rp = (const uint4*)(res + pix * p.Cout + co0 + c0);
+            const uint4* rp = (const uint4*)(res + pix + co0 + c0);
             uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
             const bf16* rb0 = (const bf16*)&r0; const bf16* rb1 = (const bf16*)&r1;
 #pragma unroll
@@ -241,7 +183,7 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_map4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
+int tc_make_map4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                      const uint32_t box[4], int swizzle_bytes) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return gg_fail("cuTensorMapEncodeTiled unavailable");
@@ -258,7 +200,7 @@ static int make_map4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], co
 }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int tc_num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -271,7 +213,7 @@ static int num_sms() {
 // returns 1 if the shape is not eligible for the tensor-core path
 int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                       int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
-                      float gain, cudaStream_t st) {
+                      float gain, const long* ystr, cudaStream_t st) {
   // ---- eligibility
   int chunk = Cin >= 64 ? 64 : Cin;
   if (!(chunk == 16 || chunk == 32 || chunk == 64) || Cin % chunk) return 1;
@@ -304,6 +246,10 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   if (stages < 2) return 1;
   p.stages = stages;
   p.act = act; p.gain = gain;
+  if (ystr) {
+    if ((ystr[0] | ystr[1] | ystr[2] | ystr[3]) & 7) return 1;
+    p.y_off = ystr[0]; p.y_sn = ystr[1]; p.y_sh = ystr[2]; p.y_sw = ystr[3];
+  } else { p.y_off = 0; p.y_sn = (long)OH * OW * Cout; p.y_sh = (long)OW * Cout; p.y_sw = Cout; }
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.sbo = 8 * chunk * 2;                                   // 8 rows of (chunk*2) bytes
   p.layout_type = chunk == 64 ? 2u : chunk == 32 ? 4u : 6u;
@@ -327,14 +273,14 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
       strides[0] = (uint64_t)2 * Cin * 2; strides[1] = (uint64_t)2 * W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
     }
     uint32_t box[4] = {(uint32_t)chunk, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
-    if (make_map4(&tmA[t], basep, dims, strides, box, chunk * 2)) return -1;
+    if (tc_make_map4(&tmA[t], basep, dims, strides, box, chunk * 2)) return -1;
   }
   {
     int taps = KH * KW;
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)taps, (uint64_t)Cout, (uint64_t)(per_sample_w ? N : 1)};
     uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)taps * Cin * 2, (uint64_t)Cout * taps * Cin * 2};
     uint32_t box[4] = {(uint32_t)chunk, 1, (uint32_t)Ntile, 1};
-    if (make_map4(&tmB, w, dims, strides, box, chunk * 2)) return -1;
+    if (tc_make_map4(&tmB, w, dims, strides, box, chunk * 2)) return -1;
   }
   size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4) + 16;
   static bool attr_set = false;
@@ -342,7 +288,7 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
     cudaFuncSetAttribute(conv_fprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  int grid = p.total_tiles < tc_num_sms() ? p.total_tiles : tc_num_sms();
   conv_fprop_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p, bias, (const bf16*)res, (bf16*)y);
   return gg_check_launch("conv_fprop_tc");
 }
@@ -362,16 +308,6 @@ struct WgP {
   int stages, stage_bytes, a_bytes, b_bytes;
   uint32_t idesc, tmem_cols;
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)(lbo_bytes >> 4) << 16;          // stride between 64-element blocks of the MN axis
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;          // stride between 8-row (K) groups
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
-  return d;
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_constant__ CUtensorMap tmX1,
@@ -537,7 +473,7 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   int base_items = p.co_blocks * p.ci_blocks * p.taps * (per_sample_w ? N : 1);
   int ntiles = per_sample_w ? p.tiles_per_image : p.pix_tiles;
   int splits = 1;
-  while (base_items * splits < 3 * num_sms() && ntiles / (splits * 2) >= 8) splits *= 2;
+  while (base_items * splits < 3 * tc_num_sms() && ntiles / (splits * 2) >= 8) splits *= 2;
   p.splits = splits;
   p.total_items = base_items * splits;
   p.a_bytes = p.nsub_a * WG_PIX * 128; p.b_bytes = p.nsub_b * WG_PIX * 128;
@@ -565,13 +501,13 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
       strides[0] = (uint64_t)2 * Cin * 2; strides[1] = (uint64_t)2 * W * Cin * 2; strides[2] = (uint64_t)H * W * Cin * 2;
     }
     uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
-    if (make_map4(&tmX[t], basep, dims, strides, box, 128)) return -1;
+    if (tc_make_map4(&tmX[t], basep, dims, strides, box, 128)) return -1;
   }
   {
     uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)OW, (uint64_t)OH, (uint64_t)N};
     uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)OW * Cout * 2, (uint64_t)OH * OW * Cout * 2};
     uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
-    if (make_map4(&tmDY, dy, dims, strides, box, 128)) return -1;
+    if (tc_make_map4(&tmDY, dy, dims, strides, box, 128)) return -1;
   }
   cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(per_sample_w ? N : 1) * Cout * KH * KW * Cin, st);
   size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4) + 16;
@@ -580,7 +516,7 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
     cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  int grid = p.total_items < num_sms() ? p.total_items : num_sms();
+  int grid = p.total_items < tc_num_sms() ? p.total_items : tc_num_sms();
   conv_wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmX[0], tmX[1], tmX[2], tmX[3], tmDY, p, dw);
   return gg_check_launch("conv_wgrad_tc");
 }

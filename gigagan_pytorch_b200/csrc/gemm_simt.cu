@@ -16,6 +16,7 @@ struct ConvP {
   int groups;
   int act;              // 0 none, 1 leaky-relu(0.2)
   float gain;
+  long y_off, y_sn, y_sh, y_sw;   // fprop output addressing (elements); dense when y_sw == Cout etc.
 };
 
 // 4x4 register micro-tile FMA over one BK slab held in shared memory.
@@ -125,13 +126,16 @@ __global__ void __launch_bounds__(256) conv_gemm_simt(const T* __restrict__ src,
       int n = n0 + tx * 4 + j;
       if (n >= Ncols) continue;
       float v = acc[i][j];
+      long o = m * Ncols + n;
       if (MODE == 0) {
+        int img = (int)(m / (p.OH * p.OW)), rr = (int)(m % (p.OH * p.OW));
+        o = p.y_off + (long)img * p.y_sn + (long)(rr / p.OW) * p.y_sh + (long)(rr % p.OW) * p.y_sw + n;
         if (bias) v += bias[n];
         if (p.act == 1) v = v > 0.f ? v : 0.2f * v;
-        if (res) v += ldf(res + m * Ncols + n);
+        if (res) v += ldf(res + o);
         v *= p.gain;
       }
-      stf(dst + m * Ncols + n, v);
+      stf(dst + o, v);
     }
   }
 }
@@ -249,6 +253,7 @@ static int fill_convp(ConvP& p, int N, int H, int W, int Cin, int OH, int OW, in
                       int pad, int per_sample_w, int mode_rows_on_input) {
   p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.OH = OH; p.OW = OW; p.Cout = Cout; p.KH = KH; p.KW = KW;
   p.stride = stride; p.pad = pad; p.act = 0; p.gain = 1.f;
+  p.y_off = 0; p.y_sn = (long)OH * OW * Cout; p.y_sh = (long)OW * Cout; p.y_sw = Cout;
   long rows_per_img = mode_rows_on_input ? (long)H * W : (long)OH * OW;
   if (per_sample_w) { p.groups = N; p.m_per_group = (int)rows_per_img; p.w_gstride = (long)Cout * KH * KW * Cin; }
   else {
@@ -260,10 +265,11 @@ static int fill_convp(ConvP& p, int N, int H, int W, int Cin, int OH, int OW, in
 
 int ggi_simt_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                        int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
-                       float gain, int dtype, cudaStream_t st) {
+                       float gain, const long* ystr, int dtype, cudaStream_t st) {
   ConvP p;
   if (fill_convp(p, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, 0)) return -1;
   p.act = act; p.gain = gain;
+  if (ystr) { p.y_off = ystr[0]; p.y_sn = ystr[1]; p.y_sh = ystr[2]; p.y_sw = ystr[3]; }
   dim3 grid(p.groups * gg_cdiv(p.m_per_group, BM), gg_cdiv(Cout, BN));
   GG_DISPATCH(dtype, (conv_gemm_simt<T, 0><<<grid, 256, 0, st>>>((const T*)x, (const T*)w, bias, (const T*)res, (T*)y, p)));
   return gg_check_launch("conv_fprop_simt");

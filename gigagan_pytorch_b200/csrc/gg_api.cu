@@ -21,10 +21,12 @@ int gg_check_launch(const char* what) {
 }
 
 #define ST ((cudaStream_t)stream)
+static int g_flags = 0;
 
 extern "C" {
 const char* gg_last_error(void) { return g_err; }
 int gg_version(void) { return 100; }
+int gg_set_flags(int flags) { int o = g_flags; g_flags = flags; return o; }
 int gg_has_tcgen05(void) {
 #ifdef GG_NO_TC
   return 0;
@@ -33,19 +35,28 @@ int gg_has_tcgen05(void) {
 #endif
 }
 
-static int g_flags = 0;
-int gg_set_flags(int flags) { int o = g_flags; g_flags = flags; return o; }
-
-int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
-                    int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
-                    float gain, int dtype, gg_stream_t stream) {
+static int conv_fprop_any(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
+                          int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                          float gain, const long* ystr, int dtype, cudaStream_t st) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ST);
+    int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, st);
     if (r <= 0) return r;
   }
 #endif
-  return ggi_simt_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, dtype, ST);
+  return ggi_simt_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, dtype, st);
+}
+int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
+                    int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                    float gain, int dtype, gg_stream_t stream) {
+  return conv_fprop_any(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, nullptr, dtype, ST);
+}
+int gg_conv2d_fprop_strided(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Cin,
+                            int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                            float gain, int64_t y_off, int64_t y_sn, int64_t y_sh, int64_t y_sw, int dtype,
+                            gg_stream_t stream) {
+  long ystr[4] = {(long)y_off, (long)y_sn, (long)y_sh, (long)y_sw};
+  return conv_fprop_any(x, w, bias, nullptr, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, dtype, ST);
 }
 int gg_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                     int KH, int KW, int stride, int pad, int per_sample_w, int dtype, gg_stream_t stream) {
@@ -63,6 +74,12 @@ int gg_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int 
 }
 int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
            const int64_t* h_sa, const int64_t* h_sb, const int64_t* h_sc, float alpha, int dtype, gg_stream_t stream) {
+#ifndef GG_NO_TC
+  if (dtype == GG_BF16 && !(g_flags & 1)) {
+    int r = ggi_tc_bmm(A, B, bias, C, b1, b2, M, N, K, (const long*)h_sa, (const long*)h_sb, (const long*)h_sc, alpha, ST);
+    if (r <= 0) return r;
+  }
+#endif
   return ggi_simt_bmm(A, B, bias, C, b1, b2, M, N, K, (const long*)h_sa, (const long*)h_sb, (const long*)h_sc, alpha, dtype, ST);
 }
 int gg_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, int64_t n, int dtype, gg_stream_t stream) {
@@ -79,7 +96,9 @@ int gg_red_rowdot(const void* a, const void* b, float* out, int64_t R, int C, in
 int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype, gg_stream_t stream) {
   return ggi_red_dot_sc(a, b, out, R, C, P, Ns, dtype, ST);
 }
-int gg_softmax_rows(const void* s, void* p, int64_t R, int C, int dtype, gg_stream_t stream) { return ggi_softmax_rows(s, p, R, C, dtype, ST); }
+int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C, int P, int Ns, int dtype, gg_stream_t stream) {
+  return ggi_softmax_rows(s, bias, p, R, C, P, Ns, dtype, ST);
+}
 int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                   int Ty, const int* ix, const float* wx, int Tx, int dtype, gg_stream_t stream) {
   return ggi_resample2d(x, y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx, dtype, ST);
@@ -93,13 +112,13 @@ int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx
   return ggi_noise_act_bwd(y, gy, noise, dx, dwn, R, C, dtype, ST);
 }
 int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, gg_stream_t stream) {
-  return ggi_adaconv_weights_fwd(bank, mod, kmod, w, attn, dinv, B, n, O, I, KK, demod, eps, dtype, ST);
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, gg_stream_t stream) {
+  return ggi_adaconv_weights_fwd(bank, mod, kmod, w, attn, dinv, B, n, O, I, KK, demod, eps, Opad, dtype, ST);
 }
 int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, gg_stream_t stream) {
-  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, ST);
+                           int demod, float eps, int Opad, gg_stream_t stream) {
+  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, Opad, ST);
 }
 int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, int B, int heads,
                 int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,

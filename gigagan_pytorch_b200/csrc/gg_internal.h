@@ -4,7 +4,7 @@
 
 int ggi_simt_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                         int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
-                        float gain, int dtype, cudaStream_t st);
+                        float gain, const long* ystr, int dtype, cudaStream_t st);
 int ggi_simt_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                         int KH, int KW, int stride, int pad, int per_sample_w, int dtype, cudaStream_t st);
 int ggi_simt_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
@@ -17,7 +17,7 @@ int ggi_pw_axpby(float alpha, const void* x, float beta, const void* y, void* ou
 int ggi_pw_bcast(const void* x, const float* s, void* out, long R, int C, int P, int Ns, int mode, int op, int dtype, cudaStream_t st);
 int ggi_red_rowdot(const void* a, const void* b, float* out, long R, int C, int dtype, cudaStream_t st);
 int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int dtype, cudaStream_t st);
-int ggi_softmax_rows(const void* s, void* p, long R, int C, int dtype, cudaStream_t st);
+int ggi_softmax_rows(const void* s, const float* bias, void* p, long R, int C, int P, int Ns, int dtype, cudaStream_t st);
 int ggi_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                    int Ty, const int* ix, const float* wx, int Tx, int dtype, cudaStream_t st);
 int ggi_nchw_to_nhwc(const float* src, void* dst, int N, int C, int HW, int Cp, int dtype, cudaStream_t st);
@@ -25,10 +25,10 @@ int ggi_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, int Cp, 
 int ggi_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, long R, int C, int dtype, cudaStream_t st);
 int ggi_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, long R, int C, int dtype, cudaStream_t st);
 int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                            int B, int n, int O, int I, int KK, int demod, float eps, int dtype, cudaStream_t st);
+                            int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, cudaStream_t st);
 int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                             float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                            int demod, float eps, cudaStream_t st);
+                            int demod, float eps, int Opad, cudaStream_t st);
 int ggi_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, int B, int heads,
                  int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale, int mode, int dtype,
                  cudaStream_t st);
@@ -43,6 +43,8 @@ int ggi_incr(int* p, cudaStream_t st);
 // tcgen05 path (conv_tc.cu).  Return 1 when the shape is not eligible (caller falls through to FFMA), 0 ok, <0 error.
 int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W,
                       int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
-                      float gain, cudaStream_t st);
+                      float gain, const long* ystr, cudaStream_t st);
 int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
                       int KH, int KW, int stride, int pad, int per_sample_w, cudaStream_t st);
+int ggi_tc_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
+               const long* sa, const long* sb, const long* sc, float alpha, cudaStream_t st);

@@ -5,6 +5,32 @@
 // :378-400 (weight modulation/demodulation), :925-940 (Noise), :588 (softmax), optimizer.py:34 (AdamW).
 #include "gg_common.cuh"
 
+// 16-byte vector access: 8 bf16 or 4 fp32 per thread
+template <typename T> struct VecN { static constexpr int N = 16 / sizeof(T); };
+template <typename T> __device__ __forceinline__ void ldv(const T* p, float* out);
+template <> __device__ __forceinline__ void ldv<float>(const float* p, float* out) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldv<bf16>(const bf16* p, float* out) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+}
+template <typename T> __device__ __forceinline__ void stv(T* p, const float* in);
+template <> __device__ __forceinline__ void stv<float>(float* p, const float* in) {
+  *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+}
+template <> __device__ __forceinline__ void stv<bf16>(bf16* p, const float* in) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
+
 // ------------------------------------------------------------------ unary maps
 enum { U_LRELU = 0, U_RELU = 1, U_GELU = 2, U_SILU = 3, U_SIGMOID = 4, U_INVNORM = 5 };
 
@@ -41,7 +67,26 @@ __device__ __forceinline__ float unary_eval(int kind, float x) {
 // level 0: out = f(x); level 1: out = a * f'(x); level 2: out = a * b * f''(x)
 template <typename T, int LEVEL>
 __global__ void unary_kernel(int kind, const T* __restrict__ x, const T* __restrict__ a, const T* __restrict__ b,
-                             T* __restrict__ out, long n) {
+                             T* __restrict__ out, long n, int vec) {
+  constexpr int V = VecN<T>::N;
+  if (vec) {
+    long nv = n / V;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+      float xv[V], av[V], bv[V], o[V];
+      ldv(x + i * V, xv);
+      if (LEVEL >= 1) ldv(a + i * V, av);
+      if (LEVEL >= 2) ldv(b + i * V, bv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float v = unary_eval<LEVEL>(kind, xv[j]);
+        if (LEVEL >= 1) v *= av[j];
+        if (LEVEL >= 2) v *= bv[j];
+        o[j] = v;
+      }
+      stv(out + i * V, o);
+    }
+    return;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float v = unary_eval<LEVEL>(kind, ldf(x + i));
     if (LEVEL >= 1) v *= ldf(a + i);
@@ -52,24 +97,51 @@ __global__ void unary_kernel(int kind, const T* __restrict__ x, const T* __restr
 
 int ggi_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, long n, int dtype,
                 cudaStream_t st) {
-  int blocks = gg_blocks(n, 256);
+  int esz = dtype == GG_F32 ? 4 : 2;
+  int vec = (n % (16 / esz) == 0) && al16(x) && al16(out) && (level < 1 || al16(a)) && (level < 2 || al16(b));
+  int blocks = gg_blocks(vec ? n / (16 / esz) : n, 256);
   GG_DISPATCH(dtype, {
-    if (level == 0) unary_kernel<T, 0><<<blocks, 256, 0, st>>>(kind, (const T*)x, nullptr, nullptr, (T*)out, n);
-    else if (level == 1) unary_kernel<T, 1><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, nullptr, (T*)out, n);
-    else unary_kernel<T, 2><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, (const T*)b, (T*)out, n);
+    if (level == 0) unary_kernel<T, 0><<<blocks, 256, 0, st>>>(kind, (const T*)x, nullptr, nullptr, (T*)out, n, vec);
+    else if (level == 1) unary_kernel<T, 1><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, nullptr, (T*)out, n, vec);
+    else unary_kernel<T, 2><<<blocks, 256, 0, st>>>(kind, (const T*)x, (const T*)a, (const T*)b, (T*)out, n, vec);
   });
   return gg_check_launch("unary");
 }
 
 // ------------------------------------------------------------------ binary maps
 template <typename T>
-__global__ void mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long n) {
+__global__ void mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long n, int vec) {
+  constexpr int V = VecN<T>::N;
+  if (vec) {
+    long nv = n / V;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+      float av[V], bv[V];
+      ldv(a + i * V, av); ldv(b + i * V, bv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) av[j] *= bv[j];
+      stv(out + i * V, av);
+    }
+    return;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     stf(out + i, ldf(a + i) * ldf(b + i));
 }
 template <typename T>
 __global__ void axpby_kernel(float alpha, const T* __restrict__ x, float beta, const T* __restrict__ y,
-                             T* __restrict__ out, long n) {
+                             T* __restrict__ out, long n, int vec) {
+  constexpr int V = VecN<T>::N;
+  if (vec) {
+    long nv = n / V;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+      float xv[V], yv[V];
+      ldv(x + i * V, xv);
+      if (y) ldv(y + i * V, yv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) xv[j] = alpha * xv[j] + (y ? beta * yv[j] : 0.f);
+      stv(out + i * V, xv);
+    }
+    return;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     float v = alpha * ldf(x + i);
     if (y) v += beta * ldf(y + i);
@@ -77,11 +149,15 @@ __global__ void axpby_kernel(float alpha, const T* __restrict__ x, float beta, c
   }
 }
 int ggi_pw_mul(const void* a, const void* b, void* out, long n, int dtype, cudaStream_t st) {
-  GG_DISPATCH(dtype, (mul_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n)));
+  int V = dtype == GG_F32 ? 4 : 8;
+  int vec = (n % V == 0) && al16(a) && al16(b) && al16(out);
+  GG_DISPATCH(dtype, (mul_kernel<T><<<gg_blocks(vec ? n / V : n, 256), 256, 0, st>>>((const T*)a, (const T*)b, (T*)out, n, vec)));
   return gg_check_launch("mul");
 }
 int ggi_pw_axpby(float alpha, const void* x, float beta, const void* y, void* out, long n, int dtype, cudaStream_t st) {
-  GG_DISPATCH(dtype, (axpby_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>(alpha, (const T*)x, beta, (const T*)y, (T*)out, n)));
+  int V = dtype == GG_F32 ? 4 : 8;
+  int vec = (n % V == 0) && al16(x) && al16(out) && (!y || al16(y));
+  GG_DISPATCH(dtype, (axpby_kernel<T><<<gg_blocks(vec ? n / V : n, 256), 256, 0, st>>>(alpha, (const T*)x, beta, (const T*)y, (T*)out, n, vec)));
   return gg_check_launch("axpby");
 }
 
@@ -90,8 +166,29 @@ int ggi_pw_axpby(float alpha, const void* x, float beta, const void* y, void* ou
 // op 0: out = x * s ; op 1: out = x + s.   s is always fp32.
 template <typename T>
 __global__ void bcast_kernel(const T* __restrict__ x, const float* __restrict__ s, T* __restrict__ out, long R, int C,
-                             int P, int Ns, int mode, int op) {
+                             int P, int Ns, int mode, int op, int vec) {
+  constexpr int V = VecN<T>::N;
   long n = R * C;
+  if (vec) {
+    long nv = n / V;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < nv; i += (long)gridDim.x * blockDim.x) {
+      long e = i * V, r = e / C;
+      int c = (int)(e - r * C);
+      float xv[V];
+      ldv(x + e, xv);
+      if (mode == 0) {
+        float sv = s[r];
+#pragma unroll
+        for (int j = 0; j < V; ++j) xv[j] = op == 0 ? xv[j] * sv : xv[j] + sv;
+      } else {
+        const float* sp = s + ((r / P) % Ns) * (long)C + c;
+#pragma unroll
+        for (int j = 0; j < V; ++j) xv[j] = op == 0 ? xv[j] * sp[j] : xv[j] + sp[j];
+      }
+      stv(out + e, xv);
+    }
+    return;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     long r = i / C;
     int c = (int)(i % C);
@@ -102,7 +199,9 @@ __global__ void bcast_kernel(const T* __restrict__ x, const float* __restrict__ 
 }
 int ggi_pw_bcast(const void* x, const float* s, void* out, long R, int C, int P, int Ns, int mode, int op, int dtype,
                 cudaStream_t st) {
-  GG_DISPATCH(dtype, (bcast_kernel<T><<<gg_blocks(R * C, 256), 256, 0, st>>>((const T*)x, s, (T*)out, R, C, P, Ns, mode, op)));
+  int V = dtype == GG_F32 ? 4 : 8;
+  int vec = (C % V == 0) && al16(x) && al16(out);
+  GG_DISPATCH(dtype, (bcast_kernel<T><<<gg_blocks(vec ? R * C / V : R * C, 256), 256, 0, st>>>((const T*)x, s, (T*)out, R, C, P, Ns, mode, op, vec)));
   return gg_check_launch("bcast");
 }
 
@@ -158,15 +257,63 @@ int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int 
   return gg_check_launch("dot_sc");
 }
 
-// ------------------------------------------------------------------ row softmax (one CTA per row)
+// ------------------------------------------------------------------ row softmax of (S + bias)
+// bias (optional) is fp32 [Ns][C]; row r uses bias row (r / P) % Ns.  Fast path: one warp per row, the row lives in
+// registers (16-byte loads); generic path: one CTA per row.
+template <typename T, int MAXV>
+__global__ void softmax_rows_warp_kernel(const T* __restrict__ s, const float* __restrict__ bias, T* __restrict__ p,
+                                         long R, int C, int P, int Ns) {
+  constexpr int V = VecN<T>::N;
+  long r = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  int lane = threadIdx.x & 31;
+  const T* sr = s + r * C;
+  const float* br = bias ? bias + ((r / P) % Ns) * (long)C : nullptr;
+  int nvec = C / V;
+  float v[MAXV][V];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+      ldv(sr + vi * V, v[i]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { if (br) v[i][j] += br[vi * V + j]; m = fmaxf(m, v[i][j]); }
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { v[i][j] = __expf(v[i][j] - m); sum += v[i][j]; }
+    }
+  }
+  sum = warp_sum(sum);
+  float inv = 1.f / sum;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[i][j] *= inv;
+      stv(p + r * C + vi * V, v[i]);
+    }
+  }
+}
+
 template <typename T>
-__global__ void softmax_rows_kernel(const T* __restrict__ s, T* __restrict__ p, int C) {
+__global__ void softmax_rows_kernel(const T* __restrict__ s, const float* __restrict__ bias, T* __restrict__ p, int C,
+                                    int P, int Ns) {
   __shared__ float red[32];
   long r = blockIdx.x;
   const T* sr = s + r * C;
+  const float* br = bias ? bias + ((r / P) % Ns) * (long)C : nullptr;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float m = -INFINITY;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, ldf(sr + c));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, ldf(sr + c) + (br ? br[c] : 0.f));
   m = warp_max(m);
   if (lane == 0) red[wid] = m;
   __syncthreads();
@@ -174,17 +321,23 @@ __global__ void softmax_rows_kernel(const T* __restrict__ s, T* __restrict__ p, 
   for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
   __syncthreads();
   float sum = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) sum += __expf(ldf(sr + c) - m);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sum += __expf(ldf(sr + c) + (br ? br[c] : 0.f) - m);
   sum = warp_sum(sum);
   if (lane == 0) red[wid] = sum;
   __syncthreads();
   sum = 0.f;
   for (int i = 0; i < nw; ++i) sum += red[i];
   float inv = 1.f / sum;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) stf(p + r * C + c, __expf(ldf(sr + c) - m) * inv);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) stf(p + r * C + c, __expf(ldf(sr + c) + (br ? br[c] : 0.f) - m) * inv);
 }
-int ggi_softmax_rows(const void* s, void* p, long R, int C, int dtype, cudaStream_t st) {
-  GG_DISPATCH(dtype, (softmax_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)s, (T*)p, C)));
+int ggi_softmax_rows(const void* s, const float* bias, void* p, long R, int C, int P, int Ns, int dtype, cudaStream_t st) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (!bias) { P = 1; Ns = 1; }
+  if (C % V == 0 && C / V <= 32 * 6 && al16(s) && al16(p)) {
+    GG_DISPATCH(dtype, (softmax_rows_warp_kernel<T, 6><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)s, bias, (T*)p, R, C, P, Ns)));
+  } else {
+    GG_DISPATCH(dtype, (softmax_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)s, bias, (T*)p, C, P, Ns)));
+  }
   return gg_check_launch("softmax_rows");
 }
 
@@ -322,7 +475,8 @@ __global__ void adaconv_attn_kernel(const float* __restrict__ kmod, float* __res
 template <typename T>
 __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
                                            const float* __restrict__ attn, T* __restrict__ w,
-                                           float* __restrict__ dinv, int n, int O, int I, int KK, int demod, float eps) {
+                                           float* __restrict__ dinv, int n, int O, int I, int KK, int demod, float eps,
+                                           int Opad) {
   __shared__ float red[32];
   int b = blockIdx.y, o = blockIdx.x;
   int E = I * KK;
@@ -349,7 +503,7 @@ __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const
     float v = 0.f;
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
     float u = v * (mod[(long)b * I + i] + 1.f);
-    stf(w + (((long)b * O + o) * KK + kk) * I + i, u * d);
+    stf(w + (((long)b * Opad + o) * KK + kk) * I + i, u * d);
   }
 }
 
@@ -358,7 +512,7 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
                                            const float* __restrict__ attn, const float* __restrict__ dinv,
                                            const float* __restrict__ gw, float* __restrict__ dbank,
                                            float* __restrict__ dmod, float* __restrict__ gattn, int n, int O, int I,
-                                           int KK, int demod, float eps) {
+                                           int KK, int demod, float eps, int Opad) {
   __shared__ float red[32];
   __shared__ float ga_sm[8];
   int b = blockIdx.y, o = blockIdx.x;
@@ -372,7 +526,7 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
       float v = 0.f;
       for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
       float u = v * (mod[(long)b * I + i] + 1.f);
-      q += gw[(((long)b * O + o) * KK + kk) * I + i] * u;
+      q += gw[(((long)b * Opad + o) * KK + kk) * I + i] * u;
     }
     q = warp_sum(q);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
@@ -390,7 +544,7 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
     float s = mod[(long)b * I + i] + 1.f;
     float u = v * s;
-    float g = gw[(((long)b * O + o) * KK + kk) * I + i];
+    float g = gw[(((long)b * Opad + o) * KK + kk) * I + i];
     float gu = d * g;
     if (demod && !clamped) gu -= d * d * d * u * q;
     atomicAdd(dmod + (long)b * I + i, gu * v);
@@ -419,21 +573,21 @@ __global__ void adaconv_kmod_bwd_kernel(const float* __restrict__ attn, const fl
 }
 
 int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, cudaStream_t st) {
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, cudaStream_t st) {
   if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
   adaconv_attn_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(kmod, attn, B, n);
   dim3 grid(O, B);
-  GG_DISPATCH(dtype, (adaconv_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(bank, mod, attn, (T*)w, dinv, n, O, I, KK, demod, eps)));
+  GG_DISPATCH(dtype, (adaconv_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(bank, mod, attn, (T*)w, dinv, n, O, I, KK, demod, eps, Opad)));
   return gg_check_launch("adaconv_weights_fwd");
 }
 int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, cudaStream_t st) {
+                           int demod, float eps, int Opad, cudaStream_t st) {
   cudaMemsetAsync(dbank, 0, sizeof(float) * (size_t)n * O * I * KK, st);
   cudaMemsetAsync(dmod, 0, sizeof(float) * (size_t)B * I, st);
   cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, st);
   dim3 grid(O, B);
-  adaconv_weights_bwd_kernel<<<grid, 256, 0, st>>>(bank, mod, attn, dinv, gw, dbank, dmod, gattn_ws, n, O, I, KK, demod, eps);
+  adaconv_weights_bwd_kernel<<<grid, 256, 0, st>>>(bank, mod, attn, dinv, gw, dbank, dmod, gattn_ws, n, O, I, KK, demod, eps, Opad);
   if (n > 1 && dkmod) adaconv_kmod_bwd_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(attn, gattn_ws, dkmod, B, n);
   return gg_check_launch("adaconv_weights_bwd");
 }

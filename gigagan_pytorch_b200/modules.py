@@ -40,7 +40,9 @@ def is_power_of_two(n):
 
 
 def img_cpad(c):
-    return c
+    """channel count of image-like NHWC tensors (rgb, images): padded to 16 in bf16 so that every convolution that
+    touches them is tcgen05-eligible (zero channels, zero weights); exact in fp32."""
+    return 16 if (_COMPUTE["dtype"] == torch.bfloat16 and c < 16) else c
 
 
 # ----------------------------------------------------------------------------- small functional blocks (NHWC)
@@ -108,7 +110,7 @@ class AdaptiveConv2DMod(nn.Module):
         self.demod = demod
         nn.init.kaiming_normal_(self.weights, a=0, mode="fan_in", nonlinearity="leaky_relu")
 
-    def forward_nhwc(self, x, mod, kernel_mod=None):
+    def forward_nhwc(self, x, mod, kernel_mod=None, out_pad=0):
         b = x.shape[0]
         if mod.shape[0] != b:                       # scale-major repeat, ref :365-366
             mod = mod.repeat(b // mod.shape[0], 1)
@@ -119,7 +121,7 @@ class AdaptiveConv2DMod(nn.Module):
         else:
             assert not exists(kernel_mod) or kernel_mod.numel() == 0
             kernel_mod = None
-        w = ops.AdaConvWeightsFn.apply(self.weights, mod, kernel_mod, self.demod, self.eps, x.dtype)
+        w = ops.AdaConvWeightsFn.apply(self.weights, mod, kernel_mod, self.demod, self.eps, x.dtype, out_pad)
         return ops.conv2d_prepared(x, w, pad=(self.kernel - 1) // 2, per_sample=True)
 
     def forward(self, fmap, mod, kernel_mod=None):
@@ -162,21 +164,35 @@ class SelfAttention(nn.Module):
         return ops.conv2d(o, self.to_out.weight, res=residual)
 
     def _composed(self, q, k, v, n, seq, heads, d):
-        """Attention from closed-under-differentiation primitives (used inside the gradient penalty)."""
-        nk = self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d)
-        nv = self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d)
-        kf = torch.cat((nk, k.view(n, seq, heads, d)), dim=1)            # (n, seq+1, heads, d)
-        vf = torch.cat((nv, v.view(n, seq, heads, d)), dim=1)
+        """Attention from closed-under-differentiation primitives (used inside the gradient penalty).  The key axis
+        (null key + tokens) is zero-padded to a multiple of 64 with a -1e30 logit bias so that every matrix has
+        16-byte aligned rows for the TMA-fed tcgen05 batched GEMMs; padded columns get probability exactly 0."""
+        L = seq + 1
+        Lp = (L + 63) // 64 * 64 if (q.dtype == torch.bfloat16 and seq >= 64 and d % 16 == 0) else L
+        parts_k = [self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d), k.view(n, seq, heads, d)]
+        parts_v = [self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d), v.view(n, seq, heads, d)]
+        if Lp > L:
+            z = torch.zeros((n, Lp - L, heads, d), dtype=q.dtype, device=q.device)
+            parts_k.append(z)
+            parts_v.append(z)
+        kf = torch.cat(parts_k, dim=1)                                     # (n, Lp, heads, d)
+        vf = torch.cat(parts_v, dim=1)
         q4 = q.view(n, seq, heads, d).permute(0, 2, 1, 3)                  # (n, heads, seq, d) view
-        kt = kf.permute(0, 2, 3, 1)                                        # (n, heads, d, seq+1) view
+        kt = kf.permute(0, 2, 3, 1)                                        # (n, heads, d, Lp) view
+        mask = None
+        if Lp > L:
+            mask = torch.zeros((1, Lp), dtype=torch.float32, device=q.device)
+            mask[:, L:] = -1e30
         if self.dot_product:
             s = ops.bmm(q4, kt, alpha=self.scale)
+            p = ops.softmax(s, mask, s.numel() // Lp, 1) if mask is not None else ops.softmax(s)
         else:   # -|q-k|^2 * scale  ==  (2 q.k - |k|^2) * scale  up to a per-row constant (softmax-invariant)
             s = ops.bmm(q4, kt, alpha=2.0 * self.scale)
-            ksq = ops.rowdot(kf, kf)                                        # (n, seq+1, heads) fp32
-            bias = ops.axpby(-self.scale, ksq.permute(0, 2, 1).contiguous())
-            s = ops.add_channels(s, bias.reshape(n * heads, seq + 1), seq, n * heads)
-        p = ops.softmax(s)
+            ksq = ops.rowdot(kf, kf)                                        # (n, Lp, heads) fp32
+            bias = ops.axpby(-self.scale, ksq.permute(0, 2, 1).contiguous()).reshape(n * heads, Lp)
+            if mask is not None:
+                bias = ops.add_channels(bias, mask, n * heads, 1)
+            p = ops.softmax(s, bias, seq, n * heads)
         o = ops.bmm(p, vf.permute(0, 2, 1, 3), out_bmhn=True)             # physical (n, seq, heads, d)
         return o.permute(0, 2, 1, 3)
 
@@ -366,7 +382,7 @@ class Generator(BaseGenerator):
             x = ops.NoiseActFn.apply(x, noise_img(x), noise2.weight)
             if exists(self_attn):
                 x = self_attn.forward_nhwc(x)
-            layer_rgb = to_rgb.forward_nhwc(x, next(mods), next(mods))
+            layer_rgb = to_rgb.forward_nhwc(x, next(mods), next(mods), out_pad=img_cpad(self.channels))
             rgb = layer_rgb if rgb is None else ops.add(rgb, layer_rgb)
             rgbs.append(rgb)
             if exists(upsample_rgb):
@@ -391,6 +407,7 @@ class SimpleDecoder(nn.Module):
         super().__init__()
         assert 0 < frac_patches <= 1.
         self.patch_dim, self.frac_patches = patch_dim, frac_patches
+        self.static_onehot = None        # trainer-owned device buffer (nsel, B, total) when running under CUDA graphs
         self.dropout = nn.Dropout(dropout)
         dims = [dim, *dims]
         layers = [nn.Conv2d(dim, dim, 3, padding=1)]
@@ -398,6 +415,15 @@ class SimpleDecoder(nn.Module):
             layers.append(nn.Sequential(UpsampleParams(dim_in), nn.Conv2d(dim_in, dim_out, 3, padding=1),
                                         nn.LeakyReLU(0.2)))
         self.net = nn.Sequential(*layers)
+
+    def draw_patch_selection(self, b):
+        """one-hot (nsel, b, patches) of the randomly kept patches; CPU randn argsort like the reference (:1310)."""
+        total = self.patch_dim ** 2
+        nsel = max(int(self.frac_patches * total), 1)
+        perm = torch.randn((b, total)).sort(dim=-1).indices[:, :nsel]
+        onehot = torch.zeros((nsel, b, total))
+        onehot.scatter_(2, perm.t()[..., None], 1.0)
+        return onehot
 
     def forward_nhwc(self, fmap, image_nhwc):
         """fmap (B,h,w,C) compute dtype; image_nhwc (B,H,W,3).  RNG draws mirror ref :1295,:1310 (dropout on the
@@ -410,10 +436,10 @@ class SimpleDecoder(nn.Module):
             pd = self.patch_dim
             total = pd * pd
             nsel = max(int(self.frac_patches * total), 1)
-            perm = torch.randn((b, total)).sort(dim=-1).indices[:, :nsel]          # CPU, like the reference
-            onehot = torch.zeros((nsel, b, total))
-            onehot.scatter_(2, perm.t()[..., None], 1.0)
-            onehot = onehot.to(fmap.device, non_blocking=True)
+            if self.static_onehot is not None:
+                onehot = self.static_onehot
+            else:
+                onehot = self.draw_patch_selection(b).to(fmap.device, non_blocking=True)
 
             def pick(t):   # '(b p) ...' selection as a one-hot weighted sum of the p1 x p2 sub-blocks
                 hh, ww = t.shape[1] // pd, t.shape[2] // pd

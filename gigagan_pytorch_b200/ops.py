@@ -75,12 +75,47 @@ def unprep_weight_grad(gk, like):
     return gk[..., : like.shape[1]].permute(0, 3, 1, 2).contiguous().to(like.dtype)
 
 
+_PROFILER = [None]
+
+
+class ConvProfiler:
+    """Context manager: CUDA-event timing of every convolution launch (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        _PROFILER[0] = self
+        return self
+
+    def __exit__(self, *a):
+        _PROFILER[0] = None
+
+    def summary(self, dtype=torch.bfloat16):
+        torch.cuda.synchronize()
+        ms = fl = 0.0
+        n = 0
+        for kind, flops, e0, e1, dt in self.records:
+            if dt == dtype:
+                ms += e0.elapsed_time(e1)
+                fl += flops
+                n += 1
+        return dict(ms=ms, tflops=(fl / ms / 1e9) if ms else 0.0, launches=n)
+
+
 def _conv_fprop_raw(x, wk, bias, res, g, out_c):
     n, h, w, cin = x.shape
     oh, ow = g.out_hw(h, w)
     y = torch.empty((n, oh, ow, out_c), dtype=x.dtype, device=x.device)
+    prof = _PROFILER[0]
+    if prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("gg_conv2d_fprop", _p(x), _p(wk), _p(bias), _p(res), _p(y), n, h, w, cin, oh, ow, out_c, g.kh, g.kw, g.stride,
          g.pad, int(g.per_sample), g.act, float(g.gain), _dt(x), _st())
+    if prof is not None:
+        e1.record()
+        prof.records.append(("fprop", 2.0 * n * oh * ow * out_c * cin * g.kh * g.kw, e0, e1, x.dtype))
     return y
 
 
@@ -94,6 +129,15 @@ def _conv_dgrad_raw(gy, wk, g, in_shape):
         gt = ConvGeom(g.kh, g.kw, 1, g.kh - 1 - g.pad, g.per_sample)
         assert g.kh == g.kw
         return _conv_fprop_raw(gy, wt, None, None, gt, cin)
+    if g.stride == 2 and g.pad == 0 and g.kh == g.kw and g.kh <= 2 and not g.per_sample and h == 2 * oh and w == 2 * ow:
+        # non-overlapping stride-2 taps: one 1x1 GEMM per tap, scattered into the interleaved gradient tensor
+        dx = (torch.empty if g.kh == 2 else torch.zeros)(in_shape, dtype=gy.dtype, device=gy.device)
+        for ky in range(g.kh):
+            for kx in range(g.kw):
+                wt = wk[:, ky, kx, :].t().contiguous()                       # (Cin, Cout) = 1x1 kernel layout
+                call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, cin, 1, 1, 1, 0,
+                     0, 0, 1.0, (ky * w + kx) * cin, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
+        return dx
     dx = torch.empty(in_shape, dtype=gy.dtype, device=gy.device)
     call("gg_conv2d_dgrad", _p(gy), _p(wk), _p(dx), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
          int(g.per_sample), _dt(gy), _st())
@@ -503,26 +547,37 @@ def sum_all(x):
 
 
 class SoftmaxFn(Function):
+    """softmax over the last axis of (s + bias); bias fp32 (Ns, C) indexed by (row // P) % Ns (optional)."""
+
     @staticmethod
-    def forward(ctx, s):
+    def forward(ctx, s, bias, P, Ns):
         s = _c(s)
         C = s.shape[-1]
         p = torch.empty_like(s)
-        call("gg_softmax_rows", _p(s), _p(p), s.numel() // C, C, _dt(s), _st())
+        if bias is not None:
+            bias = _c(bias)
+            assert bias.dtype == torch.float32 and bias.numel() == Ns * C
+        call("gg_softmax_rows", _p(s), _p(bias), _p(p), s.numel() // C, C, P, Ns, _dt(s), _st())
         ctx.save_for_backward(p)
+        ctx.cfg = (P, Ns, bias is not None, None if bias is None else tuple(bias.shape))
         return p
 
     @staticmethod
     def backward(ctx, gp):
         (p,) = ctx.saved_tensors
+        P, Ns, has_bias, bshape = ctx.cfg
         # dS = P * (gP - rowdot(P, gP))
         t = mul(p, gp)
         r = rowdot(p, gp)
-        return axpby(1.0, t, -1.0, scale_rows(p, r))
+        ds = axpby(1.0, t, -1.0, scale_rows(p, r))
+        gb = None
+        if has_bias and ctx.needs_input_grad[1]:
+            gb = dot_sc(ds, None, P, Ns).reshape(bshape)
+        return ds, gb, None, None
 
 
-def softmax(s):
-    return SoftmaxFn.apply(s)
+def softmax(s, bias=None, rows_per_sample=1, num_samples=1):
+    return SoftmaxFn.apply(s, bias, rows_per_sample, num_samples)
 
 
 # ============================================================================= resampling (separable, sparse)
@@ -672,21 +727,22 @@ class AdaConvWeightsFn(Function):
     bank (n,O,I,k,k) fp32; mod (B,I) fp32; kmod (B,n) fp32 or None -> (B,O,k,k,I) kernel layout, compute dtype."""
 
     @staticmethod
-    def forward(ctx, bank, mod, kmod, demod, eps, dtype):
+    def forward(ctx, bank, mod, kmod, demod, eps, dtype, opad=0):
         bank, mod = _c(bank), _c(mod.float())
         n, O, I, k, _ = bank.shape
         B = mod.shape[0]
+        opad = max(opad, O)
         if n > 1:
             assert kmod is not None and kmod.numel() > 0
             kmod = _c(kmod.float())
         else:
             kmod = None
-        w = torch.empty((B, O, k, k, I), dtype=dtype, device=bank.device)
+        w = (torch.empty if opad == O else torch.zeros)((B, opad, k, k, I), dtype=dtype, device=bank.device)
         attn = torch.empty((B, n), dtype=torch.float32, device=bank.device)
         dinv = torch.empty((B, O), dtype=torch.float32, device=bank.device)
         call("gg_adaconv_weights_fwd", _p(bank), _p(mod), _p(kmod), _p(w), _p(attn), _p(dinv), B, n, O, I, k * k,
-             int(demod), float(eps), _dt(w), _st())
-        ctx.cfg = (demod, eps, kmod is not None)
+             int(demod), float(eps), opad, _dt(w), _st())
+        ctx.cfg = (demod, eps, kmod is not None, opad)
         ctx.save_for_backward(bank, mod, attn, dinv)
         return w
 
@@ -694,7 +750,7 @@ class AdaConvWeightsFn(Function):
     @once_differentiable
     def backward(ctx, gw):
         bank, mod, attn, dinv = ctx.saved_tensors
-        demod, eps, has_kmod = ctx.cfg
+        demod, eps, has_kmod, opad = ctx.cfg
         n, O, I, k, _ = bank.shape
         B = mod.shape[0]
         gw = _c(gw.float())
@@ -703,8 +759,8 @@ class AdaConvWeightsFn(Function):
         dkmod = torch.empty((B, n), dtype=torch.float32, device=bank.device) if has_kmod else None
         ws = torch.empty((B, n), dtype=torch.float32, device=bank.device)
         call("gg_adaconv_weights_bwd", _p(bank), _p(mod), _p(attn), _p(dinv), _p(gw), _p(dbank), _p(dmod), _p(dkmod),
-             _p(ws), B, n, O, I, k * k, int(demod), float(eps), _st())
-        return dbank, dmod, dkmod, None, None, None
+             _p(ws), B, n, O, I, k * k, int(demod), float(eps), opad, _st())
+        return dbank, dmod, dkmod, None, None, None, None
 
 
 class NoiseActFn(Function):

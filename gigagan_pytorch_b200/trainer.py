@@ -108,7 +108,6 @@ class FlatAdamW:
         params = [p for p in module.parameters() if p.requires_grad]
         self.params = params
         dev = params[0].device
-        assert dev.type == "cuda", "move the model to the GPU before building the optimiser"
         total = sum(p.numel() for p in params)
         self.flat = torch.empty(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -143,6 +142,8 @@ class FlatAdamW:
             off += p.numel()
 
     def step(self, grad_scale=1.0):
+        if self.flat.device.type != "cuda":
+            raise RuntimeError("FlatAdamW.step needs the parameters on the GPU (no CPU path)")
         call("gg_incr", _p(self.step_t), _st())
         call("gg_adamw", _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.chunks), self.chunks.shape[0],
              _p(self.step_t), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, float(grad_scale), _st())
@@ -211,6 +212,9 @@ class GigaGAN(nn.Module):
         self.early_save_and_sample_every = early_save_and_sample_every
         self.num_samples = num_samples
         self.train_dl = None
+        self.use_cuda_graphs = False            # capture fwd+bwd of each step variant once, then replay
+        self._graphs, self._graph_pool, self.graph_kernel_launches = {}, None, 0
+        self._real_buf = None
         self.results_folder, self.model_folder = Path(results_folder), Path(model_folder)
         self.print(f"Generator: {generator.total_params:,}  Discriminator: {discriminator.total_params:,}")
 
@@ -362,6 +366,47 @@ class GigaGAN(nn.Module):
             total = ops.axpby(1.0, total, self.multiscale_divergence_loss_weight, msd)
         return total, (div, msd)
 
+    # ---- CUDA graphs: the first occurrence of a step variant runs eagerly (warm-up), the second is captured,
+    #      later ones replay.  Inputs live in static buffers; outputs are the graph's static loss scalars.
+    def _run(self, key, work):
+        if not self.use_cuda_graphs:
+            return work()
+        from . import _lib
+        st = self._graphs.get(key)
+        if st is None:
+            self._graphs[key] = "warm"
+            return work()
+        if st == "warm":
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            l0 = _lib.launch_count
+            with torch.cuda.graph(graph, pool=self._graph_pool):
+                outs = work()
+            n = _lib.launch_count - l0
+            _lib.launch_count = l0
+            st = self._graphs[key] = (graph, outs, n)
+        graph, outs, n = st
+        graph.replay()
+        self.graph_kernel_launches += n
+        return outs
+
+    def _stage_real(self, real):
+        if self._real_buf is None or self._real_buf.shape != real.shape:
+            self._real_buf = torch.empty(real.shape, dtype=torch.float32, device=self.device)
+            self._graphs.clear()
+        self._real_buf.copy_(real, non_blocking=True)
+        for layer in self.D.layers:               # fresh random patch selection for the aux decoder (host RNG)
+            dec = layer[6]
+            if dec is not None and dec.frac_patches < 1.:
+                sel = dec.draw_patch_selection(real.shape[0])
+                if dec.static_onehot is None or dec.static_onehot.shape != sel.shape:
+                    dec.static_onehot = torch.empty(sel.shape, dtype=torch.float32, device=self.device)
+                    self._pinned_sel = torch.empty(sel.shape, dtype=torch.float32).pin_memory()
+                self._pinned_sel.copy_(sel)
+                dec.static_onehot.copy_(self._pinned_sel, non_blocking=True)
+
     def _next_images(self, dl_iter):
         batch = next(dl_iter)
         if isinstance(batch, (tuple, list)):
@@ -372,15 +417,31 @@ class GigaGAN(nn.Module):
                                  calc_multiscale_loss=True):
         self._ensure_optimizers()
         self.G.train(); self.D.train()
-        self.D_opt.zero_grad()
+        d_params = self.D_opt.params
         acc = None
-        for _ in range(grad_accum_every):
-            real = self._next_images(dl_iter)
-            noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
-            total, parts = self._d_objective(real, noise, apply_gradient_penalty, calc_multiscale_loss)
-            ops.axpby(1.0 / grad_accum_every, total).backward()
-            parts = [p.detach() / grad_accum_every for p in parts]
-            acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
+        if grad_accum_every == 1:
+            self._stage_real(self._next_images(dl_iter))
+
+            def work():
+                self.D_opt.zero_grad()
+                real = self._real_buf.detach()
+                noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
+                total, parts = self._d_objective(real, noise, apply_gradient_penalty, calc_multiscale_loss)
+                total.backward(inputs=d_params)
+                return [p.detach() for p in parts]
+
+            acc = self._run(("D", bool(apply_gradient_penalty), bool(calc_multiscale_loss)), work)
+        else:
+            self.D_opt.zero_grad()
+            for _ in range(grad_accum_every):
+                real = self._next_images(dl_iter)
+                self._stage_real(real)
+                noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)
+                total, parts = self._d_objective(self._real_buf.detach(), noise, apply_gradient_penalty,
+                                                 calc_multiscale_loss)
+                ops.axpby(1.0 / grad_accum_every, total).backward(inputs=d_params)
+                parts = [p.detach() / grad_accum_every for p in parts]
+                acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
         if self.is_distributed:
             self.D_opt.all_reduce_grads()
         self.D_opt.step(grad_scale=1.0 / self.world_size)
@@ -391,18 +452,29 @@ class GigaGAN(nn.Module):
                              calc_multiscale_loss=True):
         self._ensure_optimizers()
         self.G.train(); self.D.train()
-        self.G_opt.zero_grad()
         d_params = list(self.D.parameters())
+        g_params = self.G_opt.params
         for p in d_params:                   # Q12: D's weight gradients are discarded by the reference; skip them
             p.requires_grad_(False)
         acc = None
         try:
-            for _ in range(grad_accum_every):
-                noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
-                total, parts = self._g_objective(noise, calc_multiscale_loss)
-                ops.axpby(1.0 / grad_accum_every, total).backward()
-                parts = [p.detach() / grad_accum_every for p in parts]
-                acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
+            if grad_accum_every == 1:
+                def work():
+                    self.G_opt.zero_grad()
+                    noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
+                    total, parts = self._g_objective(noise, calc_multiscale_loss)
+                    total.backward(inputs=g_params)
+                    return [p.detach() for p in parts]
+
+                acc = self._run(("G", batch_size, bool(calc_multiscale_loss)), work)
+            else:
+                self.G_opt.zero_grad()
+                for _ in range(grad_accum_every):
+                    noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
+                    total, parts = self._g_objective(noise, calc_multiscale_loss)
+                    ops.axpby(1.0 / grad_accum_every, total).backward(inputs=g_params)
+                    parts = [p.detach() / grad_accum_every for p in parts]
+                    acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
         finally:
             for p in d_params:
                 p.requires_grad_(True)

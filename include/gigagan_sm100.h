@@ -35,6 +35,13 @@ int gg_set_flags(int flags);
 int gg_conv2d_fprop(const void* x, const void* w, const float* bias, const void* res, void* y,
                     int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad,
                     int per_sample_w, int act, float gain, int dtype, gg_stream_t stream);
+/* same, but output pixel (n,oy,ox) channel c is written at y[y_off + n*y_sn + oy*y_sh + ox*y_sw + c] (elements):
+ * lets one 1x1 launch per filter tap scatter the data gradient of a stride-2 convolution (Downsample :289-293 and
+ * the stride-2 residual 1x1 :1612) straight into the interleaved input-gradient tensor. */
+int gg_conv2d_fprop_strided(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Cin,
+                            int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act,
+                            float gain, int64_t y_off, int64_t y_sn, int64_t y_sh, int64_t y_sw, int dtype,
+                            gg_stream_t stream);
 /* dx [N,H,W,Cin] = conv-transpose(dy [N,OH,OW,Cout], w)  (autograd of the calls above, data gradient) */
 int gg_conv2d_dgrad(const void* dy, const void* w, void* dx,
                     int N, int H, int W, int Cin, int OH, int OW, int Cout, int KH, int KW, int stride, int pad,
@@ -66,8 +73,10 @@ int gg_pw_bcast(const void* x, const float* s, void* out, int64_t R, int C, int 
 int gg_red_rowdot(const void* a, const void* b, float* out, int64_t R, int C, int dtype, gg_stream_t stream);
 int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype,
                   gg_stream_t stream);
-/* row softmax over the last axis of [R,C]  (gigagan_pytorch.py:588, :649; attend.py:104) */
-int gg_softmax_rows(const void* s, void* p, int64_t R, int C, int dtype, gg_stream_t stream);
+/* row softmax over the last axis of [R,C] of (s + bias); bias fp32 [Ns][C] (nullable), row r uses bias row
+ * (r / P) % Ns  (gigagan_pytorch.py:584-588 with the key bias of the L2 logits, :649; attend.py:104) */
+int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C, int P, int Ns, int dtype,
+                    gg_stream_t stream);
 
 /* ---- separable sparse resampling of NHWC maps: bilinear x2 + [1,2,1]^2/16 reflect blur (:246-261), bilinear
  * F.interpolate (:1683-1687) and their transposes.  Tap tables: iy/wy [OH][Ty], ix/wx [OW][Tx]. */
@@ -86,12 +95,13 @@ int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx
 
 /* ---- AdaptiveConv2DMod weight builder (gigagan_pytorch.py:378-400): softmax over the filter bank, (mod+1)
  * modulation, demodulation.  bank [n][O][I][KK] fp32; mod [B][I]; kmod [B][n] (NULL if n==1);
- * w [B][O][KK][I]; attn [B][n], dinv [B][O] saved for backward. */
+ * w [B][Opad][KK][I] (rows O..Opad-1 are left untouched: pre-zeroed padding so Cout is a multiple of 16);
+ * attn [B][n], dinv [B][O] saved for backward. */
 int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int dtype, gg_stream_t stream);
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, gg_stream_t stream);
 int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, gg_stream_t stream);
+                           int demod, float eps, int Opad, gg_stream_t stream);
 
 /* ---- fused attention (gigagan_pytorch.py:562-592 with null key/value and L2-distance logits; attend.py:64-110)
  * q,k,v,o: [B, n, heads, d] rows with the given row strides (elements); null_kv [2][heads][d] fp32 or NULL.

@@ -401,3 +401,45 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr=2e-4, b
     bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-lr / bc1)
+
+
+# --------------------------------------------------------------------------- #
+# a whole optimiser step on the CPU (used as the reference arm / cpu_baseline of bench.py)
+# --------------------------------------------------------------------------- #
+
+class OracleTrainer:
+    """Minimal unconditional G+D trainer over the functional oracle: one D step (optionally with the gradient
+    penalty) and one G step per call, AdamW as the reference configures it.  ref: gigagan_pytorch.py:2227-2610."""
+
+    def __init__(self, sd_g: SD, plan_g: dict, sd_d: SD, plan_d: dict, style_depth: int = 4, lr: float = 2e-4):
+        self.sd_g = {k: v.detach().clone().requires_grad_(v.is_floating_point() and not k.endswith(".f"))
+                     for k, v in sd_g.items()}
+        self.sd_d = {k: v.detach().clone().requires_grad_(v.is_floating_point() and not k.endswith(".f"))
+                     for k, v in sd_d.items()}
+        self.plan_g, self.plan_d, self.style_depth = plan_g, plan_d, style_depth
+
+        def groups(sd):
+            ps = [p for p in sd.values() if p.requires_grad]
+            return [dict(params=[p for p in ps if p.ndim >= 2]), dict(params=[p for p in ps if p.ndim < 2],
+                                                                       weight_decay=0.0)]
+        self.opt_g = torch.optim.AdamW(groups(self.sd_g), lr=lr, betas=(0.5, 0.9), weight_decay=1e-2)
+        self.opt_d = torch.optim.AdamW(groups(self.sd_d), lr=lr, betas=(0.5, 0.9), weight_decay=1e-2)
+
+    def step(self, real: Tensor, apply_gradient_penalty: bool):
+        b = real.shape[0]
+        z = torch.randn(b, self.sd_g["style_network.net.0.weight"].shape[1])
+        with torch.no_grad():
+            fake, rgbs = generator_forward(self.sd_g, self.plan_g, z, self.style_depth, return_all_rgbs=True)
+        real = real.clone().requires_grad_(apply_gradient_penalty)
+        fake = fake.detach().requires_grad_(apply_gradient_penalty)
+        rgbs = [t.detach().requires_grad_(apply_gradient_penalty) for t in rgbs]
+        self.opt_d.zero_grad()
+        d_loss, parts = discriminator_step_loss(self.sd_d, self.plan_d, real, fake, rgbs, apply_gradient_penalty)
+        d_loss.backward()
+        self.opt_d.step()
+        self.opt_g.zero_grad()
+        z = torch.randn(b, z.shape[1])
+        g_loss, _, _ = generator_step_loss(self.sd_g, self.plan_g, self.sd_d, self.plan_d, z, self.style_depth)
+        g_loss.backward()
+        self.opt_g.step()
+        return float(d_loss.detach()), float(g_loss.detach())

@@ -1,0 +1,66 @@
+"""world_size-2 gloo test (CPU) of the data-parallel plumbing: flat parameter/gradient buckets, one SUM all-reduce
+per optimiser step, identical-initial-weights broadcast.  No compute kernels are called (no GPU here)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gigagan_pytorch_b200.trainer import FlatAdamW
+    torch.manual_seed(rank)                                   # different init per rank on purpose
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Linear(4, 2))
+    for p in net.parameters():                                # what GigaGAN._ensure_optimizers does
+        dist.broadcast(p.data, src=0)
+    opt = FlatAdamW(net)
+    # parameters and grads are views of the flat buffers
+    off = 0
+    for p in net.parameters():
+        assert p.data.data_ptr() == opt.flat.data_ptr() + 4 * off
+        assert p.grad.data_ptr() == opt.grad.data_ptr() + 4 * off
+        off += p.numel()
+    assert off == opt.flat.numel()
+    # chunk table covers every element exactly once with the right decay flag
+    cov = torch.zeros(off, dtype=torch.int32)
+    for o, n, decay, hi in opt.chunks.tolist():
+        cov[o:o + n] += 1
+    assert int(cov.min()) == 1 and int(cov.max()) == 1
+    opt.zero_grad()
+    x = torch.full((2, 3, 3, 3), float(rank + 1))
+    y = net[1](net[0](x).flatten(1)).sum()
+    y.backward()
+    local = opt.grad.clone()
+    opt.all_reduce_grads()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = torch.allclose(opt.grad, sum(gathered)) and bool((net[0].weight.grad != 0).any())
+    q.put((rank, ok, opt.flat.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)
+    assert torch.equal(res[0][2], res[1][2]), "ranks must start from identical (broadcast) weights"

@@ -320,6 +320,50 @@ def test_ka5_discriminator_step_with_gradient_penalty(dtype, tol):
     assert worst[0] < tol * 10, worst
 
 
+@pytest.mark.parametrize("case", ["kk", "kmn", "mnk", "mnmn"])
+def test_tcgen05_bmm_matches_ffma(case):
+    """all four operand-majorness combinations of the tensor-core batched GEMM, on strided attention-shaped views"""
+    from gigagan_pytorch_b200 import ops, _lib
+    n, heads, seq, d, Lp = 3, 2, 256, 64, 320
+    dt = torch.bfloat16
+    q = rn(1, n, seq, heads, d).to(dev()).to(dt)
+    kf = rn(2, n, Lp, heads, d).to(dev()).to(dt)
+    pm = rn(3, n, heads, seq, Lp).to(dev()).to(dt)
+    if case == "kk":      # S = Q K^T
+        a, b = q.permute(0, 2, 1, 3), kf.permute(0, 2, 3, 1)
+    elif case == "kmn":   # O = P V
+        a, b = pm, kf.permute(0, 2, 1, 3)
+    elif case == "mnk":   # dKt = Q^T dS  -> A MN-major (M = d contiguous), B MN-major (keys contiguous)
+        a, b = q.permute(0, 2, 3, 1), pm
+    else:                 # dV = P^T dO
+        a, b = pm.transpose(-1, -2), q.permute(0, 2, 1, 3)
+    L = _lib.lib()
+    c_tc = ops.bmm(a, b, alpha=0.5)
+    old = L.gg_set_flags(1)
+    try:
+        c_ff = ops.bmm(a, b, alpha=0.5)
+    finally:
+        L.gg_set_flags(old)
+    ref = 0.5 * (a.float() @ b.float())
+    assert relmax(c_ff, ref) < 1e-2
+    assert relmax(c_tc, ref) < 1e-2, relmax(c_tc, ref)
+    o = ops.bmm(a, b, out_bmhn=True)
+    assert relmax(o, a.float() @ b.float()) < 1e-2
+
+
+def test_composed_attention_padded_bf16_vs_fp32():
+    import gigagan_pytorch_b200 as g
+    torch.manual_seed(0)
+    for dot in (False, True):
+        blk = g.SelfAttentionBlock(64, dim_head=64, heads=2, dot_product=dot).to(dev())
+        x = torch.randn(2, 16, 16, 64, device=dev())
+        ref = blk.forward_nhwc(x, fused=False)
+        out = blk.forward_nhwc(x.to(torch.bfloat16), fused=False)
+        assert relmax(out, ref) < 3e-2
+        fz = blk.forward_nhwc(x.to(torch.bfloat16), fused=True)
+        assert relmax(fz, ref) < 3e-2
+
+
 def test_fused_attention_matches_composed_large():
     """size beyond the oracle's reach: fused (online softmax) vs composed (materialised) on 32x32 tokens."""
     import gigagan_pytorch_b200 as g
