@@ -1,0 +1,333 @@
+// Fused self-attention on tcgen05 (dim_head 64, bf16): S = Q K^T and O = P V on the tensor cores with TMEM
+// accumulators, softmax in registers straight out of TMEM, P handed to the second MMA through swizzled shared memory.
+// Learned null key/value (handled in registers), dot-product or shared-QK L2-distance logits
+// ( -|q-k|^2 s == (2 q.k - |k|^2) s - |q|^2 s ; the last term is constant along the softmax axis and dropped ).
+// Two passes over the key tiles instead of an online softmax: pass A only takes the row maximum of the logits
+// (no exponentials), pass B recomputes S, forms P = exp2(t - max) exactly once per logit and accumulates O and the
+// row sum with NO rescaling of the TMEM accumulator; the extra Q K^T costs 1/4 of the MMA work, the exponentials
+// (the real bound: 16 MUFU/clk/SM) are issued once.
+// Replaces gigagan_pytorch.py:562-592 (sim / attn never touch HBM) and attend.py:64-110.
+#include "tc_common.cuh"
+
+#define ATC_THREADS 192
+#define ATC_D 64
+#define ATC_T 128          // queries per CTA == keys per tile
+
+struct AtcP {
+  int B, heads, n, tiles;          // tiles = n / 128
+  int mode, has_null;
+  float c2;                        // logit scale * log2(e)          (dot: scale, l2: 2*scale)
+  float kb2;                       // l2: -scale*log2(e), applied to |k|^2
+  long o_rs;                       // row stride of O (elements)
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// |k_j|^2 per (b, h, token): one warp per row
+__global__ void attn_ksq_kernel(const bf16* __restrict__ k, float* __restrict__ ksq, int B, int n, int heads, long k_rs) {
+  long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);     // row = (b*heads + h)*n + j
+  if (row >= (long)B * heads * n) return;
+  int lane = threadIdx.x & 31;
+  int j = (int)(row % n);
+  long bh = row / n;
+  int h = (int)(bh % heads);
+  long b = bh / heads;
+  const bf16* p = k + (b * n + j) * k_rs + h * ATC_D + lane * 2;
+  __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
+  float2 f = __bfloat1622float2(v);
+  float s = warp_sum(f.x * f.x + f.y * f.y);
+  if (lane == 0) ksq[row] = s;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const AtcP p, const float* __restrict__ null_kv,
+                   const float* __restrict__ ksq, bf16* __restrict__ o, float* __restrict__ lse2) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  // layout: Q 16K | K[2] 32K | V[2] 32K | P[2] 64K | ksq[2][128] f32 1K | null k,v 512B | barriers | tmem slot
+  const uint32_t sQ = base, sK = base + 16384, sV = sK + 32768, sP = sV + 32768;
+  float* ksq_sm = (float*)(gbase + 147456);
+  float* null_sm = (float*)(gbase + 147456 + 1024);
+  const uint32_t bars = base + 147456 + 1024 + 512;
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13, P_EMPTY = 15, O_FULL = 17 };
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(gbase + 147456 + 1024 + 512 + 8 * 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const int T = p.tiles;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Q_FULL), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
+      mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
+      mbar_init(bar(P_FULL + i), 4); mbar_init(bar(P_EMPTY + i), 1);
+    }
+    mbar_init(bar(O_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64 && p.has_null) {
+    int t = threadIdx.x - 64;                       // 128 threads: k_null[64], v_null[64]
+    null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 256;       // S[2] at columns 0 / 128, O at 256 (64 columns)
+  const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar(Q_FULL), 16384);
+      tma_load_4d(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b);
+      int kc = 0, vc = 0;
+      for (int pass = 0; pass < 2; ++pass)
+        for (int j = 0; j < T; ++j) {
+          int s = kc & 1;
+          mbar_wait(bar(K_EMPTY + s), ((kc >> 1) & 1) ^ 1u);
+          mbar_expect_tx(bar(K_FULL + s), 16384);
+          tma_load_4d(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b);
+          ++kc;
+          if (pass == 1) {
+            int sv = vc & 1;
+            mbar_wait(bar(V_EMPTY + sv), ((vc >> 1) & 1) ^ 1u);
+            mbar_expect_tx(bar(V_FULL + sv), 16384);
+            tma_load_4d(sV + sv * 16384, &tmV, bar(V_FULL + sv), 0, j * ATC_T, h, b);
+            ++vc;
+          }
+        }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    int kc = 0, sc = 0, pc = 0;
+    auto issue_S = [&]() {
+      int ks = kc & 1, ss = sc & 1;
+      mbar_wait(bar(K_FULL + ks), (kc >> 1) & 1);
+      mbar_wait(bar(S_EMPTY + ss), ((sc >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + ks * 16384, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tS + ss * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
+        tc_commit(bar(K_EMPTY + ks));
+        tc_commit(bar(S_FULL + ss));
+      }
+      __syncwarp();
+      ++kc; ++sc;
+    };
+    mbar_wait(bar(Q_FULL), 0);
+    for (int j = 0; j < T; ++j) issue_S();           // pass A: row maxima
+    issue_S();                                        // pass B, S_0
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_S();
+      int ps = pc & 1;
+      mbar_wait(bar(P_FULL + ps), (pc >> 1) & 1);
+      mbar_wait(bar(V_FULL + ps), (pc >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint64_t da = make_smem_desc(sP + ps * 32768 + (k >> 2) * 16384, 1024, 2) + (uint64_t)(2 * (k & 3));
+          uint64_t db = make_smem_desc_mn(sV + ps * 16384 + k * 2048, 0, 1024);
+          tc_mma_f16(tO, da, db, idesc_pv, (j | k) ? 1u : 0u);
+        }
+        tc_commit(bar(P_EMPTY + ps));
+        tc_commit(bar(V_EMPTY + ps));
+        if (j == T - 1) tc_commit(bar(O_FULL));
+      }
+      __syncwarp();
+      ++pc;
+    }
+  } else {
+    // ================================================= softmax / epilogue: thread <-> query row <-> TMEM lane
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                      // row inside the tile
+    const int st = threadIdx.x - 64;                  // 0..127 index among the softmax threads
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const long grow = (long)b * p.n + qt * ATC_T + r; // global token row
+    // logit of the null key from this thread's q row (read from the swizzled Q tile)
+    float t_null = -INFINITY;
+    mbar_wait(bar(Q_FULL), 0);
+    if (p.has_null) {
+      const uint8_t* qrow = gbase + (sQ - base) + r * 128;
+      float dot = 0.f, kn2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = *reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4));
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f = __bfloat1622float2(hp[e]);
+          float k0 = null_sm[c * 8 + 2 * e], k1 = null_sm[c * 8 + 2 * e + 1];
+          dot = fmaf(f.x, k0, fmaf(f.y, k1, dot));
+          kn2 = fmaf(k0, k0, fmaf(k1, k1, kn2));
+        }
+      }
+      t_null = dot * p.c2 + (p.mode == 1 ? p.kb2 * kn2 : 0.f);
+    }
+    float m = t_null;
+    int sc = 0, pc = 0;
+    // ---------------- pass A: row maximum
+    for (int j = 0; j < T; ++j) {
+      int ss = sc & 1;
+      if (p.mode == 1) {
+        ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tS + ss * 128 + lane_addr + c0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float t = __uint_as_float(v[e]) * p.c2;
+          if (p.mode == 1) t += ksq_sm[ss * 128 + c0 + e];
+          m = fmaxf(m, t);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(S_EMPTY + ss));
+      ++sc;
+    }
+    // ---------------- pass B: probabilities, row sums, P tiles for the second MMA
+    float l = p.has_null ? fast_exp2(t_null - m) : 0.f;
+    const float p_null = l;
+    for (int j = 0; j < T; ++j) {
+      int ss = sc & 1, ps = pc & 1;
+      if (p.mode == 1) {
+        ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
+      mbar_wait(bar(P_EMPTY + ps), ((pc >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      uint8_t* prow = gbase + (sP - base) + ps * 32768 + r * 128;
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tS + ss * 128 + lane_addr + c0, v);
+        float pv[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float t = __uint_as_float(v[e]) * p.c2;
+          if (p.mode == 1) t += ksq_sm[ss * 128 + c0 + e];
+          pv[e] = fast_exp2(t - m);
+          l += pv[e];
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h0[e] = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
+          h1[e] = __floats2bfloat162_rn(pv[8 + 2 * e], pv[8 + 2 * e + 1]);
+        }
+        int slab = c0 >> 6, ch = (c0 & 63) >> 3;      // 16 columns = two 16-byte chunks ch, ch+1 of a 128-byte row
+        uint8_t* dst = prow + slab * 16384;
+        *reinterpret_cast<uint4*>(dst + (((ch) ^ (r & 7)) << 4)) = o0;
+        *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ (r & 7)) << 4)) = o1;
+      }
+      fence_async_smem();                             // generic-proxy stores -> visible to the UMMA (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(P_FULL + ps)); mbar_arrive(bar(S_EMPTY + ss)); }
+      ++sc; ++pc;
+    }
+    // ---------------- epilogue: O / l (+ null value), log-sum-exp
+    mbar_wait(bar(O_FULL), 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    bf16* orow = o + grow * p.o_rs + h * ATC_D;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(tO + lane_addr + c0, v);
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        f[e] = __uint_as_float(v[e]);
+        if (p.has_null) f[e] = fmaf(p_null, null_sm[64 + c0 + e], f[e]);
+        f[e] *= inv;
+      }
+      uint4 o0, o1;
+      __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+      __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        h0[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+        h1[e] = __floats2bfloat162_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+      }
+      reinterpret_cast<uint4*>(orow + c0)[0] = o0;
+      reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+    }
+    lse2[(long)bh * p.n + qt * ATC_T + r] = m + log2f(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+static int make_qkv_map(CUtensorMap* m, const void* ptr, int B, int n, int heads, long rs) {
+  uint64_t dims[4] = {ATC_D, (uint64_t)n, (uint64_t)heads, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)rs * 2, (uint64_t)ATC_D * 2, (uint64_t)n * rs * 2};
+  uint32_t box[4] = {ATC_D, ATC_T, 1, 1};
+  return tc_make_map4(m, ptr, dims, strides, box, 128);
+}
+
+// returns 1 when the shape is not eligible (caller falls back to the FFMA kernel)
+int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
+                    int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
+                    int mode, cudaStream_t st) {
+  if (d != ATC_D || nq != nk || nq % ATC_T || nq < ATC_T) return 1;
+  if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 8)) return 1;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) return 1;
+  if (mode == 1 && !ksq_ws) return 1;
+  AtcP p;
+  p.B = B; p.heads = heads; p.n = nq; p.tiles = nq / ATC_T; p.mode = mode; p.has_null = null_kv != nullptr;
+  const float log2e = 1.4426950408889634f;
+  p.c2 = (mode == 1 ? 2.f * scale : scale) * log2e;
+  p.kb2 = -scale * log2e;
+  p.o_rs = o_rs;
+  CUtensorMap tmQ, tmK, tmV;
+  if (make_qkv_map(&tmQ, q, B, nq, heads, q_rs) || make_qkv_map(&tmK, k, B, nk, heads, k_rs) || make_qkv_map(&tmV, v, B, nk, heads, v_rs)) return -1;
+  if (mode == 1) {
+    long rows = (long)B * heads * nk;
+    attn_ksq_kernel<<<gg_cdiv(rows, 8), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
+  }
+  size_t smem = 1024 + 147456 + 1024 + 512 + 8 * 18 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = B * heads * p.tiles;
+  attn_fwd_tc_kernel<<<grid, ATC_THREADS, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
+  return gg_check_launch("attn_fwd_tc");
+}

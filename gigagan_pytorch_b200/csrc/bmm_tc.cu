@@ -154,7 +154,7 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 // returns 1 if not eligible.  sa/sb: {batch1, batch2, row, col} element strides; B indexed [k][n].
 int ggi_tc_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
                const long* sa, const long* sb, const long* sc, float alpha, cudaStream_t st) {
-  if (M < 64 || N < 16 || K < 16) return 1;
+  if (M < 16 || N < 16 || K < 16) return 1;      // short M: TMA zero-fills the rest of the 128-row tile
   int a_mn, b_mn;
   long a_outer, b_outer;
   if (sa[3] == 1 && sa[2] % 8 == 0) { a_mn = 0; a_outer = sa[2]; }            // K contiguous

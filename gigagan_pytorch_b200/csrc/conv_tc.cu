@@ -17,7 +17,7 @@ struct TcP {
   int N, OH, OW, Cout;
   int Wt, Ht, Nt, tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles;
   int Ntile, chunk, cchunks, KH, KW, pad, stride, per_sample;
-  int stages, stage_bytes, a_bytes, b_bytes;
+  int stages, stage_bytes, a_bytes, b_bytes, b_slab, ts;   // ts = filter taps packed into one pipeline stage
   int act;
   float gain;
   long y_off, y_sn, y_sh, y_sw;          // output addressing (elements): y_off + n*y_sn + oy*y_sh + ox*y_sw + co
@@ -55,7 +55,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int kblocks = p.KH * p.KW * p.cchunks;
+  const int kblocks = (p.KH * p.KW / p.ts) * p.cchunks;
 
   if (warp == 0) {
     // ===================================================== TMA producer
@@ -66,18 +66,22 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
         int ox0 = tw * p.Wt, oy0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Ntile;
         for (int kb = 0; kb < kblocks; ++kb) {
-          int tap = kb / p.cchunks, cc = kb - tap * p.cchunks;
+          int tap0 = (kb / p.cchunks) * p.ts, cc = kb % p.cchunks;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
-          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
-          if (p.stride == 1) {
-            int ky = tap / p.KW, kx = tap - ky * p.KW;
-            tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
-          } else {
-            const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
-            tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0, oy0, n0);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(p.ts * (p.a_bytes + p.b_bytes)));
+          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + p.ts * p.a_bytes;
+          for (int t = 0; t < p.ts; ++t) {
+            int tap = tap0 + t;
+            uint32_t sa = sa0 + t * p.a_bytes, sb = sb0 + t * p.b_slab;
+            if (p.stride == 1) {
+              int ky = tap / p.KW, kx = tap - ky * p.KW;
+              tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
+            } else {
+              const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
+              tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0, oy0, n0);
+            }
+            tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0 : 0);
           }
-          tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0 : 0);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -93,11 +97,14 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
-          uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
-          uint64_t da = make_smem_desc(sa, p.sbo, p.layout_type), db = make_smem_desc(sb, p.sbo, p.layout_type);
+          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + p.ts * p.a_bytes;
           int ksteps = p.chunk >> 4;
-          for (int k = 0; k < ksteps; ++k)
-            tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int t = 0; t < p.ts; ++t) {
+            uint64_t da = make_smem_desc(sa0 + t * p.a_bytes, p.sbo, p.layout_type);
+            uint64_t db = make_smem_desc(sb0 + t * p.b_slab, p.sbo, p.layout_type);
+            for (int k = 0; k < ksteps; ++k)
+              tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | t | k) != 0 ? 1u : 0u);
+          }
           tc_commit(empty_bar(stage));
           if (kb == kblocks - 1) tc_commit(tfull_bar(acc));
         }
@@ -223,7 +230,7 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   if (stride == 1) { if (OH != H + 2 * pad - KH + 1 || OW != W + 2 * pad - KW + 1) return 1; }
   else if (stride == 2) { if (pad != 0 || KH != KW || KH > 2 || H != 2 * OH || W != 2 * OW) return 1; }
   else return 1;
-  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 4 || OH < 4) return 1;
+  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 2 || OH < 2) return 1;
   int Wt = OW < 16 ? OW : 16;
   int Ht = OH < 128 / Wt ? OH : 128 / Wt;
   int Nt = 128 / (Wt * Ht);
@@ -240,7 +247,19 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   p.chunk = chunk; p.cchunks = Cin / chunk; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
   p.per_sample = per_sample_w;
   p.a_bytes = 128 * chunk * 2; p.b_bytes = Ntile * chunk * 2;
-  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023) / 1024 * 1024;
+  p.b_slab = (p.b_bytes + 1023) / 1024 * 1024;
+  // small-channel layers: pack several filter taps into one stage so a stage carries enough bytes / MMAs to hide
+  // the TMA + mbarrier round trip (the 16/32-channel 128^2 / 256^2 layers were latency-bound at 1 tap per stage)
+  int taps = KH * KW, ts = 1;
+  if (stride == 1 && p.cchunks == 1) {
+    const int cand[4] = {taps, 7, 3, 1};
+    for (int ci_ = 0; ci_ < 4; ++ci_) {
+      int c = cand[ci_];
+      if (c >= 1 && taps % c == 0 && c * (p.a_bytes + p.b_slab) <= 64 * 1024) { ts = c; break; }
+    }
+  }
+  p.ts = ts;
+  p.stage_bytes = ts * (p.a_bytes + p.b_slab);
   int stages = (200 * 1024) / p.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) return 1;
@@ -299,13 +318,13 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
 //   (64 channels x Pw x Ph x Pn pixels, 128 B rows, SWIZZLE_128B) are consumed directly with the pixel axis as K.
 //   Work item = (co block, ci block, tap, [image], pixel-range split); partial sums are reduced with fp32 red.add.
 // =================================================================================================
-#define WG_PIX 64     // pixels per pipeline stage (4 UMMA K-steps of 16)
+#define WG_PIX_MAX 256   // pixels per pipeline stage: 64 (4 UMMA K-steps) ... 256 (16 K-steps)
 
 struct WgP {
   int N, OH, OW, Cout, Cin, taps, KW, pad, stride;
   int Wt, Ht, Nt, tiles_w, tiles_h, tiles_n, pix_tiles;   // pixel tiling of the OUTPUT grid
   int co_blocks, ci_blocks, Ntile, nsub_a, nsub_b, splits, per_sample, tiles_per_image, total_items;
-  int stages, stage_bytes, a_bytes, b_bytes;
+  int stages, stage_bytes, a_bytes, b_bytes, pix;
   uint32_t idesc, tmem_cols;
 };
 
@@ -365,13 +384,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
           mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
           for (int s = 0; s < p.nsub_a; ++s)
-            tma_load_4d(sa + s * (WG_PIX * 128), &tmDY, full_bar(stage), cob * 128 + s * 64, ox0, oy0, n0);
+            tma_load_4d(sa + s * (p.pix * 128), &tmDY, full_bar(stage), cob * 128 + s * 64, ox0, oy0, n0);
           for (int s = 0; s < p.nsub_b; ++s) {
             int c0 = cib * p.Ntile + s * 64;
-            if (p.stride == 1) tma_load_4d(sb + s * (WG_PIX * 128), &tmX0, full_bar(stage), c0, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
+            if (p.stride == 1) tma_load_4d(sb + s * (p.pix * 128), &tmX0, full_bar(stage), c0, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
             else {
               const CUtensorMap* m = tap == 0 ? &tmX0 : tap == 1 ? &tmX1 : tap == 2 ? &tmX2 : &tmX3;
-              tma_load_4d(sb + s * (WG_PIX * 128), m, full_bar(stage), c0, ox0, oy0, n0);
+              tma_load_4d(sb + s * (p.pix * 128), m, full_bar(stage), c0, ox0, oy0, n0);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -380,7 +399,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
     }
   } else if (warp == 1) {
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-    const uint32_t lbo_a = p.nsub_a > 1 ? WG_PIX * 128 : 0, lbo_b = WG_PIX * 128;
+    const uint32_t lbo_a = p.nsub_a > 1 ? p.pix * 128 : 0, lbo_b = p.pix * 128;
+    const int ksteps = p.pix / 16;
     for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
       int cob, cib, tap, img, t0, t1;
       decode(item, cob, cib, tap, img, t0, t1);
@@ -392,8 +412,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
         tc_fence_after();
         if (lane == 0) {
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
-#pragma unroll
-          for (int k = 0; k < WG_PIX / 16; ++k) {
+          for (int k = 0; k < ksteps; ++k) {
             uint64_t da = make_smem_desc_mn(sa + k * 2048, lbo_a, 1024), db = make_smem_desc_mn(sb + k * 2048, lbo_b, 1024);
             tc_mma_f16(d_tmem, da, db, p.idesc, (t > t0 || k > 0) ? 1u : 0u);
           }
@@ -451,11 +470,14 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   if (stride == 1) { if (OH != H + 2 * pad - KH + 1 || OW != W + 2 * pad - KW + 1) return 1; }
   else if (stride == 2) { if (pad != 0 || KH != KW || KH > 2 || H != 2 * OH || W != 2 * OW) return 1; }
   else return 1;
-  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 4 || OH < 4) return 1;
+  if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 2 || OH < 2) return 1;
+  int nsub_a_ = Cout > 64 ? 2 : 1, nsub_b_ = ((Cin > 256 ? 256 : Cin) + 63) / 64;
+  int pix = 64;                                       // bigger pixel slabs for thin layers: ~48-64 KB per stage
+  while (pix < WG_PIX_MAX && (nsub_a_ + nsub_b_) * (pix * 2) * 128 <= 64 * 1024 && (long)OH * OW * (per_sample_w ? 1 : N) >= 4L * pix * 2) pix *= 2;
   int Wt = OW < 16 ? OW : 16;
-  int Ht = OH < WG_PIX / Wt ? OH : WG_PIX / Wt;
-  int Nt = WG_PIX / (Wt * Ht);
-  if (Wt * Ht * Nt != WG_PIX) return 1;
+  int Ht = OH < pix / Wt ? OH : pix / Wt;
+  int Nt = pix / (Wt * Ht);
+  if (Wt * Ht * Nt != pix) return 1;
   if (per_sample_w && Nt != 1) return 1;
   if (N % Nt) return 1;                               // zero-filled phantom images would be harmless, keep it exact
   if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return 1;
@@ -476,7 +498,8 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   while (base_items * splits < 3 * tc_num_sms() && ntiles / (splits * 2) >= 8) splits *= 2;
   p.splits = splits;
   p.total_items = base_items * splits;
-  p.a_bytes = p.nsub_a * WG_PIX * 128; p.b_bytes = p.nsub_b * WG_PIX * 128;
+  p.pix = pix;
+  p.a_bytes = p.nsub_a * pix * 128; p.b_bytes = p.nsub_b * pix * 128;
   p.stage_bytes = p.a_bytes + p.b_bytes;
   int stages = (200 * 1024) / p.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;

@@ -1,6 +1,7 @@
 // extern "C" surface of libgigagan_sm100.so (declared in include/gigagan_sm100.h).
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/gigagan_sm100.h"
 #include "gg_internal.h"
 
@@ -22,6 +23,11 @@ int gg_check_launch(const char* what) {
 
 #define ST ((cudaStream_t)stream)
 static int g_flags = 0;
+static int dbg_fallback() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GG_DEBUG_FALLBACK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
 
 extern "C" {
 const char* gg_last_error(void) { return g_err; }
@@ -42,6 +48,7 @@ static int conv_fprop_any(const void* x, const void* w, const float* bias, const
   if (dtype == GG_BF16 && !(g_flags & 1)) {
     int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, st);
     if (r <= 0) return r;
+    if (dbg_fallback()) fprintf(stderr, "[gg] FFMA fprop: N%d H%d W%d Cin%d -> OH%d OW%d Cout%d k%dx%d s%d p%d ps%d\n", N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w);
   }
 #endif
   return ggi_simt_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, dtype, st);
@@ -68,6 +75,7 @@ int gg_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int 
   if (dtype == GG_BF16 && !(g_flags & 1)) {
     int r = ggi_tc_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, ST);
     if (r <= 0) return r;
+    if (dbg_fallback()) fprintf(stderr, "[gg] FFMA wgrad: N%d H%d W%d Cin%d -> OH%d OW%d Cout%d k%dx%d s%d p%d ps%d\n", N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w);
   }
 #endif
   return ggi_simt_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, dtype, ST);
@@ -78,6 +86,9 @@ int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int
   if (dtype == GG_BF16 && !(g_flags & 1)) {
     int r = ggi_tc_bmm(A, B, bias, C, b1, b2, M, N, K, (const long*)h_sa, (const long*)h_sb, (const long*)h_sc, alpha, ST);
     if (r <= 0) return r;
+    if (dbg_fallback()) fprintf(stderr, "[gg] FFMA bmm: b%dx%d M%d N%d K%d sa(%ld,%ld,%ld,%ld) sb(%ld,%ld,%ld,%ld) A%%16=%d B%%16=%d\n", b1, b2, M, N, K,
+                                (long)h_sa[0], (long)h_sa[1], (long)h_sa[2], (long)h_sa[3], (long)h_sb[0], (long)h_sb[1], (long)h_sb[2], (long)h_sb[3],
+                                (int)((uintptr_t)A & 15), (int)((uintptr_t)B & 15));
   }
 #endif
   return ggi_simt_bmm(A, B, bias, C, b1, b2, M, N, K, (const long*)h_sa, (const long*)h_sb, (const long*)h_sc, alpha, dtype, ST);
@@ -98,6 +109,9 @@ int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, in
 }
 int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C, int P, int Ns, int dtype, gg_stream_t stream) {
   return ggi_softmax_rows(s, bias, p, R, C, P, Ns, dtype, ST);
+}
+int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream) {
+  return ggi_softmax_bwd_rows(p, gp, ds, R, C, dtype, ST);
 }
 int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                   int Ty, const int* ix, const float* wx, int Tx, int dtype, gg_stream_t stream) {
@@ -125,6 +139,13 @@ int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_k
                 int dtype, gg_stream_t stream) {
   return ggi_attn_fwd(q, k, v, null_kv, o, lse, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, dtype, ST);
 }
+int gg_attn_fwd_tc(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse2, float* ksq_ws,
+                   int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
+                   float scale, int mode, gg_stream_t stream) {
+  int r = ggi_tc_attn_fwd(q, k, v, null_kv, o, lse2, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
+  if (r == 1) return gg_fail("gg_attn_fwd_tc: shape not eligible (dim_head 64, tokens %% 128 == 0, 16-byte aligned rows)");
+  return r;
+}
 int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
                 const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, int B, int heads,
                 int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,
@@ -136,4 +157,8 @@ int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, i
   return ggi_adamw(p, g, m, v, chunks, nchunks, step_ptr, lr, b1, b2, eps, wd, grad_scale, ST);
 }
 int gg_incr(int* p, gg_stream_t stream) { return ggi_incr(p, ST); }
+int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
+                         int dtype, gg_stream_t stream) {
+  return ggi_weight_prep_multi(master, entries, chunks, nchunks, fwd, bwd, dtype, ST);
+}
 }

@@ -32,7 +32,7 @@ template <> __device__ __forceinline__ void stv<bf16>(bf16* p, const float* in) 
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 // ------------------------------------------------------------------ unary maps
-enum { U_LRELU = 0, U_RELU = 1, U_GELU = 2, U_SILU = 3, U_SIGMOID = 4, U_INVNORM = 5 };
+enum { U_LRELU = 0, U_RELU = 1, U_GELU = 2, U_SILU = 3, U_SIGMOID = 4, U_INVNORM = 5, U_RSQRT_EPS8 = 6 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 
@@ -57,6 +57,11 @@ __device__ __forceinline__ float unary_eval(int kind, float x) {
     }
     case U_INVNORM: {   // 1 / max(sqrt(x), 1e-12)  (F.normalize's denominator), x = sum of squares
       if (x <= 1e-24f) return LEVEL == 0 ? 1e12f : 0.f;
+      float r = rsqrtf(x);
+      return LEVEL == 0 ? r : LEVEL == 1 ? -0.5f * r * r * r : 0.75f * r * r * r * r * r;
+    }
+    case U_RSQRT_EPS8: {   // rsqrt(max(x, 1e-8))  (StyleGAN2 demodulation, gigagan_pytorch.py:399)
+      if (x <= 1e-8f) return LEVEL == 0 ? 1e4f : 0.f;
       float r = rsqrtf(x);
       return LEVEL == 0 ? r : LEVEL == 1 ? -0.5f * r * r * r : 0.75f * r * r * r * r * r;
     }
@@ -246,13 +251,66 @@ __global__ void dot_sc_kernel(const T* __restrict__ a, const T* __restrict__ b, 
     atomicAdd(out + (long)ns * C + c, t);
   }
 }
+// vector variant: each thread owns V consecutive channels (16-byte loads); block = 32 channel-vectors x 8 row lanes
+template <typename T>
+__global__ void dot_sc_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, int C, int P,
+                                  int Ns, long rows_per_out, int splits) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sm[8][32 * V + 1];
+  int cv = blockIdx.x * 32 + threadIdx.x;          // channel-vector index
+  int c = cv * V;
+  int ns = blockIdx.y;
+  long chunk = (rows_per_out + splits - 1) / splits;
+  long j0 = blockIdx.z * chunk, j1 = min(rows_per_out, j0 + chunk);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  if (c < C)
+    for (long j = j0 + threadIdx.y; j < j1; j += 8) {
+      long rep = j / P, pp = j - rep * P;
+      long r = (rep * Ns + ns) * P + pp;
+      float av[V], bv[V];
+      ldv(a + r * C + c, av);
+      if (b) {
+        ldv(b + r * C + c, bv);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaf(av[k], bv[k], acc[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += av[k];
+      }
+    }
+#pragma unroll
+  for (int k = 0; k < V; ++k) sm[threadIdx.y][threadIdx.x * V + k] = acc[k];
+  __syncthreads();
+  int t = threadIdx.y * 32 + threadIdx.x;            // 256 threads reduce 32*V columns
+  for (int col = t; col < 32 * V; col += 256) {
+    int cc = blockIdx.x * 32 * V + col;
+    if (cc < C) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += sm[i][col];
+      atomicAdd(out + (long)ns * C + cc, s);
+    }
+  }
+}
 int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int dtype, cudaStream_t st) {
   long N = R / P;
   long rows_per_out = (N / Ns) * P;
   cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Ns * C, st);
+  int V = dtype == GG_F32 ? 4 : 8;
+  dim3 block(32, 8);
+  if (C % V == 0 && al16(a) && (!b || al16(b))) {
+    int gx = gg_cdiv(C, 32 * V);
+    int base = gx * Ns, splits = 1;
+    while (base * splits < 148 * 8 && rows_per_out / (splits * 2) >= 32) splits *= 2;
+    dim3 grid(gx, Ns, splits);
+    GG_DISPATCH(dtype, (dot_sc_vec_kernel<T><<<grid, block, 0, st>>>((const T*)a, (const T*)b, out, C, P, Ns, rows_per_out, splits)));
+    return gg_check_launch("dot_sc_vec");
+  }
   int base = gg_cdiv(C, 32) * Ns, splits = 1;
   while (base * splits < 148 * 4 && rows_per_out / (splits * 2) >= 64) splits *= 2;
-  dim3 grid(gg_cdiv(C, 32), Ns, splits), block(32, 8);
+  dim3 grid(gg_cdiv(C, 32), Ns, splits);
   GG_DISPATCH(dtype, (dot_sc_kernel<T><<<grid, block, 0, st>>>((const T*)a, (const T*)b, out, C, P, Ns, rows_per_out, splits)));
   return gg_check_launch("dot_sc");
 }
@@ -339,6 +397,61 @@ int ggi_softmax_rows(const void* s, const float* bias, void* p, long R, int C, i
     GG_DISPATCH(dtype, (softmax_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)s, bias, (T*)p, C, P, Ns)));
   }
   return gg_check_launch("softmax_rows");
+}
+
+// dS = P * (gP - sum_j P_j gP_j), one warp per row, rows in registers
+template <typename T, int MAXV>
+__global__ void softmax_bwd_rows_warp_kernel(const T* __restrict__ p, const T* __restrict__ gp, T* __restrict__ ds,
+                                             long R, int C) {
+  constexpr int V = VecN<T>::N;
+  long r = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  int lane = threadIdx.x & 31, nvec = C / V;
+  float pv[MAXV][V], gv[MAXV][V];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+      ldv(p + r * C + vi * V, pv[i]);
+      ldv(gp + r * C + vi * V, gv[i]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) dot = fmaf(pv[i][j], gv[i][j], dot);
+    }
+  }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) pv[i][j] *= (gv[i][j] - dot);
+      stv(ds + r * C + vi * V, pv[i]);
+    }
+  }
+}
+template <typename T>
+__global__ void softmax_bwd_rows_kernel(const T* __restrict__ p, const T* __restrict__ gp, T* __restrict__ ds, int C) {
+  __shared__ float red[32];
+  long r = blockIdx.x;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dot += ldf(p + r * C + c) * ldf(gp + r * C + c);
+  dot = warp_sum(dot);
+  if (lane == 0) red[wid] = dot;
+  __syncthreads();
+  dot = 0.f;
+  for (int i = 0; i < nw; ++i) dot += red[i];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) stf(ds + r * C + c, ldf(p + r * C + c) * (ldf(gp + r * C + c) - dot));
+}
+int ggi_softmax_bwd_rows(const void* p, const void* gp, void* ds, long R, int C, int dtype, cudaStream_t st) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V == 0 && C / V <= 32 * 6 && al16(p) && al16(gp) && al16(ds)) {
+    GG_DISPATCH(dtype, (softmax_bwd_rows_warp_kernel<T, 6><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)p, (const T*)gp, (T*)ds, R, C)));
+  } else {
+    GG_DISPATCH(dtype, (softmax_bwd_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)p, (const T*)gp, (T*)ds, C)));
+  }
+  return gg_check_launch("softmax_bwd_rows");
 }
 
 // ------------------------------------------------------------------ separable sparse resampling (NHWC)
@@ -507,59 +620,75 @@ __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const
   }
 }
 
-// backward: gw [B][o][kk][i] fp32 -> dbank (atomic), dmod [B][I] (atomic), gattn [B][n] (atomic)
-__global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
-                                           const float* __restrict__ attn, const float* __restrict__ dinv,
-                                           const float* __restrict__ gw, float* __restrict__ dbank,
-                                           float* __restrict__ dmod, float* __restrict__ gattn, int n, int O, int I,
-                                           int KK, int demod, float eps, int Opad) {
+// backward, pass 1 (demod only): q[b,o] = sum_{i,kk} gw * u        (one CTA per (b,o))
+__global__ void adaconv_q_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+                                 const float* __restrict__ attn, const float* __restrict__ gw, float* __restrict__ q,
+                                 int n, int O, int I, int KK, int Opad) {
   __shared__ float red[32];
-  __shared__ float ga_sm[8];
   int b = blockIdx.y, o = blockIdx.x;
   int E = I * KK;
-  float d = dinv[(long)b * O + o];
-  float q = 0.f;
-  bool clamped = false;
-  if (demod) {
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      int i = e / KK, kk = e % KK;
-      float v = 0.f;
-      for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
-      float u = v * (mod[(long)b * I + i] + 1.f);
-      q += gw[(((long)b * Opad + o) * KK + kk) * I + i] * u;
-    }
-    q = warp_sum(q);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
-    __syncthreads();
-    q = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) q += red[i];
-    clamped = d * d * eps >= 0.999999f;   // d == rsqrt(eps)  <=>  sum u^2 <= eps: inv-norm is constant
-  }
-  if (threadIdx.x < 8) ga_sm[threadIdx.x] = 0.f;
-  __syncthreads();
-  float ga[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc = 0.f;
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    int i = e / KK, kk = e % KK;
+    int kk = e / I, i = e - kk * I;                        // i fastest: coalesced over gw's kernel layout
     float v = 0.f;
-    for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
-    float s = mod[(long)b * I + i] + 1.f;
-    float u = v * s;
-    float g = gw[(((long)b * Opad + o) * KK + kk) * I + i];
-    float gu = d * g;
-    if (demod && !clamped) gu -= d * d * d * u * q;
-    atomicAdd(dmod + (long)b * I + i, gu * v);
-    float gv = gu * s;
-    for (int j = 0; j < n; ++j) {
-      atomicAdd(dbank + ((long)j * O + o) * E + e, attn[b * n + j] * gv);
-      ga[j] += gv * bank[((long)j * O + o) * E + e];
-    }
+    for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[(((long)j * O + o) * I + i) * KK + kk];
+    acc += gw[(((long)b * Opad + o) * KK + kk) * I + i] * v * (mod[(long)b * I + i] + 1.f);
   }
-  for (int j = 0; j < n; ++j) {
-    float t = warp_sum(ga[j]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&ga_sm[j], t);
-  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x < n) atomicAdd(gattn + b * n + threadIdx.x, ga_sm[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    q[(long)b * O + o] = t;
+  }
+}
+
+// backward, pass 2: thread = (kk, i) of one output channel o, loops over the batch.  dbank is owned (plain store),
+// dmod gets one atomic per (b, o, i), gattn one per (block, b, n).
+__global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+                                           const float* __restrict__ attn, const float* __restrict__ dinv,
+                                           const float* __restrict__ q, const float* __restrict__ gw,
+                                           float* __restrict__ dbank, float* __restrict__ dmod,
+                                           float* __restrict__ gattn, int B, int n, int O, int I, int KK, int demod,
+                                           float eps, int Opad) {
+  extern __shared__ float sm[];              // [KK*32] partial dmod terms, then [B*n] gattn partials
+  float* sm_dm = sm;
+  float* sm_ga = sm + KK * 32;
+  const int o = blockIdx.y, i0 = blockIdx.x * 32;
+  const int il = threadIdx.x & 31, kk = threadIdx.x >> 5;          // blockDim = 32 * KK
+  const int i = i0 + il;
+  const bool live = i < I;
+  for (int t = threadIdx.x; t < B * n; t += blockDim.x) sm_ga[t] = 0.f;
+  float wb[8], acc[8];
+  for (int j = 0; j < n; ++j) { wb[j] = live ? bank[(((long)j * O + o) * I + i) * KK + kk] : 0.f; acc[j] = 0.f; }
+  __syncthreads();
+  for (int b = 0; b < B; ++b) {
+    float d = dinv[(long)b * O + o];
+    float v = 0.f;
+    for (int j = 0; j < n; ++j) v += attn[b * n + j] * wb[j];
+    float s = live ? mod[(long)b * I + i] + 1.f : 0.f;
+    float g = live ? gw[(((long)b * Opad + o) * KK + kk) * I + i] : 0.f;
+    float gu = d * g;
+    if (demod && d * d * eps < 0.999999f) gu -= d * d * d * (v * s) * q[(long)b * O + o];
+    float gv = gu * s;
+    sm_dm[kk * 32 + il] = gu * v;
+    for (int j = 0; j < n; ++j) {
+      acc[j] += attn[b * n + j] * gv;
+      float t = warp_sum(gv * wb[j]);
+      if (il == 0) atomicAdd(&sm_ga[b * n + j], t);
+    }
+    __syncthreads();
+    if (kk == 0 && live) {
+      float t = 0.f;
+      for (int k2 = 0; k2 < KK; ++k2) t += sm_dm[k2 * 32 + il];
+      atomicAdd(dmod + (long)b * I + i, t);
+    }
+    __syncthreads();
+  }
+  if (live)
+    for (int j = 0; j < n; ++j) dbank[(((long)j * O + o) * I + i) * KK + kk] = acc[j];
+  for (int t = threadIdx.x; t < B * n; t += blockDim.x) atomicAdd(gattn + t, sm_ga[t]);
 }
 
 // dkmod = attn * (gattn - sum_j attn_j gattn_j)
@@ -583,11 +712,19 @@ int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* km
 int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
                            int demod, float eps, int Opad, cudaStream_t st) {
-  cudaMemsetAsync(dbank, 0, sizeof(float) * (size_t)n * O * I * KK, st);
+  // gattn_ws: B*n floats of gattn followed by B*O floats for q
+  float* q = gattn_ws + (size_t)B * n;
   cudaMemsetAsync(dmod, 0, sizeof(float) * (size_t)B * I, st);
   cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, st);
-  dim3 grid(O, B);
-  adaconv_weights_bwd_kernel<<<grid, 256, 0, st>>>(bank, mod, attn, dinv, gw, dbank, dmod, gattn_ws, n, O, I, KK, demod, eps, Opad);
+  if (KK > 32) return gg_fail("adaconv backward: kernel area %d unsupported", KK);
+  if (demod) {
+    dim3 g1(O, B);
+    adaconv_q_kernel<<<g1, 256, 0, st>>>(bank, mod, attn, gw, q, n, O, I, KK, Opad);
+  }
+  dim3 grid(gg_cdiv(I, 32), O);
+  size_t smem = sizeof(float) * ((size_t)KK * 32 + (size_t)B * n);
+  adaconv_weights_bwd_kernel<<<grid, 32 * KK, smem, st>>>(bank, mod, attn, dinv, q, gw, dbank, dmod, gattn_ws, B, n, O, I,
+                                                         KK, demod, eps, Opad);
   if (n > 1 && dkmod) adaconv_kmod_bwd_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(attn, gattn_ws, dkmod, B, n);
   return gg_check_launch("adaconv_weights_bwd");
 }
@@ -620,3 +757,29 @@ int ggi_adamw(float* p, const float* g, float* m, float* v, const void* chunks, 
 }
 __global__ void incr_kernel(int* p) { *p += 1; }
 int ggi_incr(int* p, cudaStream_t st) { incr_kernel<<<1, 1, 0, st>>>(p); return gg_check_launch("incr"); }
+
+// ------------------------------------------------------------------ multi-tensor weight re-layout (once per step)
+// For every registered conv weight (fp32 master, reference layout [O][I][KK]) write BOTH kernel layouts in bf16/fp32:
+//   fwd[o][kk][ipad]            (K-major B operand of the forward implicit GEMM, input channels zero-padded)
+//   bwd[ipad][KK-1-kk][o]       (flipped + in/out swapped: the data gradient runs as a forward convolution)
+// entries: int64 x 8 = {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32 x 4 = {entry, start, count, 0}
+template <typename T>
+__global__ void weight_prep_multi_kernel(const float* __restrict__ master, const long* __restrict__ entries,
+                                         const int4* __restrict__ chunks, T* __restrict__ fwd, T* __restrict__ bwd) {
+  int4 ch = chunks[blockIdx.x];
+  const long* e = entries + (long)ch.x * 8;
+  const long src = e[0], O = e[1], I = e[2], KK = e[3], Ip = e[4], fo = e[5], bo = e[6];
+  for (int t = threadIdx.x; t < ch.z; t += blockDim.x) {
+    long idx = (long)ch.y + t;                 // linear index in the fwd layout [o][kk][ipad]
+    long i = idx % Ip, r = idx / Ip;
+    long kk = r % KK, o = r / KK;
+    float v = i < I ? master[src + (o * I + i) * KK + kk] : 0.f;
+    stf(fwd + fo + idx, v);
+    stf(bwd + bo + (i * KK + (KK - 1 - kk)) * O + o, v);
+  }
+}
+int ggi_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
+                          int dtype, cudaStream_t st) {
+  GG_DISPATCH(dtype, (weight_prep_multi_kernel<T><<<nchunks, 256, 0, st>>>(master, (const long*)entries, (const int4*)chunks, (T*)fwd, (T*)bwd)));
+  return gg_check_launch("weight_prep_multi");
+}

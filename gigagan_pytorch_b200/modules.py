@@ -16,9 +16,9 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .ops import U_GELU, U_INVNORM, U_SIGMOID, U_SILU
+from .ops import U_GELU, U_INVNORM, U_RSQRT_EPS8, U_SIGMOID, U_SILU
 
-_COMPUTE = {"dtype": torch.float32, "fused_attention": True}
+_COMPUTE = {"dtype": torch.float32, "fused_attention": False}
 
 
 def set_compute_dtype(dtype):
@@ -121,8 +121,51 @@ class AdaptiveConv2DMod(nn.Module):
         else:
             assert not exists(kernel_mod) or kernel_mod.numel() == 0
             kernel_mod = None
+        hw = x.shape[1] * x.shape[2]
+        if x.dtype == torch.bfloat16 and hw < 128 and self.eps == 1e-8:
+            return self._forward_shared_bank(x, mod, kernel_mod, out_pad)
         w = ops.AdaConvWeightsFn.apply(self.weights, mod, kernel_mod, self.demod, self.eps, x.dtype, out_pad)
         return ops.conv2d_prepared(x, w, pad=(self.kernel - 1) // 2, per_sample=True)
+
+    def _forward_shared_bank(self, x, mod, kernel_mod, out_pad=0):
+        """Low-resolution layers (4x4, 8x8): B private 512x512x9 filters are weight-bandwidth bound and leave the
+        128-row MMA tile empty.  Use  y_b = d_b * sum_n a_bn conv(x_b * s_b, W_n)  with the SHARED bank W_n
+        (SURVEY.md section 7 identity): dense tcgen05 convolutions whose M tile spans images; the demodulation
+        d_bo = rsqrt(max(sum_i s_bi^2 sum_nm a_bn a_bm <W_n,W_m>_k [o,i], eps)) is built from small fp32 operators."""
+        b, h, w_, i = x.shape
+        n, o, _, k, _ = self.weights.shape
+        one = torch.ones((1, i), dtype=torch.float32, device=x.device)
+        s = ops.add_channels(mod.float().contiguous(), one, b, 1)                    # (b, i) = mod + 1
+        xs = ops.scale_channels(x, s, h * w_, b)
+        if self.adaptive:
+            a = ops.softmax(kernel_mod.float().contiguous())                          # (b, n)
+        else:
+            a = torch.ones((b, 1), dtype=torch.float32, device=x.device)
+        pad = (self.kernel - 1) // 2
+        y = None
+        for j in range(n):
+            wj = self.weights[j]
+            if out_pad > o:                 # zero filters up to the padded channel count of image-like tensors
+                wj = F.pad(wj, (0, 0, 0, 0, 0, 0, 0, out_pad - o))
+            yj = ops.conv2d(xs, wj, pad=pad)
+            if self.adaptive:
+                yj = ops.scale_channels(yj, a[:, j:j + 1].expand(b, yj.shape[-1]).contiguous(), h * w_, b)
+            y = yj if y is None else ops.add(y, yj)
+        if not self.demod:
+            return y
+        s2 = ops.mul(s, s)
+        wf = self.weights.reshape(n, o * i, k * k)
+        t = None
+        for j in range(n):
+            for l in range(j, n):
+                gram = ops.rowdot(wf[j], wf[l]).reshape(o, i)                         # <W_j, W_l> over the taps
+                term = ops.linear(s2, gram)                                           # (b, o)
+                if self.adaptive:
+                    coef = ops.mul(a[:, j].contiguous(), a[:, l].contiguous())
+                    term = ops.scale_rows(term, coef if j == l else ops.axpby(2.0, coef))
+                t = term if t is None else ops.add(t, term)
+        d = ops.unary(U_RSQRT_EPS8, t)
+        return ops.scale_channels(y, d, h * w_, b)
 
     def forward(self, fmap, mod, kernel_mod=None):
         x = ops.to_nhwc(fmap, fmap.shape[1], compute_dtype())
@@ -485,7 +528,9 @@ class Predictor(nn.Module):
             x = ops.conv2d(x, conv2.weight, conv2.bias, pad=1, act=1)
             x = ops.axpby(self.residual_scale, x, self.residual_scale, inner)
         x = ops.add(x, residual)
-        return ops.conv2d(x, self.to_logits.weight, self.to_logits.bias)
+        n, h, w, c = x.shape
+        y = ops.linear_rows(x.reshape(n * h * w, c), self.to_logits.weight.reshape(1, c), self.to_logits.bias)
+        return y.reshape(n, h, w, 1)
 
 
 def DownsampleParams(dim):
@@ -628,8 +673,10 @@ class Discriminator(nn.Module):
                 img3 = images if images.shape[-1] == self.channels else images[..., : self.channels].contiguous()
                 aux_losses.append(decoder.forward_nhwc(x[:batch], img3))
         x = ops.conv2d(x, self.to_logits[0].weight, self.to_logits[0].bias, pad=1)
-        lw = self.to_logits[2].weight
-        logits = ops.conv2d(x, lw.view(1, x.shape[-1], 4, 4), self.to_logits[2].bias)      # flatten(c h w) @ W^T
+        lw = self.to_logits[2].weight                                                   # (1, c*h*w) in (c h w) order
+        c = x.shape[-1]
+        lw = lw.view(1, c, 4, 4).permute(0, 2, 3, 1).reshape(1, 16 * c)                  # -> (h w c) like NHWC rows
+        logits = ops.linear_rows(x.reshape(x.shape[0], 16 * c), lw, self.to_logits[2].bias)
         logits = logits.float().reshape(-1, batch)
         return logits, ms_outputs, aux_losses
 

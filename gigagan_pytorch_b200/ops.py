@@ -19,7 +19,7 @@ from torch.autograd.function import once_differentiable
 
 from ._lib import call
 
-U_LRELU, U_RELU, U_GELU, U_SILU, U_SIGMOID, U_INVNORM = range(6)
+U_LRELU, U_RELU, U_GELU, U_SILU, U_SIGMOID, U_INVNORM, U_RSQRT_EPS8 = range(7)
 ROWS, SAMPLE_CH = 0, 1
 MUL, ADD = 0, 1
 
@@ -62,12 +62,111 @@ class ConvGeom:
         return ConvGeom(self.kh, self.kw, self.stride, self.pad, self.per_sample)
 
 
+_WCACHE = {}
+
+
+def clear_weight_cache():
+    """Prepared (kernel-layout) weights are cached between the passes of one optimiser step; the trainer clears the
+    cache whenever parameters change (and at the start of every captured step)."""
+    _WCACHE.clear()
+
+
+class WeightBank:
+    """Both kernel layouts of every 4-D conv weight (and every filter of the 5-D AdaptiveConv banks) of a module
+    whose parameters live in one flat fp32 buffer, refreshed by ONE kernel launch per optimiser step."""
+
+    CHUNK = 1 << 14
+
+    def __init__(self, flat, params, dtype, cin_pad):
+        dev = flat.device
+        self.flat, self.dtype = flat, dtype
+        entries, chunks, self.views = [], [], {}
+        fo = bo = 0
+        base = flat.data_ptr()
+
+        def add(ptr, shape):
+            nonlocal fo, bo
+            O, I, KH, KW = shape
+            ipad = cin_pad(I)
+            n = O * KH * KW * ipad
+            eid = len(entries)
+            entries.append([(ptr - base) // 4, O, I, KH * KW, ipad, fo, bo, 0])
+            for s in range(0, n, self.CHUNK):
+                chunks.append([eid, s, min(self.CHUNK, n - s), 0])
+            self.views[(ptr, (O, I, KH, KW), ipad)] = (fo, (O, KH, KW, ipad), bo, (ipad, KH, KW, O))
+            fo += (n + 7) // 8 * 8
+            bo += (n + 7) // 8 * 8
+
+        for p in params:
+            if p.ndim == 4:
+                add(p.data_ptr(), tuple(p.shape))
+            elif p.ndim == 5:
+                per = p[0].numel() * 4
+                for j in range(p.shape[0]):
+                    add(p.data_ptr() + j * per, tuple(p.shape[1:]))
+        self.fwd = torch.empty(max(fo, 8), dtype=dtype, device=dev)
+        self.bwd = torch.empty(max(bo, 8), dtype=dtype, device=dev)
+        self.entries = torch.tensor(entries, dtype=torch.int64, device=dev)
+        self.chunks = torch.tensor(chunks, dtype=torch.int32, device=dev)
+
+    def refresh(self):
+        call("gg_weight_prep_multi", _p(self.flat), _p(self.entries), _p(self.chunks), self.chunks.shape[0],
+             _p(self.fwd), _p(self.bwd), _dt(self.fwd), _st())
+
+    def lookup(self, weight, cin, dtype):
+        if dtype != self.dtype:
+            return None
+        v = self.views.get((weight.data_ptr(), tuple(weight.shape), cin))
+        if v is None:
+            return None
+        fo, fs, bo, bs = v
+        n = fs[0] * fs[1] * fs[2] * fs[3]
+        return self.fwd[fo:fo + n].view(fs), self.bwd[bo:bo + n].view(bs)
+
+
+_BANKS = []
+
+
+def register_weight_bank(bank):
+    _BANKS.append(bank)
+
+
+def _bank_lookup(weight, cin, dtype):
+    for b in _BANKS:
+        r = b.lookup(weight, cin, dtype)
+        if r is not None:
+            return r
+    return None
+
+
 def prep_weight(weight, cin, dtype):
     """fp32 master (O,I,KH,KW) -> kernel layout (O,KH,KW,cin) in the compute dtype, zero-padding I up to cin."""
+    key = (weight.data_ptr(), tuple(weight.shape), cin, dtype, "f")
+    hit = _WCACHE.get(key)
+    if hit is not None:
+        return hit
+    r = _bank_lookup(weight, cin, dtype)
+    if r is not None:
+        _WCACHE[key] = r[0]
+        _WCACHE[(r[0].data_ptr(), tuple(r[0].shape), r[0].dtype, "t")] = (r[0], r[1])
+        return r[0]
     w = weight.detach().permute(0, 2, 3, 1)
     if w.shape[-1] != cin:
         w = torch.nn.functional.pad(w, (0, cin - w.shape[-1]))
-    return w.to(dtype).contiguous()
+    w = w.to(dtype).contiguous()
+    _WCACHE[key] = w
+    return w
+
+
+def flipped_weight(wk):
+    """kernel-layout ([N,]Cout,KH,KW,Cin) -> ([N,]Cin,KH,KW,Cout) with the taps reversed (dgrad as a convolution)."""
+    key = (wk.data_ptr(), tuple(wk.shape), wk.dtype, "t")
+    hit = _WCACHE.get(key)
+    if hit is not None and hit[0] is wk:
+        return hit[1]
+    wt = wk.flip((-3, -2)).transpose(-4, -1).contiguous()
+    _WCACHE[key] = (wk, wt)
+    return wt
 
 
 def unprep_weight_grad(gk, like):
@@ -125,7 +224,7 @@ def _conv_dgrad_raw(gy, wk, g, in_shape):
     if g.stride == 1:
         # data gradient of a stride-1 convolution == convolution of dy with the spatially flipped, in/out-swapped
         # filter and padding k-1-pad: reuse the forward kernel (tcgen05 when eligible).
-        wt = wk.flip((-3, -2)).transpose(-4, -1).contiguous()          # ([N,]Cin,KH,KW,Cout)
+        wt = flipped_weight(wk)                                        # ([N,]Cin,KH,KW,Cout)
         gt = ConvGeom(g.kh, g.kw, 1, g.kh - 1 - g.pad, g.per_sample)
         assert g.kh == g.kw
         return _conv_fprop_raw(gy, wt, None, None, gt, cin)
@@ -310,6 +409,19 @@ class BmmFn(Function):
 
 def bmm(a, b, alpha=1.0, out_bmhn=False):
     return BmmFn.apply(a, b, None, alpha, out_bmhn)
+
+
+def linear_rows(x2d, weight, bias=None):
+    """(R,K) activations (compute dtype) @ fp32 master weight (O,K)^T + bias -> (R,O).  In bf16 the output width is
+    padded to 16 so the product runs on the tcgen05 batched GEMM (used for 1-channel logit heads)."""
+    O, K = weight.shape
+    if x2d.dtype == torch.float32:
+        return linear(x2d, weight, bias)
+    opad = (O + 15) // 16 * 16
+    w = torch.nn.functional.pad(weight, (0, 0, 0, opad - O)).to(x2d.dtype)
+    b = None if bias is None else torch.nn.functional.pad(bias.float(), (0, opad - O))
+    y = BmmFn.apply(x2d[None, None], w.t()[None, None], b, 1.0, False)[0, 0]
+    return y[:, :O]
 
 
 def linear(x, weight, bias=None, alpha=1.0):
@@ -566,14 +678,37 @@ class SoftmaxFn(Function):
     def backward(ctx, gp):
         (p,) = ctx.saved_tensors
         P, Ns, has_bias, bshape = ctx.cfg
-        # dS = P * (gP - rowdot(P, gP))
-        t = mul(p, gp)
-        r = rowdot(p, gp)
-        ds = axpby(1.0, t, -1.0, scale_rows(p, r))
+        ds = SoftmaxBwdFn.apply(p, gp)
         gb = None
         if has_bias and ctx.needs_input_grad[1]:
             gb = dot_sc(ds, None, P, Ns).reshape(bshape)
         return ds, gb, None, None
+
+
+class SoftmaxBwdFn(Function):
+    """dS = P * (gP - rowdot(P, gP)) in one pass; its own backward is composed from closed primitives."""
+
+    @staticmethod
+    def forward(ctx, p, gp):
+        p, gp = _c(p), _c(gp)
+        C = p.shape[-1]
+        ds = torch.empty_like(p)
+        call("gg_softmax_bwd_rows", _p(p), _p(gp), _p(ds), p.numel() // C, C, _dt(p), _st())
+        ctx.save_for_backward(p, gp)
+        return ds
+
+    @staticmethod
+    def backward(ctx, G):
+        p, gp = ctx.saved_tensors
+        d_p = d_gp = None
+        if ctx.needs_input_grad[1]:
+            d_gp = SoftmaxBwdFn.apply(p, G)
+        if ctx.needs_input_grad[0]:
+            # d/dp_k = G_k (gp_k - r) - gp_k * rowdot(G, p),  r = rowdot(p, gp)
+            r = rowdot(p, gp)
+            t = axpby(1.0, mul(G, gp), -1.0, scale_rows(G, r))
+            d_p = axpby(1.0, t, -1.0, scale_rows(gp, rowdot(G, p)))
+        return d_p, d_gp
 
 
 def softmax(s, bias=None, rows_per_sample=1, num_samples=1):
@@ -757,7 +892,7 @@ class AdaConvWeightsFn(Function):
         dbank = torch.empty_like(bank)
         dmod = torch.empty_like(mod)
         dkmod = torch.empty((B, n), dtype=torch.float32, device=bank.device) if has_kmod else None
-        ws = torch.empty((B, n), dtype=torch.float32, device=bank.device)
+        ws = torch.empty((B * n + B * O,), dtype=torch.float32, device=bank.device)
         call("gg_adaconv_weights_bwd", _p(bank), _p(mod), _p(attn), _p(dinv), _p(gw), _p(dbank), _p(dmod), _p(dkmod),
              _p(ws), B, n, O, I, k * k, int(demod), float(eps), opad, _st())
         return dbank, dmod, dkmod, None, None, None, None

@@ -142,6 +142,7 @@ class FlatAdamW:
             off += p.numel()
 
     def step(self, grad_scale=1.0):
+        ops.clear_weight_cache()
         if self.flat.device.type != "cuda":
             raise RuntimeError("FlatAdamW.step needs the parameters on the GPU (no CPU path)")
         call("gg_incr", _p(self.step_t), _st())
@@ -256,6 +257,12 @@ class GigaGAN(nn.Module):
                 self.create_ema_generator()          # before flattening: deepcopy of flat views would copy storages
             self.G_opt = FlatAdamW(self.G, lr=self.learning_rate, betas=self.betas)
             self.D_opt = FlatAdamW(self.D, lr=self.learning_rate, betas=self.betas)
+            self._banks = []
+            if compute_dtype() == torch.bfloat16:
+                for opt in (self.G_opt, self.D_opt):
+                    bank = ops.WeightBank(opt.flat, opt.params, torch.bfloat16, img_cpad)
+                    ops.register_weight_bank(bank)
+                    self._banks.append(bank)
 
     def create_ema_generator(self, update_every=10, update_after_step=100, decay=0.995):
         if not self.is_main:
@@ -327,7 +334,7 @@ class GigaGAN(nn.Module):
             fake, rgbs = G.forward_nhwc(noise=noise)
         fake = fake.detach().requires_grad_(gp_on)
         rgbs = [t.detach().requires_grad_(gp_on) for t in rgbs]
-        fused = not gp_on
+        fused = False if gp_on else None      # gradient penalty needs the any-order-differentiable attention
         fl, fm, _ = D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False, fused_attention=fused)
         rl, rm, aux = D.forward_nhwc(real_n, real_rgbs, calc_multiscale_loss, True, fused_attention=fused)
         div = discriminator_hinge_loss(rl, fl)
@@ -392,6 +399,13 @@ class GigaGAN(nn.Module):
         self.graph_kernel_launches += n
         return outs
 
+    def _begin_work(self):
+        """start of a fwd+bwd pass over fresh parameters: drop cached layouts, re-lay-out all conv weights (1 launch
+        per model)."""
+        ops.clear_weight_cache()
+        for bank in getattr(self, "_banks", []):
+            bank.refresh()
+
     def _stage_real(self, real):
         if self._real_buf is None or self._real_buf.shape != real.shape:
             self._real_buf = torch.empty(real.shape, dtype=torch.float32, device=self.device)
@@ -423,6 +437,7 @@ class GigaGAN(nn.Module):
             self._stage_real(self._next_images(dl_iter))
 
             def work():
+                self._begin_work()
                 self.D_opt.zero_grad()
                 real = self._real_buf.detach()
                 noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
@@ -432,6 +447,7 @@ class GigaGAN(nn.Module):
 
             acc = self._run(("D", bool(apply_gradient_penalty), bool(calc_multiscale_loss)), work)
         else:
+            self._begin_work()
             self.D_opt.zero_grad()
             for _ in range(grad_accum_every):
                 real = self._next_images(dl_iter)
@@ -460,6 +476,7 @@ class GigaGAN(nn.Module):
         try:
             if grad_accum_every == 1:
                 def work():
+                    self._begin_work()
                     self.G_opt.zero_grad()
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
                     total, parts = self._g_objective(noise, calc_multiscale_loss)
@@ -468,6 +485,7 @@ class GigaGAN(nn.Module):
 
                 acc = self._run(("G", batch_size, bool(calc_multiscale_loss)), work)
             else:
+                self._begin_work()
                 self.G_opt.zero_grad()
                 for _ in range(grad_accum_every):
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)

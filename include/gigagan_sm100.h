@@ -59,7 +59,7 @@ int gg_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int
 
 /* ---- pointwise maps with explicit derivative levels (replaces nn.LeakyReLU :109, F.relu :163, nn.GELU :738,
  * nn.SiLU/nn.Sigmoid :303-305, F.normalize's 1/max(||x||,eps) :231).  kind: 0 lrelu 1 relu 2 gelu 3 silu
- * 4 sigmoid 5 invnorm.  level 0: out=f(x); 1: out=a*f'(x); 2: out=a*b*f''(x). */
+ * 4 sigmoid 5 invnorm 6 rsqrt(max(x,1e-8)) (demodulation :399).  level 0: out=f(x); 1: out=a*f'(x); 2: out=a*b*f''(x). */
 int gg_pw_unary(int kind, int level, const void* x, const void* a, const void* b, void* out, int64_t n, int dtype,
                 gg_stream_t stream);
 int gg_pw_mul(const void* a, const void* b, void* out, int64_t n, int dtype, gg_stream_t stream);
@@ -77,6 +77,9 @@ int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, in
  * (r / P) % Ns  (gigagan_pytorch.py:584-588 with the key bias of the L2 logits, :649; attend.py:104) */
 int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C, int P, int Ns, int dtype,
                     gg_stream_t stream);
+
+/* ds = p * (gp - rowsum(p * gp)): softmax backward for one [R,C] matrix (autograd of the softmax at :588) */
+int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream);
 
 /* ---- separable sparse resampling of NHWC maps: bilinear x2 + [1,2,1]^2/16 reflect blur (:246-261), bilinear
  * F.interpolate (:1683-1687) and their transposes.  Tap tables: iy/wy [OH][Ty], ix/wx [OW][Tx]. */
@@ -99,6 +102,7 @@ int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx
  * attn [B][n], dinv [B][O] saved for backward. */
 int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
                            int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, gg_stream_t stream);
+/* gattn_ws: workspace of B*n + B*O floats */
 int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
                            int demod, float eps, int Opad, gg_stream_t stream);
@@ -109,6 +113,12 @@ int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* att
 int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse,
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
                 float scale, int mode, int dtype, gg_stream_t stream);
+/* tcgen05 variant of gg_attn_fwd (bf16, dim_head 64, tokens a multiple of 128): QK^T and PV on the tensor cores,
+ * TMEM accumulators, two-pass softmax.  lse2 is the log-sum-exp in log2 units of the scaled logits;
+ * ksq_ws [B*heads*nk] fp32 workspace (L2 mode). */
+int gg_attn_fwd_tc(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse2, float* ksq_ws,
+                   int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
+                   float scale, int mode, gg_stream_t stream);
 int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
                 const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws,
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
@@ -119,6 +129,12 @@ int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_k
 int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr,
              float lr, float b1, float b2, float eps, float wd, float grad_scale, gg_stream_t stream);
 int gg_incr(int* p, gg_stream_t stream);
+/* ---- once-per-step re-layout of all conv weights of a model from the flat fp32 master buffer (reference layout
+ * [O][I][KK]) into both kernel layouts: fwd [O][KK][Ipad] and bwd [Ipad][KK reversed][O] (replaces the per-call
+ * weight permutes cuDNN does internally for nn.Conv2d / F.conv2d and their autograd).
+ * entries: int64[8] {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32[4] {entry, start, count, 0}. */
+int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
+                         int dtype, gg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -374,3 +374,57 @@ def test_fused_attention_matches_composed_large():
     a = blk.forward_nhwc(x, fused=True)
     b = blk.forward_nhwc(x, fused=False)
     assert relmax(a, b) < 1e-4
+
+
+def test_adaptive_conv_shared_bank_identity_matches_per_sample():
+    """low-resolution AdaptiveConv2DMod: shared-bank dense formulation (bf16, tcgen05) vs the reference algorithm
+    (oracle, fp32) forward and every gradient."""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    from oracle import gigagan_oracle as O
+    torch.manual_seed(0)
+    m = g.AdaptiveConv2DMod(64, 32, 3, num_conv_kernels=2).to(dev())
+    x = rn(1, 4, 64, 8, 8).to(dev())
+    mod, km = (rn(2, 4, 64) * 0.5).to(dev()), rn(3, 4, 2).to(dev())
+    xr, wr, mr, kr = (t.detach().clone().requires_grad_() for t in (x, m.weights, mod, km))
+    ref = O.adaptive_conv2d_mod(wr, xr, mr, kr)
+    gy = torch.randn_like(ref)
+    gref = torch.autograd.grad(ref, (xr, wr, mr, kr), gy)
+    g.set_compute_dtype(torch.bfloat16)
+    xn = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).requires_grad_()
+    mod2, km2 = mod.clone().requires_grad_(), km.clone().requires_grad_()
+    y = m.forward_nhwc(xn, mod2, km2)
+    assert relmax(y.permute(0, 3, 1, 2), ref) < 2e-2
+    gm = torch.autograd.grad(y, (xn, m.weights, mod2, km2), gy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    assert relmax(gm[0].permute(0, 3, 1, 2), gref[0]) < 3e-2
+    for a, b in zip(gm[1:], gref[1:]):
+        assert relmax(a, b) < 3e-2
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n", [256, 1024])
+def test_tcgen05_fused_attention_forward(mode, n):
+    """tcgen05 fused attention (TMEM S/O, two-pass softmax) vs the FFMA flash kernel on identical bf16 inputs."""
+    from gigagan_pytorch_b200 import _lib
+    from gigagan_pytorch_b200.ops import _p, _st
+    B, heads, d = 3, 2, 64
+    dt = torch.bfloat16
+    qkv = (rn(1, B, n, 3 * heads * d) * 0.7).to(dev()).to(dt)          # strided views into one conv-like output
+    q, k, v = qkv[..., : heads * d], qkv[..., heads * d: 2 * heads * d], qkv[..., 2 * heads * d:]
+    if mode == 1:
+        k = q
+    null_kv = rn(2, 2, heads, d).to(dev())
+    scale = d ** -0.5
+    o1 = torch.empty((B, n, heads * d), dtype=dt, device=dev())
+    o2 = torch.empty_like(o1)
+    l1 = torch.empty((B * heads, n), dtype=torch.float32, device=dev())
+    l2 = torch.empty_like(l1)
+    ws = torch.empty((B * heads * n,), dtype=torch.float32, device=dev())
+    rs = qkv.stride(1)
+    _lib.call("gg_attn_fwd", _p(q), _p(k), _p(v), _p(null_kv), _p(o1), _p(l1), B, heads, n, n, d, rs, rs, rs, o1.stride(1),
+              float(scale), mode, 1, _st())
+    _lib.call("gg_attn_fwd_tc", _p(q), _p(k), _p(v), _p(null_kv), _p(o2), _p(l2), _p(ws), B, heads, n, n, d, rs, rs, rs,
+              o2.stride(1), float(scale), mode, _st())
+    torch.cuda.synchronize()
+    assert relmax(o2, o1) < 2e-2, relmax(o2, o1)
+    assert (l2 - l1 * 1.4426950408889634).abs().max().item() < 2e-2

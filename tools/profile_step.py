@@ -45,3 +45,9 @@ for name, gp in (("plain", False), ("gp", True)):
         torch.cuda.synchronize()
     print(f"===== {name} step: top kernels by CUDA time")
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=32, max_name_column_width=70))
+    ka = [k for k in prof.key_averages() if k.device_type.name == "CUDA" or getattr(k, "self_device_time_total", 0) > 0]
+    rows = sorted(((k.count, k.self_device_time_total / 1e3, k.key[:90]) for k in prof.key_averages()
+                   if k.self_device_time_total > 0), reverse=True)[:45]
+    print(f"===== {name} step: kernels/ops by launch count (count, self CUDA ms, name)")
+    for r in rows:
+        print(f"{r[0]:6d} {r[1]:9.3f}  {r[2]}")
