@@ -331,3 +331,482 @@ int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* nu
   attn_fwd_tc_kernel<<<grid, ATC_THREADS, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
   return gg_check_launch("attn_fwd_tc");
 }
+
+// =================================================================================================
+// Backward.  Two kernels (same structure as the forward: TMA producer warp, MMA warp, 4 softmax warps):
+//   attn_bwd_dq_tc : CTA per query tile, loops key tiles:  S = Q K^T, dP = dO V^T, dS' = P (dP - delta) ls,
+//                    dQ += dS' K.  Also delta = rowsum(dO * O) and the null key/value gradients.
+//   attn_bwd_dkv_tc: CTA per key tile, loops query tiles:  S, dP as above, dV += P^T dO, dK += dS'^T [Q | 1]
+//                    (the extra ones block makes column 64 of the accumulator the column sum needed by the L2 form).
+// P is recomputed from the saved log-sum-exp (log2 units); every matrix product runs on tcgen05.
+// =================================================================================================
+struct AtbP {
+  int B, heads, n, tiles, mode, has_null;
+  float c2, kb2, ls;
+  long o_rs;
+};
+
+// read the 64 bf16 of row r of a [128 x 64] SWIZZLE_128B K-major tile
+__device__ __forceinline__ void read_tile_row(const uint8_t* tile, int r, float* out) {
+  const uint8_t* row = tile + r * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 v = *reinterpret_cast<const uint4*>(row + ((c ^ (r & 7)) << 4));
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(hp[e]); out[c * 8 + 2 * e] = f.x; out[c * 8 + 2 * e + 1] = f.y; }
+  }
+}
+// write 16 consecutive columns [c0, c0+16) of row r of a [128 rows x 128 cols] bf16 tile stored as two 64-column
+// SWIZZLE_128B slabs (16 KB apart)
+__device__ __forceinline__ void write_tile16(uint8_t* tile, int r, int c0, const float* v) {
+  uint4 o0, o1;
+  __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+  __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    h1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+  }
+  int slab = c0 >> 6, ch = (c0 & 63) >> 3;
+  uint8_t* dst = tile + slab * 16384 + r * 128;
+  *reinterpret_cast<uint4*>(dst + ((ch ^ (r & 7)) << 4)) = o0;
+  *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ (r & 7)) << 4)) = o1;
+}
+__device__ __forceinline__ void store_row16(bf16* dst, const float* f) {
+  uint4 o0, o1;
+  __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+  __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h0[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    h1[e] = __floats2bfloat162_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
+  }
+  reinterpret_cast<uint4*>(dst)[0] = o0;
+  reinterpret_cast<uint4*>(dst)[1] = o1;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AtbP p,
+                      const float* __restrict__ null_kv, const float* __restrict__ ksq, const bf16* __restrict__ o,
+                      const float* __restrict__ lse2, bf16* __restrict__ dq, float* __restrict__ delta,
+                      float* __restrict__ dnull) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sQ = base, sDO = base + 16384, sK = base + 32768, sV = base + 65536, sDS = base + 98304;
+  float* ksq_sm = (float*)(gbase + 163840);
+  float* null_sm = (float*)(gbase + 164864);
+  float* red_sm = (float*)(gbase + 165376);
+  const uint32_t bars = base + 166400;
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, DP_FULL = 13, DP_EMPTY = 14,
+         DS_FULL = 15, DS_EMPTY = 17, DQ_FULL = 19, NBAR = 20 };
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(gbase + 166400 + 8 * NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const int T = p.tiles;
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Q_FULL), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
+      mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
+      mbar_init(bar(DS_FULL + i), 4); mbar_init(bar(DS_EMPTY + i), 1);
+    }
+    mbar_init(bar(DP_FULL), 1); mbar_init(bar(DP_EMPTY), 4); mbar_init(bar(DQ_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x >= 64) {
+    int t = threadIdx.x - 64;
+    if (p.has_null) null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
+    red_sm[t] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + 256, tDQ = tmem + 384;
+  const uint32_t idesc_kk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc_dq = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar(Q_FULL), 32768);
+      tma_load_4d(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b);
+      tma_load_4d(sDO, &tmDO, bar(Q_FULL), 0, qt * ATC_T, h, b);
+      for (int j = 0; j < T; ++j) {
+        int s = j & 1;
+        uint32_t par = ((j >> 1) & 1) ^ 1u;
+        mbar_wait(bar(K_EMPTY + s), par);
+        mbar_expect_tx(bar(K_FULL + s), 16384);
+        tma_load_4d(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b);
+        mbar_wait(bar(V_EMPTY + s), par);
+        mbar_expect_tx(bar(V_FULL + s), 16384);
+        tma_load_4d(sV + s * 16384, &tmV, bar(V_FULL + s), 0, j * ATC_T, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    auto issue_S = [&](int j) {
+      int s = j & 1;
+      mbar_wait(bar(K_FULL + s), (j >> 1) & 1);
+      mbar_wait(bar(S_EMPTY + s), ((j >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + s * 16384, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tS + s * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        tc_commit(bar(S_FULL + s));
+      }
+      __syncwarp();
+    };
+    auto issue_dP = [&](int j) {
+      int s = j & 1;
+      mbar_wait(bar(V_FULL + s), (j >> 1) & 1);
+      mbar_wait(bar(DP_EMPTY), (j & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        uint64_t da = make_smem_desc(sDO, 1024, 2), db = make_smem_desc(sV + s * 16384, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        tc_commit(bar(DP_FULL));
+        tc_commit(bar(V_EMPTY + s));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(Q_FULL), 0);
+    issue_S(0);
+    issue_dP(0);
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) issue_S(j + 1);
+      int s = j & 1;
+      mbar_wait(bar(DS_FULL + s), (j >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint64_t da = make_smem_desc(sDS + s * 32768 + (k >> 2) * 16384, 1024, 2) + (uint64_t)(2 * (k & 3));
+          uint64_t db = make_smem_desc_mn(sK + s * 16384 + k * 2048, 0, 1024);
+          tc_mma_f16(tDQ, da, db, idesc_dq, (j | k) ? 1u : 0u);
+        }
+        tc_commit(bar(DS_EMPTY + s));
+        tc_commit(bar(K_EMPTY + s));
+        if (j == T - 1) tc_commit(bar(DQ_FULL));
+      }
+      __syncwarp();
+      if (j + 1 < T) issue_dP(j + 1);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int st = threadIdx.x - 64;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const long grow = (long)b * p.n + qt * ATC_T + r;
+    const long srow = (long)bh * p.n + qt * ATC_T + r;
+    mbar_wait(bar(Q_FULL), 0);
+    float qrow[64], dorow[64];
+    read_tile_row(gbase + (sQ - base), r, qrow);
+    read_tile_row(gbase + (sDO - base), r, dorow);
+    // delta = rowsum(dO * O)
+    float dl = 0.f;
+    {
+      const bf16* orow = o + grow * p.o_rs + h * ATC_D;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(hp[e]); dl = fmaf(dorow[c * 8 + 2 * e], f.x, fmaf(dorow[c * 8 + 2 * e + 1], f.y, dl)); }
+      }
+    }
+    delta[srow] = dl;
+    const float L2 = lse2[srow];
+    float ds_null = 0.f, p_null = 0.f;
+    if (p.has_null) {
+      float dot = 0.f, kn2 = 0.f, dpn = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { dot = fmaf(qrow[c], null_sm[c], dot); kn2 = fmaf(null_sm[c], null_sm[c], kn2); dpn = fmaf(dorow[c], null_sm[64 + c], dpn); }
+      float tn = dot * p.c2 + (p.mode == 1 ? p.kb2 * kn2 : 0.f);
+      p_null = fast_exp2(tn - L2);
+      ds_null = p_null * (dpn - dl) * p.ls;
+    }
+    for (int j = 0; j < T; ++j) {
+      int s = j & 1;
+      if (p.mode == 1) {
+        ksq_sm[s * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 128);
+      }
+      mbar_wait(bar(S_FULL + s), (j >> 1) & 1);
+      mbar_wait(bar(DP_FULL), j & 1);
+      mbar_wait(bar(DS_EMPTY + s), ((j >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      uint8_t* dstile = gbase + (sDS - base) + s * 32768;
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t sv[16], dv[16];
+        tc_ld16(tS + s * 128 + lane_addr + c0, sv);
+        tc_ld16(tDP + lane_addr + c0, dv);
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float t = __uint_as_float(sv[e]) * p.c2;
+          if (p.mode == 1) t += ksq_sm[s * 128 + c0 + e];
+          f[e] = fast_exp2(t - L2) * (__uint_as_float(dv[e]) - dl) * p.ls;
+        }
+        write_tile16(dstile, r, c0, f);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(DS_FULL + s)); mbar_arrive(bar(S_EMPTY + s)); mbar_arrive(bar(DP_EMPTY)); }
+    }
+    mbar_wait(bar(DQ_FULL), 0);
+    tc_fence_after();
+    bf16* dqrow = dq + grow * (long)(p.heads * ATC_D) + h * ATC_D;
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(tDQ + lane_addr + c0, v);
+      float f[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + (p.has_null ? ds_null * null_sm[c0 + e] : 0.f);
+      store_row16(dqrow + c0, f);
+    }
+    if (p.has_null) {        // null key/value gradients: reduce over the 128 rows of this CTA, then one atomic per value
+#pragma unroll 4
+      for (int c = 0; c < 64; ++c) {
+        float gk = ds_null * (qrow[c] - (p.mode == 1 ? null_sm[c] : 0.f));
+        float gv = p_null * dorow[c];
+        gk = warp_sum(gk); gv = warp_sum(gv);
+        if (lane == 0) { atomicAdd(&red_sm[c], gk); atomicAdd(&red_sm[64 + c], gv); }
+      }
+      named_bar_sync(1, 128);
+      atomicAdd(dnull + (st < 64 ? h * ATC_D + st : (p.heads + h) * ATC_D + (st - 64)), red_sm[st]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AtbP p,
+                       const float* __restrict__ ksq, const float* __restrict__ lse2, const float* __restrict__ delta,
+                       bf16* __restrict__ dk, bf16* __restrict__ dv) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  // K 16K | V 16K | [Q 16K | ones 16K] x2 | dO x2 | P 32K | dS 32K
+  const uint32_t sK = base, sV = base + 16384, sQO = base + 32768, sDO = base + 98304, sP = base + 131072, sDS = base + 163840;
+  float* ksq_sm = (float*)(gbase + 196608);
+  const uint32_t bars = base + 197120;
+  enum { KV_FULL = 0, QO_FULL = 1, QO_EMPTY = 3, SDP_FULL = 5, SDP_EMPTY = 6, PDS_FULL = 7, PDS_EMPTY = 8, OUT_FULL = 9, NBAR = 10 };
+  auto bar = [&](int i) { return bars + 8u * i; };
+  uint32_t* tmem_slot = (uint32_t*)(gbase + 197120 + 8 * NBAR);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
+  const int b = bh / p.heads, h = bh % p.heads;
+  const int T = p.tiles;
+  if (threadIdx.x == 0) {
+    mbar_init(bar(KV_FULL), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar(QO_FULL + i), 1); mbar_init(bar(QO_EMPTY + i), 1); }
+    mbar_init(bar(SDP_FULL), 1); mbar_init(bar(SDP_EMPTY), 4);
+    mbar_init(bar(PDS_FULL), 4); mbar_init(bar(PDS_EMPTY), 1); mbar_init(bar(OUT_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {   // the two "ones" slabs (bf16 1.0 everywhere; swizzle-invariant)
+    uint4 one4 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = threadIdx.x; i < 2 * 1024; i += ATC_THREADS) {
+      int buf = i >> 10, off = (i & 1023) << 4;
+      *reinterpret_cast<uint4*>(gbase + (sQO - base) + buf * 32768 + 16384 + off) = one4;
+    }
+    fence_async_smem();
+  }
+  if (threadIdx.x >= 64 && p.mode == 1) ksq_sm[threadIdx.x - 64] = ksq[(long)bh * p.n + kt * ATC_T + (threadIdx.x - 64)] * p.kb2;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+  const uint32_t idesc_kk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc_dv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t idesc_dk = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(80 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(bar(KV_FULL), 32768);
+      tma_load_4d(sK, &tmK, bar(KV_FULL), 0, kt * ATC_T, h, b);
+      tma_load_4d(sV, &tmV, bar(KV_FULL), 0, kt * ATC_T, h, b);
+      for (int i = 0; i < T; ++i) {
+        int s = i & 1;
+        mbar_wait(bar(QO_EMPTY + s), ((i >> 1) & 1) ^ 1u);
+        mbar_expect_tx(bar(QO_FULL + s), 32768);
+        tma_load_4d(sQO + s * 32768, &tmQ, bar(QO_FULL + s), 0, i * ATC_T, h, b);
+        tma_load_4d(sDO + s * 16384, &tmDO, bar(QO_FULL + s), 0, i * ATC_T, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    auto issue_SdP = [&](int i) {
+      int s = i & 1;
+      mbar_wait(bar(QO_FULL + s), (i >> 1) & 1);
+      mbar_wait(bar(SDP_EMPTY), (i & 1) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        uint64_t dq_ = make_smem_desc(sQO + s * 32768, 1024, 2), dk_ = make_smem_desc(sK, 1024, 2);
+        uint64_t do_ = make_smem_desc(sDO + s * 16384, 1024, 2), dv_ = make_smem_desc(sV, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tS, dq_ + (uint64_t)(2 * k), dk_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, do_ + (uint64_t)(2 * k), dv_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        tc_commit(bar(SDP_FULL));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(KV_FULL), 0);
+    issue_SdP(0);
+    for (int i = 0; i < T; ++i) {
+      int s = i & 1;
+      mbar_wait(bar(PDS_FULL), i & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {      // K axis = the 128 queries of this tile, 16 per step
+          uint64_t ap = make_smem_desc_mn(sP + k * 2048, 16384, 1024);
+          uint64_t bo = make_smem_desc_mn(sDO + s * 16384 + k * 2048, 0, 1024);
+          tc_mma_f16(tDV, ap, bo, idesc_dv, (i | k) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint64_t as_ = make_smem_desc_mn(sDS + k * 2048, 16384, 1024);
+          uint64_t bq = make_smem_desc_mn(sQO + s * 32768 + k * 2048, 16384, 1024);
+          tc_mma_f16(tDK, as_, bq, idesc_dk, (i | k) ? 1u : 0u);
+        }
+        tc_commit(bar(PDS_EMPTY));
+        tc_commit(bar(QO_EMPTY + s));
+        if (i == T - 1) tc_commit(bar(OUT_FULL));
+      }
+      __syncwarp();
+      if (i + 1 < T) issue_SdP(i + 1);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint8_t* ptile = gbase + (sP - base);
+    uint8_t* dstile = gbase + (sDS - base);
+    for (int i = 0; i < T; ++i) {
+      const long srow = (long)bh * p.n + i * ATC_T + r;
+      const float L2 = lse2[srow], dl = delta[srow];
+      mbar_wait(bar(SDP_FULL), i & 1);
+      mbar_wait(bar(PDS_EMPTY), (i & 1) ^ 1u);
+      tc_fence_after();
+#pragma unroll 2
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        uint32_t sv[16], dv_[16];
+        tc_ld16(tS + lane_addr + c0, sv);
+        tc_ld16(tDP + lane_addr + c0, dv_);
+        float pf[16], df[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float t = __uint_as_float(sv[e]) * p.c2;
+          if (p.mode == 1) t += ksq_sm[c0 + e];
+          pf[e] = fast_exp2(t - L2);
+          df[e] = pf[e] * (__uint_as_float(dv_[e]) - dl) * p.ls;
+        }
+        write_tile16(ptile, r, c0, pf);
+        write_tile16(dstile, r, c0, df);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar(PDS_FULL)); mbar_arrive(bar(SDP_EMPTY)); }
+    }
+    // epilogue: thread <-> key row
+    mbar_wait(bar(OUT_FULL), 0);
+    tc_fence_after();
+    const long grow = (long)b * p.n + kt * ATC_T + r;
+    bf16* dvrow = dv + grow * (long)(p.heads * ATC_D) + h * ATC_D;
+    bf16* dkrow = dk + grow * (long)(p.heads * ATC_D) + h * ATC_D;
+    float csum = 0.f;
+    float krow[64];
+    if (p.mode == 1) {
+      uint32_t v[16];
+      tc_ld16(tDK + lane_addr + 64, v);
+      csum = __uint_as_float(v[0]);
+      read_tile_row(gbase + (sK - base), r, krow);
+    }
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 16) {
+      uint32_t v[16];
+      float f[16];
+      tc_ld16(tDV + lane_addr + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+      store_row16(dvrow + c0, f);
+      tc_ld16(tDK + lane_addr + c0, v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) - (p.mode == 1 ? csum * krow[c0 + e] : 0.f);
+      store_row16(dkrow + c0, f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+// go, dq, dk, dv: dense (B, n, heads*64).  Returns 1 when not eligible.
+int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
+                    const float* lse2, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
+                    int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
+                    int mode, cudaStream_t st) {
+  if (d != ATC_D || nq != nk || nq % ATC_T || nq < ATC_T) return 1;
+  if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 8)) return 1;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)go | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) return 1;
+  if (mode == 1 && !ksq_ws) return 1;
+  AtbP p;
+  p.B = B; p.heads = heads; p.n = nq; p.tiles = nq / ATC_T; p.mode = mode; p.has_null = null_kv != nullptr;
+  const float log2e = 1.4426950408889634f;
+  p.ls = mode == 1 ? 2.f * scale : scale;
+  p.c2 = p.ls * log2e;
+  p.kb2 = -scale * log2e;
+  p.o_rs = o_rs;
+  CUtensorMap tmQ, tmK, tmV, tmDO;
+  long hd = (long)heads * ATC_D;
+  if (make_qkv_map(&tmQ, q, B, nq, heads, q_rs) || make_qkv_map(&tmK, k, B, nk, heads, k_rs) ||
+      make_qkv_map(&tmV, v, B, nk, heads, v_rs) || make_qkv_map(&tmDO, go, B, nq, heads, hd)) return -1;
+  if (mode == 1) {
+    long rows = (long)B * heads * nk;
+    attn_ksq_kernel<<<gg_cdiv(rows, 8), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
+  }
+  if (p.has_null) cudaMemsetAsync(dnull_kv, 0, sizeof(float) * 2 * heads * ATC_D, st);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  int grid = B * heads * p.tiles;
+  size_t smem1 = 1024 + 166400 + 8 * 20 + 16, smem2 = 1024 + 197120 + 8 * 10 + 16;
+  attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, dnull_kv);
+  attn_bwd_dkv_tc_kernel<<<grid, ATC_THREADS, smem2, st>>>(tmQ, tmK, tmV, tmDO, p, ksq_ws, lse2, delta_ws, (bf16*)dk, (bf16*)dv);
+  return gg_check_launch("attn_bwd_tc");
+}

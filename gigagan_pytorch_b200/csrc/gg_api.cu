@@ -134,22 +134,27 @@ int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* att
                            int demod, float eps, int Opad, gg_stream_t stream) {
   return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, Opad, ST);
 }
-int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, int B, int heads,
-                int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,
-                int dtype, gg_stream_t stream) {
+int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
+                int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale,
+                int mode, int dtype, gg_stream_t stream) {
+#ifndef GG_NO_TC
+  if (dtype == GG_BF16 && !(g_flags & 1)) {
+    int r = ggi_tc_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
+    if (r <= 0) return r;
+  }
+#endif
   return ggi_attn_fwd(q, k, v, null_kv, o, lse, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, dtype, ST);
 }
-int gg_attn_fwd_tc(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse2, float* ksq_ws,
-                   int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
-                   float scale, int mode, gg_stream_t stream) {
-  int r = ggi_tc_attn_fwd(q, k, v, null_kv, o, lse2, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
-  if (r == 1) return gg_fail("gg_attn_fwd_tc: shape not eligible (dim_head 64, tokens %% 128 == 0, 16-byte aligned rows)");
-  return r;
-}
 int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
-                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, int B, int heads,
-                int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, int mode,
-                int dtype, gg_stream_t stream) {
+                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws, int B,
+                int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale,
+                int mode, int dtype, gg_stream_t stream) {
+#ifndef GG_NO_TC
+  if (dtype == GG_BF16 && !(g_flags & 1)) {
+    int r = ggi_tc_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
+    if (r <= 0) return r;
+  }
+#endif
   return ggi_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, dtype, ST);
 }
 int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr, float lr,

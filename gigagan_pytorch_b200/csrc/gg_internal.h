@@ -54,3 +54,7 @@ int ggi_weight_prep_multi(const float* master, const void* entries, const void* 
 int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
                     int mode, cudaStream_t st);
+int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
+                    const float* lse2, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
+                    int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
+                    int mode, cudaStream_t st);

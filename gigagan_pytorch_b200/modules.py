@@ -18,7 +18,7 @@ from torch import nn
 from . import ops
 from .ops import U_GELU, U_INVNORM, U_RSQRT_EPS8, U_SIGMOID, U_SILU
 
-_COMPUTE = {"dtype": torch.float32, "fused_attention": False}
+_COMPUTE = {"dtype": torch.float32, "fused_attention": True}
 
 
 def set_compute_dtype(dtype):

@@ -141,20 +141,21 @@ def _bank_lookup(weight, cin, dtype):
 
 def prep_weight(weight, cin, dtype):
     """fp32 master (O,I,KH,KW) -> kernel layout (O,KH,KW,cin) in the compute dtype, zero-padding I up to cin."""
+    base = weight._base if weight._base is not None else weight
     key = (weight.data_ptr(), tuple(weight.shape), cin, dtype, "f")
     hit = _WCACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[1] is base and hit[2] == base._version:     # same storage owner, not modified since
+        return hit[0]
     r = _bank_lookup(weight, cin, dtype)
     if r is not None:
-        _WCACHE[key] = r[0]
+        _WCACHE[key] = (r[0], base, base._version)
         _WCACHE[(r[0].data_ptr(), tuple(r[0].shape), r[0].dtype, "t")] = (r[0], r[1])
         return r[0]
     w = weight.detach().permute(0, 2, 3, 1)
     if w.shape[-1] != cin:
         w = torch.nn.functional.pad(w, (0, cin - w.shape[-1]))
     w = w.to(dtype).contiguous()
-    _WCACHE[key] = w
+    _WCACHE[key] = (w, base, base._version)
     return w
 
 
@@ -936,8 +937,9 @@ class FusedAttnFn(Function):
         nkv = None if null_kv is None else _c(null_kv.float())
         o = torch.empty((B, nq, hd), dtype=q.dtype, device=q.device)
         lse = torch.empty((B * heads, nq), dtype=torch.float32, device=q.device)
-        call("gg_attn_fwd", _p(q), _p(k), _p(v), _p(nkv), _p(o), _p(lse), B, heads, nq, nk, d, q.stride(1), k.stride(1),
-             v.stride(1), o.stride(1), float(scale), int(l2), _dt(q), _st())
+        ws = torch.empty((B * heads * nk,), dtype=torch.float32, device=q.device) if l2 else None
+        call("gg_attn_fwd", _p(q), _p(k), _p(v), _p(nkv), _p(o), _p(lse), _p(ws), B, heads, nq, nk, d, q.stride(1),
+             k.stride(1), v.stride(1), o.stride(1), float(scale), int(l2), _dt(q), _st())
         ctx.cfg = (heads, scale, l2, shared_qk)
         ctx.save_for_backward(q, k, v, nkv, o, lse)
         return o
@@ -958,8 +960,9 @@ class FusedAttnFn(Function):
         # the backward kernel indexes dq/dk/dv with the strides of q/k/v: give it dense copies' strides
         assert go.stride(1) == o.stride(1)
         qc, kc, vc = _c(q), _c(k), _c(v)
+        ws = torch.empty((B * heads * nk,), dtype=torch.float32, device=q.device) if l2 else None
         call("gg_attn_bwd", _p(qc), _p(kc), _p(vc), _p(nkv), _p(o), _p(go), _p(lse), _p(dq), _p(dk), _p(dv), _p(dnull),
-             _p(delta), B, heads, nq, nk, d, qc.stride(1), kc.stride(1), vc.stride(1), o.stride(1), float(scale),
+             _p(delta), _p(ws), B, heads, nq, nk, d, qc.stride(1), kc.stride(1), vc.stride(1), o.stride(1), float(scale),
              int(l2), _dt(q), _st())
         if shared:
             dq = add(dq, dk)

@@ -109,18 +109,16 @@ int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* att
 
 /* ---- fused attention (gigagan_pytorch.py:562-592 with null key/value and L2-distance logits; attend.py:64-110)
  * q,k,v,o: [B, n, heads, d] rows with the given row strides (elements); null_kv [2][heads][d] fp32 or NULL.
- * mode 0 dot-product, 1 shared-QK L2 distance.  lse [B*heads][nq] fp32 saved for backward. */
-int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse,
+ * mode 0 dot-product, 1 shared-QK L2 distance.  lse [B*heads][nq] fp32 saved for backward (opaque: natural-log
+ * units from the FFMA kernels, log2 units from the tcgen05 kernels; fwd and bwd of one call pair agree).
+ * bf16 with dim_head 64 and tokens %% 128 == 0 runs on tcgen05 (QK^T, PV, and all five backward products on the
+ * tensor cores, TMEM accumulators, softmax out of TMEM); ksq_ws [B*heads*nk] fp32 workspace for the L2 form;
+ * go/dq/dk/dv of the backward are dense (B, n, heads*d). */
+int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
                 float scale, int mode, int dtype, gg_stream_t stream);
-/* tcgen05 variant of gg_attn_fwd (bf16, dim_head 64, tokens a multiple of 128): QK^T and PV on the tensor cores,
- * TMEM accumulators, two-pass softmax.  lse2 is the log-sum-exp in log2 units of the scaled logits;
- * ksq_ws [B*heads*nk] fp32 workspace (L2 mode). */
-int gg_attn_fwd_tc(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse2, float* ksq_ws,
-                   int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
-                   float scale, int mode, gg_stream_t stream);
 int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
-                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws,
+                const float* lse, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
                 float scale, int mode, int dtype, gg_stream_t stream);
 

@@ -403,28 +403,29 @@ def test_adaptive_conv_shared_bank_identity_matches_per_sample():
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("n", [256, 1024])
-def test_tcgen05_fused_attention_forward(mode, n):
-    """tcgen05 fused attention (TMEM S/O, two-pass softmax) vs the FFMA flash kernel on identical bf16 inputs."""
-    from gigagan_pytorch_b200 import _lib
-    from gigagan_pytorch_b200.ops import _p, _st
+def test_tcgen05_fused_attention(mode, n):
+    """tcgen05 fused attention forward + backward (TMEM accumulators, softmax out of TMEM, P/dS through swizzled
+    smem) vs the FFMA flash kernels on identical bf16 inputs (strided q/k/v views, null key/value, dot and L2)."""
+    from gigagan_pytorch_b200 import _lib, ops
     B, heads, d = 3, 2, 64
     dt = torch.bfloat16
-    qkv = (rn(1, B, n, 3 * heads * d) * 0.7).to(dev()).to(dt)          # strided views into one conv-like output
-    q, k, v = qkv[..., : heads * d], qkv[..., heads * d: 2 * heads * d], qkv[..., 2 * heads * d:]
-    if mode == 1:
-        k = q
+    L = _lib.lib()
     null_kv = rn(2, 2, heads, d).to(dev())
-    scale = d ** -0.5
-    o1 = torch.empty((B, n, heads * d), dtype=dt, device=dev())
-    o2 = torch.empty_like(o1)
-    l1 = torch.empty((B * heads, n), dtype=torch.float32, device=dev())
-    l2 = torch.empty_like(l1)
-    ws = torch.empty((B * heads * n,), dtype=torch.float32, device=dev())
-    rs = qkv.stride(1)
-    _lib.call("gg_attn_fwd", _p(q), _p(k), _p(v), _p(null_kv), _p(o1), _p(l1), B, heads, n, n, d, rs, rs, rs, o1.stride(1),
-              float(scale), mode, 1, _st())
-    _lib.call("gg_attn_fwd_tc", _p(q), _p(k), _p(v), _p(null_kv), _p(o2), _p(l2), _p(ws), B, heads, n, n, d, rs, rs, rs,
-              o2.stride(1), float(scale), mode, _st())
+    go = (rn(3, B, n, heads * d)).to(dev()).to(dt)
+    res = []
+    for force_ffma in (0, 1):
+        qkv = (rn(1, B, n, 3 * heads * d) * 0.7).to(dev()).to(dt).requires_grad_()
+        nk = null_kv.clone().requires_grad_()
+        q, k, v = qkv[..., : heads * d], qkv[..., heads * d: 2 * heads * d], qkv[..., 2 * heads * d:]
+        old = L.gg_set_flags(force_ffma)
+        try:
+            o = ops.fused_attention(q, q if mode == 1 else k, v, nk, heads, d ** -0.5, l2=(mode == 1))
+            g1, g2 = torch.autograd.grad(o, (qkv, nk), go)
+        finally:
+            L.gg_set_flags(old)
+        res.append((o.detach(), g1, g2))
     torch.cuda.synchronize()
-    assert relmax(o2, o1) < 2e-2, relmax(o2, o1)
-    assert (l2 - l1 * 1.4426950408889634).abs().max().item() < 2e-2
+    (o_tc, gq_tc, gn_tc), (o_ff, gq_ff, gn_ff) = res
+    assert relmax(o_tc, o_ff) < 2e-2, relmax(o_tc, o_ff)
+    assert relmax(gq_tc, gq_ff) < 3e-2, relmax(gq_tc, gq_ff)
+    assert relmax(gn_tc, gn_ff) < 3e-2, relmax(gn_tc, gn_ff)
