@@ -391,7 +391,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AtbP p,
                       const float* __restrict__ null_kv, const float* __restrict__ ksq, const bf16* __restrict__ o,
                       const float* __restrict__ lse2, bf16* __restrict__ dq, float* __restrict__ delta,
-                      float* __restrict__ dnull) {
+                      float* __restrict__ nullrow) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -399,7 +399,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t sQ = base, sDO = base + 16384, sK = base + 32768, sV = base + 65536, sDS = base + 98304;
   float* ksq_sm = (float*)(gbase + 163840);
   float* null_sm = (float*)(gbase + 164864);
-  float* red_sm = (float*)(gbase + 165376);
   const uint32_t bars = base + 166400;
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, DP_FULL = 13, DP_EMPTY = 14,
          DS_FULL = 15, DS_EMPTY = 17, DQ_FULL = 19, NBAR = 20 };
@@ -427,7 +426,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (threadIdx.x >= 64) {
     int t = threadIdx.x - 64;
     if (p.has_null) null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
-    red_sm[t] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -511,31 +509,43 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const long grow = (long)b * p.n + qt * ATC_T + r;
     const long srow = (long)bh * p.n + qt * ATC_T + r;
     mbar_wait(bar(Q_FULL), 0);
-    float qrow[64], dorow[64];
-    read_tile_row(gbase + (sQ - base), r, qrow);
-    read_tile_row(gbase + (sDO - base), r, dorow);
-    // delta = rowsum(dO * O)
-    float dl = 0.f;
+    // streaming pass over this row of Q, dO (smem tiles) and O (global): delta = dO.O, q.k_null, dO.v_null
+    float dl = 0.f, dot = 0.f, kn2 = 0.f, dpn = 0.f;
     {
+      const uint8_t* qr = gbase + (sQ - base) + r * 128;
+      const uint8_t* dr = gbase + (sDO - base) + r * 128;
       const bf16* orow = o + grow * p.o_rs + h * ATC_D;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        uint4 v = __ldg(reinterpret_cast<const uint4*>(orow) + c);
-        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&v);
+        uint4 qv = *reinterpret_cast<const uint4*>(qr + ((c ^ (r & 7)) << 4));
+        uint4 dv = *reinterpret_cast<const uint4*>(dr + ((c ^ (r & 7)) << 4));
+        uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+        const __nv_bfloat162* qh = reinterpret_cast<const __nv_bfloat162*>(&qv);
+        const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dv);
+        const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(hp[e]); dl = fmaf(dorow[c * 8 + 2 * e], f.x, fmaf(dorow[c * 8 + 2 * e + 1], f.y, dl)); }
+        for (int e = 0; e < 4; ++e) {
+          float2 qf = __bfloat1622float2(qh[e]), df = __bfloat1622float2(dh[e]), of = __bfloat1622float2(oh[e]);
+          dl = fmaf(df.x, of.x, fmaf(df.y, of.y, dl));
+          if (p.has_null) {
+            float k0 = null_sm[c * 8 + 2 * e], k1 = null_sm[c * 8 + 2 * e + 1];
+            float v0 = null_sm[64 + c * 8 + 2 * e], v1 = null_sm[64 + c * 8 + 2 * e + 1];
+            dot = fmaf(qf.x, k0, fmaf(qf.y, k1, dot));
+            kn2 = fmaf(k0, k0, fmaf(k1, k1, kn2));
+            dpn = fmaf(df.x, v0, fmaf(df.y, v1, dpn));
+          }
+        }
       }
     }
     delta[srow] = dl;
     const float L2 = lse2[srow];
     float ds_null = 0.f, p_null = 0.f;
     if (p.has_null) {
-      float dot = 0.f, kn2 = 0.f, dpn = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) { dot = fmaf(qrow[c], null_sm[c], dot); kn2 = fmaf(null_sm[c], null_sm[c], kn2); dpn = fmaf(dorow[c], null_sm[64 + c], dpn); }
       float tn = dot * p.c2 + (p.mode == 1 ? p.kb2 * kn2 : 0.f);
       p_null = fast_exp2(tn - L2);
       ds_null = p_null * (dpn - dl) * p.ls;
+      nullrow[srow] = ds_null;                         // consumed by attn_null_grad_kernel
+      nullrow[(long)p.B * p.heads * p.n + srow] = p_null;
     }
     for (int j = 0; j < T; ++j) {
       int s = j & 1;
@@ -578,17 +588,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + (p.has_null ? ds_null * null_sm[c0 + e] : 0.f);
       store_row16(dqrow + c0, f);
-    }
-    if (p.has_null) {        // null key/value gradients: reduce over the 128 rows of this CTA, then one atomic per value
-#pragma unroll 4
-      for (int c = 0; c < 64; ++c) {
-        float gk = ds_null * (qrow[c] - (p.mode == 1 ? null_sm[c] : 0.f));
-        float gv = p_null * dorow[c];
-        gk = warp_sum(gk); gv = warp_sum(gv);
-        if (lane == 0) { atomicAdd(&red_sm[c], gk); atomicAdd(&red_sm[64 + c], gv); }
-      }
-      named_bar_sync(1, 128);
-      atomicAdd(dnull + (st < 64 ? h * ATC_D + st : (p.heads + h) * ATC_D + (st - 64)), red_sm[st]);
     }
   }
   tc_fence_before();
@@ -773,7 +772,33 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
-// go, dq, dk, dv: dense (B, n, heads*64).  Returns 1 when not eligible.
+// dk_null[h][c] = sum_rows ds_null * (q - [l2] k_null), dv_null[h][c] = sum_rows p_null * dO   (rows = all (b, token))
+__global__ void attn_null_grad_kernel(const bf16* __restrict__ q, const bf16* __restrict__ go, const float* __restrict__ nullrow,
+                                      const float* __restrict__ null_kv, float* __restrict__ dnull, int B, int n, int heads,
+                                      long q_rs, int mode, int rows_per_block) {
+  __shared__ float sm[4][128];
+  const int h = blockIdx.y, c = threadIdx.x & 63, rl = threadIdx.x >> 6;        // 256 threads: 4 row lanes x 64 columns
+  const long total = (long)B * n, r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = min(total, r0 + rows_per_block);
+  const float kn = mode == 1 ? null_kv[h * ATC_D + c] : 0.f;
+  float gk = 0.f, gv = 0.f;
+  for (long row = r0 + rl; row < r1; row += 4) {
+    long b = row / n, i = row - b * n;
+    long srow = (b * heads + h) * (long)n + i;
+    float dsn = nullrow[srow], pn = nullrow[(long)B * heads * n + srow];
+    gk = fmaf(dsn, __bfloat162float(q[row * q_rs + h * ATC_D + c]) - kn, gk);
+    gv = fmaf(pn, __bfloat162float(go[row * (long)(heads * ATC_D) + h * ATC_D + c]), gv);
+  }
+  sm[rl][c] = gk; sm[rl][64 + c] = gv;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
+    int cc = threadIdx.x & 63;
+    atomicAdd(dnull + (threadIdx.x < 64 ? h * ATC_D + cc : (heads + h) * ATC_D + cc), t);
+  }
+}
+
+// go, dq, dk, dv: dense (B, n, heads*64); delta_ws holds 3*B*heads*n floats.  Returns 1 when not eligible.
 int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
                     const float* lse2, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
@@ -806,7 +831,13 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
   }
   int grid = B * heads * p.tiles;
   size_t smem1 = 1024 + 166400 + 8 * 20 + 16, smem2 = 1024 + 197120 + 8 * 10 + 16;
-  attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, dnull_kv);
+  float* nullrow = delta_ws + (size_t)B * heads * nq;
+  attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);
+  if (p.has_null) {
+    int rpb = 2048;
+    dim3 g2(gg_cdiv((long)B * nq, rpb), heads);
+    attn_null_grad_kernel<<<g2, 256, 0, st>>>((const bf16*)q, (const bf16*)go, nullrow, null_kv, dnull_kv, B, nq, heads, q_rs, mode, rpb);
+  }
   attn_bwd_dkv_tc_kernel<<<grid, ATC_THREADS, smem2, st>>>(tmQ, tmK, tmV, tmDO, p, ksq_ws, lse2, delta_ws, (bf16*)dk, (bf16*)dv);
   return gg_check_launch("attn_bwd_tc");
 }

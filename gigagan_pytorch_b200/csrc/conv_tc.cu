@@ -442,8 +442,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
         uint32_t r[16];
         tc_ld16(taddr + c0, r);
         if (live) {
+          if (p.splits == 1) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + c0 + j, __uint_as_float(r[j]));
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                     __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+          }
         }
       }
       tc_fence_before();
@@ -494,8 +503,10 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   p.per_sample = per_sample_w;
   int base_items = p.co_blocks * p.ci_blocks * p.taps * (per_sample_w ? N : 1);
   int ntiles = per_sample_w ? p.tiles_per_image : p.pix_tiles;
+  // split the pixel reduction only while every item keeps a long MMA chain: the fp32 red.add epilogue of one item
+  // (128 x Ntile values) costs as much as ~60-100 pipeline stages, so short items must not be split further
   int splits = 1;
-  while (base_items * splits < 3 * tc_num_sms() && ntiles / (splits * 2) >= 8) splits *= 2;
+  while (base_items * splits < 2 * tc_num_sms() && ntiles / (splits * 2) >= 96) splits *= 2;
   p.splits = splits;
   p.total_items = base_items * splits;
   p.pix = pix;
@@ -532,7 +543,7 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
     uint32_t box[4] = {64, (uint32_t)Wt, (uint32_t)Ht, (uint32_t)Nt};
     if (tc_make_map4(&tmDY, dy, dims, strides, box, 128)) return -1;
   }
-  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(per_sample_w ? N : 1) * Cout * KH * KW * Cin, st);
+  if (p.splits > 1) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)(per_sample_w ? N : 1) * Cout * KH * KW * Cin, st);
   size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4) + 16;
   static bool attr_set = false;
   if (!attr_set) {

@@ -298,6 +298,19 @@ int ggi_simt_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, 
   return gg_check_launch("conv_wgrad_simt");
 }
 
+// skinny fp32 products (style network, squeeze-excite MLPs, modulation projections: M = batch <= 64): one warp per
+// output element, lanes stride over K - these sit on serial dependency chains, so latency matters, not throughput.
+__global__ void __launch_bounds__(256) skinny_gemm_f32(const float* __restrict__ A, const float* __restrict__ B,
+                                                       const float* __restrict__ bias, float* __restrict__ C, BmmP p) {
+  long w = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long)p.M * p.N) return;
+  int m = (int)(w / p.N), n = (int)(w % p.N), lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int k = lane; k < p.K; k += 32) acc = fmaf(A[m * p.rsA + k * p.csA], B[k * p.rsB + n * p.csB], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) C[m * p.rsC + n] = acc * p.alpha + (bias ? bias[n] : 0.f);
+}
+
 int ggi_simt_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
                 const long* sa, const long* sb, const long* sc, float alpha, int dtype, cudaStream_t st) {
   BmmP p;
@@ -306,6 +319,10 @@ int ggi_simt_bmm(const void* A, const void* B, const float* bias, void* C, int b
   p.sB1 = sb[0]; p.sB2 = sb[1]; p.rsB = sb[2]; p.csB = sb[3];
   p.sC1 = sc[0]; p.sC2 = sc[1]; p.rsC = sc[2];
   p.alpha = alpha;
+  if (dtype == GG_F32 && b1 * b2 == 1 && M <= 64 && (long)M * N <= (1L << 22)) {
+    skinny_gemm_f32<<<gg_cdiv((long)M * N, 8), 256, 0, st>>>((const float*)A, (const float*)B, bias, (float*)C, p);
+    return gg_check_launch("skinny_gemm_f32");
+  }
   if ((long)b1 * b2 > 65535) return gg_fail("bmm batch too large");
   dim3 grid(gg_cdiv(M, BM), gg_cdiv(N, BN), b1 * b2);
   GG_DISPATCH(dtype, (bmm_simt<T><<<grid, 256, 0, st>>>((const T*)A, (const T*)B, bias, (T*)C, p)));

@@ -956,7 +956,7 @@ class FusedAttnFn(Function):
         dk = torch.empty((B, nk, hd), dtype=q.dtype, device=q.device)
         dv = torch.empty((B, nk, hd), dtype=q.dtype, device=q.device)
         dnull = None if nkv is None else torch.empty_like(nkv)
-        delta = torch.empty_like(lse)
+        delta = torch.empty((3 * lse.numel(),), dtype=torch.float32, device=q.device)   # delta | ds_null | p_null
         # the backward kernel indexes dq/dk/dv with the strides of q/k/v: give it dense copies' strides
         assert go.stride(1) == o.stride(1)
         qc, kc, vc = _c(q), _c(k), _c(v)
