@@ -18,6 +18,7 @@ struct TcP {
   int Wt, Ht, Nt, tiles_w, tiles_h, tiles_n, n_tiles_n, total_tiles;
   int Ntile, chunk, cchunks, KH, KW, pad, stride, per_sample;
   int stages, stage_bytes, a_bytes, b_bytes, b_slab, ts;   // ts = filter taps packed into one pipeline stage
+  int mdual, m_tiles;                                       // mdual = 2: two 128-pixel M tiles share every weight slab
   int act;
   float gain;
   long y_off, y_sn, y_sh, y_sw;          // output addressing (elements): y_off + n*y_sn + oy*y_sh + ox*y_sw + co
@@ -62,25 +63,34 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-        int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-        int ox0 = tw * p.Wt, oy0 = th * p.Ht, n0 = tn * p.Nt, co0 = nt * p.Ntile;
+        int nt = tile % p.n_tiles_n, mp = tile / p.n_tiles_n;
+        int co0 = nt * p.Ntile;
+        int ox0[2], oy0[2], n0[2];
+        for (int d = 0; d < p.mdual; ++d) {
+          int mt = mp * p.mdual + d;
+          int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+          ox0[d] = tw * p.Wt; oy0[d] = th * p.Ht; n0[d] = tn * p.Nt;          // past the last tile: n0 >= N -> zero fill
+        }
+        const int nA = p.ts * p.mdual;                      // A slabs per stage (mdual == 2 implies ts == 1)
         for (int kb = 0; kb < kblocks; ++kb) {
           int tap0 = (kb / p.cchunks) * p.ts, cc = kb % p.cchunks;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)(p.ts * (p.a_bytes + p.b_bytes)));
-          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + p.ts * p.a_bytes;
+          mbar_expect_tx(full_bar(stage), (uint32_t)(nA * p.a_bytes + p.ts * p.b_bytes));
+          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + nA * p.a_bytes;
           for (int t = 0; t < p.ts; ++t) {
             int tap = tap0 + t;
-            uint32_t sa = sa0 + t * p.a_bytes, sb = sb0 + t * p.b_slab;
-            if (p.stride == 1) {
-              int ky = tap / p.KW, kx = tap - ky * p.KW;
-              tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
-            } else {
-              const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
-              tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0, oy0, n0);
+            uint32_t sb = sb0 + t * p.b_slab;
+            for (int d = 0; d < p.mdual; ++d) {
+              uint32_t sa = sa0 + (t * p.mdual + d) * p.a_bytes;
+              if (p.stride == 1) {
+                int ky = tap / p.KW, kx = tap - ky * p.KW;
+                tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0[d] + kx - p.pad, oy0[d] + ky - p.pad, n0[d]);
+              } else {
+                const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
+                tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0[d], oy0[d], n0[d]);
+              }
             }
-            tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0 : 0);
+            tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0[0] : 0);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
@@ -89,21 +99,25 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+    const int nacc = p.mdual == 2 ? 1 : 2;                 // dual-M uses all 512 TMEM columns for one tile pair
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile);
+      uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.Ntile * p.mdual);
+      const int nA = p.ts * p.mdual;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
-          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + p.ts * p.a_bytes;
+          uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + nA * p.a_bytes;
           int ksteps = p.chunk >> 4;
           for (int t = 0; t < p.ts; ++t) {
-            uint64_t da = make_smem_desc(sa0 + t * p.a_bytes, p.sbo, p.layout_type);
             uint64_t db = make_smem_desc(sb0 + t * p.b_slab, p.sbo, p.layout_type);
-            for (int k = 0; k < ksteps; ++k)
-              tc_mma_f16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | t | k) != 0 ? 1u : 0u);
+            for (int d = 0; d < p.mdual; ++d) {
+              uint64_t da = make_smem_desc(sa0 + (t * p.mdual + d) * p.a_bytes, p.sbo, p.layout_type);
+              for (int k = 0; k < ksteps; ++k)
+                tc_mma_f16(d_tmem + d * p.Ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | t | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(empty_bar(stage));
           if (kb == kblocks - 1) tc_commit(tfull_bar(acc));
@@ -111,7 +125,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ===================================================== epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
@@ -119,15 +133,19 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
     const int m = q * 32 + lane;
     const int ww = m % p.Wt, hh = (m / p.Wt) % p.Ht, nn = m / (p.Wt * p.Ht);
     int acc = 0; uint32_t acc_phase = 0;
+    const int nacc = p.mdual == 2 ? 1 : 2;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt = tile % p.n_tiles_n, mt = tile / p.n_tiles_n;
-      int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
-      int n = tn * p.Nt + nn, co0 = nt * p.Ntile;
-      long pix = p.y_off + (long)n * p.y_sn + (long)(th * p.Ht + hh) * p.y_sh + (long)(tw * p.Wt + ww) * p.y_sw;
-      bool live = n < p.N;
+      int nt = tile % p.n_tiles_n, mp = tile / p.n_tiles_n;
+      int co0 = nt * p.Ntile;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ntile);
+     for (int d = 0; d < p.mdual; ++d) {
+      int mt = mp * p.mdual + d;
+      int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tn = mt / (p.tiles_w * p.tiles_h);
+      int n = tn * p.Nt + nn;
+      long pix = p.y_off + (long)n * p.y_sn + (long)(th * p.Ht + hh) * p.y_sh + (long)(tw * p.Wt + ww) * p.y_sw;
+      bool live = n < p.N && mt < p.m_tiles;
+      uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ntile * p.mdual + d * p.Ntile);
       for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
         uint32_t r[16];
         tc_ld16(taddr + c0, r);
@@ -162,10 +180,11 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           ((uint4*)dst)[1] = o1;
         }
       }
+     }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -243,7 +262,13 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   p.Wt = Wt; p.Ht = Ht; p.Nt = Nt;
   p.tiles_w = OW / Wt; p.tiles_h = OH / Ht; p.tiles_n = (N + Nt - 1) / Nt;
   p.Ntile = Ntile; p.n_tiles_n = Cout / Ntile;
-  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles_n;
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // L2 -> SM operand traffic bounds the 128x256 tile (85 flop/B): when the layer is wide and deep, let two pixel
+  // tiles share every weight slab (256x256 effective tile, 128 flop/B), using all 512 TMEM columns
+  // (only for long K loops - the epilogue is not overlapped in this mode - and when >= 2 full waves of tile pairs remain)
+  p.mdual = (Ntile == 256 && KH * KW * (Cin / chunk) >= 32 && !per_sample_w &&
+             (p.m_tiles / 2) * p.n_tiles_n >= 2 * tc_num_sms()) ? 2 : 1;
+  p.total_tiles = ((p.m_tiles + p.mdual - 1) / p.mdual) * p.n_tiles_n;
   p.chunk = chunk; p.cchunks = Cin / chunk; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
   p.per_sample = per_sample_w;
   p.a_bytes = 128 * chunk * 2; p.b_bytes = Ntile * chunk * 2;
@@ -258,8 +283,9 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
       if (c >= 1 && taps % c == 0 && c * (p.a_bytes + p.b_slab) <= 64 * 1024) { ts = c; break; }
     }
   }
+  if (p.mdual == 2) ts = 1;
   p.ts = ts;
-  p.stage_bytes = ts * (p.a_bytes + p.b_slab);
+  p.stage_bytes = ts * (p.mdual * p.a_bytes + p.b_slab);
   int stages = (200 * 1024) / p.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) return 1;
@@ -506,7 +532,8 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   // split the pixel reduction only while every item keeps a long MMA chain: the fp32 red.add epilogue of one item
   // (128 x Ntile values) costs as much as ~60-100 pipeline stages, so short items must not be split further
   int splits = 1;
-  while (base_items * splits < 2 * tc_num_sms() && ntiles / (splits * 2) >= 96) splits *= 2;
+  int min_stages = p.Ntile * 3 / 8 > 8 ? p.Ntile * 3 / 8 : 8;       // epilogue cost scales with the accumulator width
+  while (base_items * splits < 2 * tc_num_sms() && ntiles / (splits * 2) >= min_stages) splits *= 2;
   p.splits = splits;
   p.total_items = base_items * splits;
   p.pix = pix;

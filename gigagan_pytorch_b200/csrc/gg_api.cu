@@ -113,6 +113,12 @@ int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C,
 int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream) {
   return ggi_softmax_bwd_rows(p, gp, ds, R, C, dtype, ST);
 }
+int gg_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, int64_t R, int C, int dtype,
+                         gg_stream_t stream) {
+  int r = ggi_softmax_bwd2_rows(p, gp, G, d_p, d_gp, R, C, dtype, ST);
+  if (r == 1) return gg_fail("gg_softmax_bwd2_rows: row length %d not supported by the one-pass kernel", C);
+  return r;
+}
 int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                   int Ty, const int* ix, const float* wx, int Tx, int dtype, gg_stream_t stream) {
   return ggi_resample2d(x, y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx, dtype, ST);

@@ -454,6 +454,50 @@ int ggi_softmax_bwd_rows(const void* p, const void* gp, void* ds, long R, int C,
   return gg_check_launch("softmax_bwd_rows");
 }
 
+// second-order softmax backward in one pass (gradient-penalty path):  given P, gP (inputs of dS = P*(gP - r)) and the
+// upstream G = d/d(dS):   d_gP = P * (G - <G,P>)      d_P = G * (gP - <P,gP>) - gP * <G,P>
+template <typename T, int MAXV>
+__global__ void softmax_bwd2_rows_warp_kernel(const T* __restrict__ p, const T* __restrict__ gp, const T* __restrict__ G,
+                                              T* __restrict__ d_p, T* __restrict__ d_gp, long R, int C) {
+  constexpr int V = VecN<T>::N;
+  long r = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  int lane = threadIdx.x & 31, nvec = C / V;
+  float pv[MAXV][V], gv[MAXV][V], Gv[MAXV][V];
+  float r_pg = 0.f, r_Gp = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+      ldv(p + r * C + vi * V, pv[i]); ldv(gp + r * C + vi * V, gv[i]); ldv(G + r * C + vi * V, Gv[i]);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { r_pg = fmaf(pv[i][j], gv[i][j], r_pg); r_Gp = fmaf(Gv[i][j], pv[i][j], r_Gp); }
+    }
+  }
+  r_pg = warp_sum(r_pg); r_Gp = warp_sum(r_Gp);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    int vi = lane + 32 * i;
+    if (vi < nvec) {
+      float a[V], b[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        a[j] = Gv[i][j] * (gv[i][j] - r_pg) - gv[i][j] * r_Gp;
+        b[j] = pv[i][j] * (Gv[i][j] - r_Gp);
+      }
+      stv(d_p + r * C + vi * V, a);
+      stv(d_gp + r * C + vi * V, b);
+    }
+  }
+}
+int ggi_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, long R, int C, int dtype,
+                          cudaStream_t st) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (!(C % V == 0 && C / V <= 32 * 5 && al16(p) && al16(gp) && al16(G) && al16(d_p) && al16(d_gp))) return 1;
+  GG_DISPATCH(dtype, (softmax_bwd2_rows_warp_kernel<T, 5><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)p, (const T*)gp, (const T*)G, (T*)d_p, (T*)d_gp, R, C)));
+  return gg_check_launch("softmax_bwd2_rows");
+}
+
 // ------------------------------------------------------------------ separable sparse resampling (NHWC)
 // y[n,oy,ox,c] = sum_{a<Ty} sum_{b<Tx} wy[oy,a] wx[ox,b] x[n, iy[oy,a], ix[ox,b], c]
 template <typename T>

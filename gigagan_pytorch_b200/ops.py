@@ -380,7 +380,9 @@ class BmmFn(Function):
         b1, b2, m, k = a.shape
         n = b.shape[-1]
         assert b.shape[:3] == (b1, b2, k) and a.dtype == b.dtype
-        if out_bmhn:
+        if isinstance(out_bmhn, torch.Tensor):      # lay the result out like this tensor (same shape, last dim dense)
+            c = torch.empty_strided((b1, b2, m, n), out_bmhn.stride(), dtype=a.dtype, device=a.device)
+        elif out_bmhn:
             c = torch.empty((b1, m, b2, n), dtype=a.dtype, device=a.device).permute(0, 2, 1, 3)
         else:
             c = torch.empty((b1, b2, m, n), dtype=a.dtype, device=a.device)
@@ -398,14 +400,42 @@ class BmmFn(Function):
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         ga = gb = gbias = None
+        # gradients are produced directly in the memory layout of their operand (views of (batch, tokens, heads, d)
+        # activations), so that autograd's view-backward / accumulation never needs a strided copy
         if ctx.needs_input_grad[0]:
-            ga = BmmFn.apply(g, b.transpose(-1, -2), None, ctx.alpha, False)
+            if _dense_like(a):
+                ga = BmmFn.apply(g, b.transpose(-1, -2), None, ctx.alpha, a)
+            elif _dense_like(a.transpose(-1, -2)):
+                ga = BmmFn.apply(b, g.transpose(-1, -2), None, ctx.alpha, a.transpose(-1, -2)).transpose(-1, -2)
+            else:
+                ga = BmmFn.apply(g, b.transpose(-1, -2), None, ctx.alpha, False)
         if ctx.needs_input_grad[1]:
-            gb = BmmFn.apply(a.transpose(-1, -2), g, None, ctx.alpha, False)
+            if _dense_like(b):
+                gb = BmmFn.apply(a.transpose(-1, -2), g, None, ctx.alpha, b)
+            elif _dense_like(b.transpose(-1, -2)):
+                gb = BmmFn.apply(g.transpose(-1, -2), a, None, ctx.alpha, b.transpose(-1, -2)).transpose(-1, -2)
+            else:
+                gb = BmmFn.apply(a.transpose(-1, -2), g, None, ctx.alpha, False)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gc = _c(g)
             gbias = dot_sc(gc, None, gc.numel() // gc.shape[-1], 1).reshape(-1)
         return ga, gb, gbias, None, None
+
+
+def _dense_like(t):
+    """True when t (b1,b2,M,N) has a unit last stride and is a non-overlapping permutation of a dense tensor, so a
+    result can be written with exactly its strides."""
+    if t.stride(-1) != 1 or 0 in t.stride():
+        return False
+    dims = sorted(range(4), key=lambda i: t.stride(i))
+    expect = 1
+    for i in dims:
+        if t.shape[i] == 1:
+            continue
+        if t.stride(i) != expect:
+            return False
+        expect *= t.shape[i]
+    return True
 
 
 def bmm(a, b, alpha=1.0, out_bmhn=False):
@@ -702,6 +732,13 @@ class SoftmaxBwdFn(Function):
     def backward(ctx, G):
         p, gp = ctx.saved_tensors
         d_p = d_gp = None
+        C = p.shape[-1]
+        V = 4 if p.dtype == torch.float32 else 8
+        if (not torch.is_grad_enabled()) and C % V == 0 and C // V <= 160 and all(ctx.needs_input_grad):
+            G = _c(G)
+            d_p, d_gp = torch.empty_like(p), torch.empty_like(p)       # terminal (third order is never needed)
+            call("gg_softmax_bwd2_rows", _p(p), _p(gp), _p(G), _p(d_p), _p(d_gp), p.numel() // C, C, _dt(p), _st())
+            return d_p, d_gp
         if ctx.needs_input_grad[1]:
             d_gp = SoftmaxBwdFn.apply(p, G)
         if ctx.needs_input_grad[0]:

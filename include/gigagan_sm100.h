@@ -81,6 +81,12 @@ int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C,
 /* ds = p * (gp - rowsum(p * gp)): softmax backward for one [R,C] matrix (autograd of the softmax at :588) */
 int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream);
 
+/* second-order softmax backward (double backward of :588 inside the gradient penalty), one pass:
+ * d_gp = p*(G - <G,p>), d_p = G*(gp - <p,gp>) - gp*<G,p>.  Row length must be a multiple of the 16-byte vector and
+ * <= 1280 (bf16) / 640 (fp32); otherwise returns an error and the caller composes it from the primitives. */
+int gg_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, int64_t R, int C, int dtype,
+                         gg_stream_t stream);
+
 /* ---- separable sparse resampling of NHWC maps: bilinear x2 + [1,2,1]^2/16 reflect blur (:246-261), bilinear
  * F.interpolate (:1683-1687) and their transposes.  Tap tables: iy/wy [OH][Ty], ix/wx [OW][Tx]. */
 int gg_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,

@@ -71,6 +71,8 @@ def test_conv_family(cfg, dtype, tol):
     dict(n=2, h=64, w=64, ci=16, co=16, k=3, s=1, p=1, ps=False), dict(n=2, h=32, w=32, ci=32, co=64, k=3, s=1, p=1, ps=False),
     dict(n=2, h=16, w=16, ci=64, co=128, k=2, s=2, p=0, ps=False), dict(n=2, h=16, w=16, ci=64, co=128, k=1, s=2, p=0, ps=False),
     dict(n=3, h=16, w=16, ci=64, co=32, k=3, s=1, p=1, ps=True), dict(n=2, h=8, w=8, ci=256, co=1024, k=1, s=1, p=0, ps=False),
+    dict(n=75, h=32, w=32, ci=256, co=256, k=3, s=1, p=1, ps=False),      # dual-M tile mode (600 pixel tiles)
+    dict(n=149, h=16, w=16, ci=256, co=512, k=3, s=1, p=1, ps=False),     # dual-M, odd tile count (298 tiles x 2)
 ])
 def test_tcgen05_conv_matches_ffma(cfg):
     """bf16 tensor-core implicit GEMM (TMA taps, TMEM accumulators) vs the FFMA kernel on identical bf16 inputs;

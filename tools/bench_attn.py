@@ -1,0 +1,28 @@
+"""Fused attention (tcgen05) timing at the discriminator's shapes: forward and backward, CUDA events."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gigagan_pytorch_b200 import ops
+dev = torch.device("cuda:0")
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=dev)
+for name, B, n, l2 in (("D_res32_l2", 64, 1024, True), ("D_res16_l2", 128, 256, True), ("G_res32_dot", 16, 1024, False)):
+    heads, d = 8, 64
+    qkv = (torch.randn(B, n, 3 * heads * d, device=dev) * 0.5).to(torch.bfloat16).requires_grad_()
+    nk = torch.randn(2, heads, d, device=dev).requires_grad_()
+    q, k, v = qkv[..., :512], qkv[..., 512:1024], qkv[..., 1024:]
+    go = torch.randn(B, n, heads * d, device=dev).to(torch.bfloat16)
+    def fwd():
+        return ops.fused_attention(q, q if l2 else k, v, nk, heads, d ** -0.5, l2=l2)
+    for _ in range(2):
+        o = fwd(); torch.autograd.grad(o, (qkv, nk), go)
+    tf, tb = [], []
+    for _ in range(5):
+        flush.zero_()
+        e0, e1, e2 = (torch.cuda.Event(True) for _ in range(3))
+        e0.record(); o = fwd(); e1.record(); torch.autograd.grad(o, (qkv, nk), go); e2.record()
+        torch.cuda.synchronize()
+        tf.append(e0.elapsed_time(e1)); tb.append(e1.elapsed_time(e2))
+    tf, tb = sorted(tf)[2], sorted(tb)[2]
+    flops = 4.0 * B * heads * n * (n + 1) * d
+    print(json.dumps(dict(name=name, fwd_ms=round(tf, 4), bwd_ms=round(tb, 4), fwd_tflops=round(flops / tf / 1e9, 1),
+                          bwd_tflops=round(2.5 * flops / tb / 1e9, 1), exps_per_s_fwd=round(B * heads * n * n / tf / 1e9 * 1e3, 1))), flush=True)

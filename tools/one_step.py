@@ -16,8 +16,8 @@ it = cycle(Pool())
 gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=False)
 gan.train_generator_step(batch_size=B, dl_iter=it)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_push("measured")
+torch.cuda.profiler.start()          # ncu --profile-from-start off: captures every thread (autograd worker too)
 gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=False)
 gan.train_generator_step(batch_size=B, dl_iter=it)
 torch.cuda.synchronize()
-torch.cuda.nvtx.range_pop()
+torch.cuda.profiler.stop()
