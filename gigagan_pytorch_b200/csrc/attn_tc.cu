@@ -281,8 +281,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         h0[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
         h1[e] = __floats2bfloat162_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
       }
-      reinterpret_cast<uint4*>(orow + c0)[0] = o0;
-      reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+      st_global_256(orow + c0, o0, o1);
     }
     lse2[(long)bh * p.n + qt * ATC_T + r] = m + log2f(l);
   }
@@ -306,8 +305,9 @@ int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* nu
                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
                     int mode, cudaStream_t st) {
   if (d != ATC_D || nq != nk || nq % ATC_T || nq < ATC_T) return 1;
-  if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 8)) return 1;
-  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o) & 15) return 1;
+  if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 16)) return 1;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) & 15) return 1;
+  if (((uintptr_t)o) & 31) return 1;
   if (mode == 1 && !ksq_ws) return 1;
   AtcP p;
   p.B = B; p.heads = heads; p.n = nq; p.tiles = nq / ATC_T; p.mode = mode; p.has_null = null_kv != nullptr;
@@ -382,8 +382,7 @@ __device__ __forceinline__ void store_row16(bf16* dst, const float* f) {
     h0[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
     h1[e] = __floats2bfloat162_rn(f[8 + 2 * e], f[8 + 2 * e + 1]);
   }
-  reinterpret_cast<uint4*>(dst)[0] = o0;
-  reinterpret_cast<uint4*>(dst)[1] = o1;
+  st_global_256(dst, o0, o1);
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 1)
@@ -805,7 +804,8 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
                     int mode, cudaStream_t st) {
   if (d != ATC_D || nq != nk || nq % ATC_T || nq < ATC_T) return 1;
   if ((q_rs % 8) || (k_rs % 8) || (v_rs % 8) || (o_rs % 8)) return 1;
-  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)go | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 15) return 1;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)go) & 15) return 1;
+  if (((uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) & 31) return 1;
   if (mode == 1 && !ksq_ws) return 1;
   AtbP p;
   p.B = B; p.heads = heads; p.n = nq; p.tiles = nq / ATC_T; p.mode = mode; p.has_null = null_kv != nullptr;
@@ -834,7 +834,7 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
   float* nullrow = delta_ws + (size_t)B * heads * nq;
   attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);
   if (p.has_null) {
-    int rpb = 2048;
+    int rpb = 128;
     dim3 g2(gg_cdiv((long)B * nq, rpb), heads);
     attn_null_grad_kernel<<<g2, 256, 0, st>>>((const bf16*)q, (const bf16*)go, nullrow, null_kv, dnull_kv, B, nq, heads, q_rs, mode, rpb);
   }

@@ -98,7 +98,7 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    const bool vec_ok = (p.rsC % 8 == 0) && (p.sC1 % 8 == 0) && (p.sC2 % 8 == 0) && (((uintptr_t)C & 15) == 0);
+    const bool vec_ok = (p.rsC % 16 == 0) && (p.sC1 % 16 == 0) && (p.sC2 % 16 == 0) && (((uintptr_t)C & 31) == 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int z = tile / tiles_per_batch, r = tile - z * tiles_per_batch;
       int mt = r / p.n_tiles, nt = r - mt * p.n_tiles;
@@ -129,8 +129,7 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               ob0[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
               ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j], v[8 + 2 * j + 1]);
             }
-            ((uint4*)(crow + n))[0] = o0;
-            ((uint4*)(crow + n))[1] = o1;
+            st_global_256(crow + n, o0, o1);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (n + j < p.N) crow[n + j] = __float2bfloat16_rn(v[j]);

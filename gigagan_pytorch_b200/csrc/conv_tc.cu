@@ -163,8 +163,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
           }
           bf16* dst = y + pix + co0 + c0;
           if (res) {
-            const uint4* rp = (const uint4*)(res + pix + co0 + c0);
-            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            uint4 r0, r1;
+            ld_global_256(res + pix + co0 + c0, r0, r1);
             const bf16* rb0 = (const bf16*)&r0; const bf16* rb1 = (const bf16*)&r1;
 #pragma unroll
             for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(rb0[j]); v[8 + j] += __bfloat162float(rb1[j]); }
@@ -176,8 +176,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
             ob0[j] = __floats2bfloat162_rn(v[2 * j] * p.gain, v[2 * j + 1] * p.gain);
             ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j] * p.gain, v[8 + 2 * j + 1] * p.gain);
           }
-          ((uint4*)dst)[0] = o0;
-          ((uint4*)dst)[1] = o1;
+          st_global_256(dst, o0, o1);
         }
       }
      }
@@ -255,7 +254,8 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   int Nt = 128 / (Wt * Ht);
   if (Wt * Ht * Nt != 128) return 1;
   if (per_sample_w && Nt != 1) return 1;
-  if (((uintptr_t)x | (uintptr_t)w | (uintptr_t)y | (uintptr_t)res) & 15) return 1;
+  if (((uintptr_t)x | (uintptr_t)w) & 15) return 1;
+  if (((uintptr_t)y | (uintptr_t)res) & 31) return 1;          // 256-bit epilogue accesses
 
   TcP p;
   p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout;
@@ -292,7 +292,7 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   p.stages = stages;
   p.act = act; p.gain = gain;
   if (ystr) {
-    if ((ystr[0] | ystr[1] | ystr[2] | ystr[3]) & 7) return 1;
+    if ((ystr[0] | ystr[1] | ystr[2] | ystr[3]) & 15) return 1;
     p.y_off = ystr[0]; p.y_sn = ystr[1]; p.y_sh = ystr[2]; p.y_sw = ystr[3];
   } else { p.y_off = 0; p.y_sn = (long)OH * OW * Cout; p.y_sh = (long)OW * Cout; p.y_sw = Cout; }
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Ntile >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);

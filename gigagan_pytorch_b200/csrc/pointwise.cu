@@ -526,9 +526,47 @@ __global__ void resample_kernel(const T* __restrict__ x, T* __restrict__ y, int 
     stf(y + i, acc);
   }
 }
+// vector variant: one thread = 16 bytes of channels of one output pixel
+template <typename T>
+__global__ void resample_vec_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
+                                    const int* __restrict__ iy, const float* __restrict__ wy, int Ty,
+                                    const int* __restrict__ ix, const float* __restrict__ wx, int Tx) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
+  long n = (long)N * OH * OW * CV;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % CV);
+    long t = i / CV;
+    int ox = (int)(t % OW); t /= OW;
+    int oy = (int)(t % OH);
+    int b = (int)(t / OH);
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int a = 0; a < Ty; ++a) {
+      float wa = wy[oy * Ty + a];
+      if (wa == 0.f) continue;
+      const T* row = x + ((long)b * H + iy[oy * Ty + a]) * W * C + cv * V;
+      for (int q = 0; q < Tx; ++q) {
+        float wq = wx[ox * Tx + q] * wa;
+        if (wq == 0.f) continue;
+        float v[V];
+        ldv(row + (long)ix[ox * Tx + q] * C, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = fmaf(wq, v[k], acc[k]);
+      }
+    }
+    stv(y + i * V, acc);
+  }
+}
 int ggi_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                   int Ty, const int* ix, const float* wx, int Tx, int dtype, cudaStream_t st) {
   long n = (long)N * OH * OW * C;
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V == 0 && al16(x) && al16(y)) {
+    GG_DISPATCH(dtype, (resample_vec_kernel<T><<<gg_blocks(n / V, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+    return gg_check_launch("resample2d_vec");
+  }
   GG_DISPATCH(dtype, (resample_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
   return gg_check_launch("resample2d");
 }

@@ -72,6 +72,16 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr, uint32_t lb
   return d;
 }
 
+// one 256-bit global store (STG.E.256): a full 32-byte sector per lane, instead of two half-sector 16-byte stores
+__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w),
+               "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 int tc_make_map4(CUtensorMap* m, const void* ptr, const uint64_t dims[4], const uint64_t strides_bytes[3],
                  const uint32_t box[4], int swizzle_bytes);
 int tc_num_sms();

@@ -431,3 +431,25 @@ def test_tcgen05_fused_attention(mode, n):
     assert relmax(o_tc, o_ff) < 2e-2, relmax(o_tc, o_ff)
     assert relmax(gq_tc, gq_ff) < 3e-2, relmax(gq_tc, gq_ff)
     assert relmax(gn_tc, gn_ff) < 3e-2, relmax(gn_tc, gn_ff)
+
+
+def test_fused_adamw_matches_torch_adamw():
+    """gg_adamw over the flat buffer == torch.optim.AdamW as the reference configures it (wd 1e-2 on ndim>=2 only)."""
+    from gigagan_pytorch_b200.trainer import FlatAdamW
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Linear(8, 5)).to(dev())
+    ref = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.Linear(8, 5)).to(dev())
+    ref.load_state_dict(net.state_dict())
+    opt = FlatAdamW(net, lr=2e-4, betas=(0.5, 0.9))
+    wd, nwd = [p for p in ref.parameters() if p.ndim >= 2], [p for p in ref.parameters() if p.ndim < 2]
+    ropt = torch.optim.AdamW([dict(params=wd), dict(params=nwd, weight_decay=0.0)], lr=2e-4, betas=(0.5, 0.9), weight_decay=1e-2)
+    for step in range(5):
+        opt.zero_grad()
+        for p, q in zip(net.parameters(), ref.parameters()):
+            g = torch.randn_like(p)
+            p.grad.copy_(g)
+            q.grad = g.clone()
+        opt.step()
+        ropt.step()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert (p - q).abs().max().item() < 1e-6, (p - q).abs().max().item()
