@@ -1,7 +1,7 @@
 """gigagan_pytorch_b200 — B200 (sm_100a) native GigaGAN generator/discriminator training path, drop-in for the
 class API of lucidrains/gigagan-pytorch (GigaGAN / Generator / Discriminator / AdaptiveConv2DMod / StyleNetwork)."""
-from .modules import (AdaptiveConv2DMod, Discriminator, Generator, SelfAttention, SelfAttentionBlock,  # noqa: F401
-                      StyleNetwork, compute_dtype, set_compute_dtype)
+from .modules import (AdaptiveConv2DMod, Attend, Discriminator, Generator, SelfAttention,  # noqa: F401
+                      SelfAttentionBlock, StyleNetwork, UnetUpsampler, compute_dtype, set_compute_dtype)
 
 from .trainer import GigaGAN, get_optimizer  # noqa: F401,E402
 

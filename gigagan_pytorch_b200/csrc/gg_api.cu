@@ -168,6 +168,11 @@ int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, i
   return ggi_adamw(p, g, m, v, chunks, nchunks, step_ptr, lr, b1, b2, eps, wd, grad_scale, ST);
 }
 int gg_incr(int* p, gg_stream_t stream) { return ggi_incr(p, ST); }
+int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream) { return ggi_maxpool2_fwd(x, y, N, H, W, C, dtype, ST); }
+int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream) {
+  return ggi_maxpool2_bwd(x, gy, gx, N, H, W, C, dtype, ST);
+}
+int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream) { return ggi_softmax_tokens(x, y, B, n, C, dtype, ST); }
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream) {
   return ggi_weight_prep_multi(master, entries, chunks, nchunks, fwd, bwd, dtype, ST);

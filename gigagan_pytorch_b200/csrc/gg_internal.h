@@ -60,3 +60,6 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
                     int mode, cudaStream_t st);
 int ggi_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, long R, int C, int dtype,
                           cudaStream_t st);
+int ggi_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
+int ggi_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, cudaStream_t st);
+int ggi_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, cudaStream_t st);

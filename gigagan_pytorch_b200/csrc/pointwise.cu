@@ -865,3 +865,80 @@ int ggi_weight_prep_multi(const float* master, const void* entries, const void* 
   GG_DISPATCH(dtype, (weight_prep_multi_kernel<T><<<nchunks, 256, 0, st>>>(master, (const long*)entries, (const int4*)chunks, (T*)fwd, (T*)bwd)));
   return gg_check_launch("weight_prep_multi");
 }
+
+// ------------------------------------------------------------------ UnetUpsampler extras (unet_upsampler.py)
+// 2x2 max-pool of NHWC maps (ref :158 F.max_pool2d) and its gradient (first maximum in row-major order wins, as ATen)
+template <typename T>
+__global__ void maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C) {
+  int OH = H / 2, OW = W / 2;
+  long n = (long)N * OH * OW * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long t = i / C;
+    int ox = (int)(t % OW); t /= OW;
+    int oy = (int)(t % OH); int b = (int)(t / OH);
+    const T* p0 = x + (((long)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    float m = fmaxf(fmaxf(ldf(p0), ldf(p0 + C)), fmaxf(ldf(p0 + (long)W * C), ldf(p0 + (long)W * C + C)));
+    stf(y + i, m);
+  }
+}
+template <typename T>
+__global__ void maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, int N, int H,
+                                    int W, int C) {
+  int OH = H / 2, OW = W / 2;
+  long n = (long)N * OH * OW * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C); long t = i / C;
+    int ox = (int)(t % OW); t /= OW;
+    int oy = (int)(t % OH); int b = (int)(t / OH);
+    long o00 = (((long)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    long off[4] = {o00, o00 + C, o00 + (long)W * C, o00 + (long)W * C + C};
+    float v[4];
+    int best = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = ldf(x + off[k]); if (v[k] > v[best]) best = k; }
+    float g = ldf(gy + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) stf(gx + off[k], k == best ? g : 0.f);
+  }
+}
+int ggi_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st) {
+  long n = (long)N * (H / 2) * (W / 2) * C;
+  GG_DISPATCH(dtype, (maxpool2_fwd_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C)));
+  return gg_check_launch("maxpool2_fwd");
+}
+int ggi_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, cudaStream_t st) {
+  long n = (long)N * (H / 2) * (W / 2) * C;
+  GG_DISPATCH(dtype, (maxpool2_bwd_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)x, (const T*)gy, (T*)gx, N, H, W, C)));
+  return gg_check_launch("maxpool2_bwd");
+}
+
+// softmax over the TOKEN axis of (B, n, C) maps, per (sample, channel)  (LinearAttention k.softmax(dim=-1), ref :340)
+template <typename T>
+__global__ void softmax_tokens_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int C) {
+  __shared__ float sm[8][33];
+  int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+  const T* xb = x + (long)b * n * C;
+  T* yb = y + (long)b * n * C;
+  float m = -INFINITY;
+  if (c < C) for (int r = threadIdx.y; r < n; r += 8) m = fmaxf(m, ldf(xb + (long)r * C + c));
+  sm[threadIdx.y][threadIdx.x] = m;
+  __syncthreads();
+  m = sm[0][threadIdx.x];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, sm[i][threadIdx.x]);
+  __syncthreads();
+  float s = 0.f;
+  if (c < C) for (int r = threadIdx.y; r < n; r += 8) s += __expf(ldf(xb + (long)r * C + c) - m);
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += sm[i][threadIdx.x];
+  float inv = 1.f / s;
+  if (c < C) for (int r = threadIdx.y; r < n; r += 8) stf(yb + (long)r * C + c, __expf(ldf(xb + (long)r * C + c) - m) * inv);
+}
+int ggi_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, cudaStream_t st) {
+  dim3 grid(gg_cdiv(C, 32), B), block(32, 8);
+  GG_DISPATCH(dtype, (softmax_tokens_kernel<T><<<grid, block, 0, st>>>((const T*)x, (T*)y, n, C)));
+  return gg_check_launch("softmax_tokens");
+}

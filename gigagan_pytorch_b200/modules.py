@@ -688,3 +688,326 @@ class Discriminator(nn.Module):
         r = [ops.to_nhwc(t, img_cpad(self.channels), dt) for t in rgbs]
         logits, ms, aux = self.forward_nhwc(x, r, return_multiscale_outputs, calc_aux_loss)
         return logits, [ops.to_nchw(m, 1) for m in ms], aux
+
+
+# ----------------------------------------------------------------------------- attend.py (ref attend.py:34-110)
+class Attend(nn.Module):
+    """softmax(q k^T / sqrt(d)) v for (b, h, n, d) tensors — the reference's ``Attend`` (plain or "flash" SDPA path;
+    both compute the same function).  Runs the fused attention kernels (tcgen05 for bf16, d = 64, n % 128 == 0)."""
+
+    def __init__(self, dropout=0., flash=False):
+        super().__init__()
+        assert dropout == 0., "attention dropout is not used on the training hot path (reference default 0.)"
+        self.dropout, self.flash = dropout, flash
+
+    def forward(self, q, k, v):
+        b, h, n, d = q.shape
+        dt = compute_dtype()
+
+        def rows(t):      # (b, h, n, d) -> (b, n, h*d) rows, the layout the kernels read
+            return t.to(dt).permute(0, 2, 1, 3).reshape(t.shape[0], t.shape[2], h * d).contiguous()
+
+        o = ops.fused_attention(rows(q), rows(k), rows(v), None, h, d ** -0.5, l2=False)
+        return o.view(b, n, h, d).permute(0, 2, 1, 3).to(q.dtype)
+
+
+# ============================================================================= UnetUpsampler (ref unet_upsampler.py)
+def _rmsnorm_vec(x, gamma):
+    """unet RMSNorm (ref unet_upsampler.py:224-234): gamma has shape (C,)."""
+    return channel_rmsnorm(x, gamma.reshape(-1, 1, 1))
+
+
+class RMSNorm2d(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+    def forward_nhwc(self, x):
+        return _rmsnorm_vec(x, self.gamma)
+
+
+class UnetBlock(nn.Module):
+    """AdaptiveConv2DMod -> RMSNorm -> SiLU (ref :238-270)"""
+
+    def __init__(self, dim, dim_out, num_conv_kernels=0):
+        super().__init__()
+        self.proj = AdaptiveConv2DMod(dim, dim_out, kernel=3, num_conv_kernels=num_conv_kernels)
+        self.norm = RMSNorm2d(dim_out)
+        self.act = nn.SiLU()
+
+    def forward_nhwc(self, x, mods):
+        x = self.proj.forward_nhwc(x, next(mods), next(mods))
+        return ops.unary(U_SILU, self.norm.forward_nhwc(x))
+
+
+class UnetResnetBlock(nn.Module):
+    def __init__(self, dim, dim_out, *, num_conv_kernels=0, style_dims=None):
+        super().__init__()
+        mod_dims = [dim, num_conv_kernels, dim_out, num_conv_kernels]
+        style_dims.extend(mod_dims)
+        self.num_mods = len(mod_dims)
+        self.block1 = UnetBlock(dim, dim_out, num_conv_kernels)
+        self.block2 = UnetBlock(dim_out, dim_out, num_conv_kernels)
+        self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+
+    def forward_nhwc(self, x, mods):
+        h = self.block2.forward_nhwc(self.block1.forward_nhwc(x, mods), mods)
+        if isinstance(self.res_conv, nn.Identity):
+            return ops.add(h, x)
+        return ops.conv2d(x, self.res_conv.weight, self.res_conv.bias, res=h)
+
+
+class UnetLinearAttention(nn.Module):
+    """ref :312-349: softmax over d on q, over tokens on k, context = k v^T (d x d per head), out = context^T q."""
+
+    def __init__(self, dim, heads=4, dim_head=32):
+        super().__init__()
+        self.scale, self.heads, self.dim_head = dim_head ** -0.5, heads, dim_head
+        hidden = dim_head * heads
+        self.norm = RMSNorm2d(dim)
+        self.to_qkv = nn.Conv2d(dim, hidden * 3, 1, bias=False)
+        self.to_out = nn.Sequential(nn.Conv2d(hidden, dim, 1), RMSNorm2d(dim))
+
+    def forward_nhwc(self, x):
+        b, hh, ww, _ = x.shape
+        n, H, d = hh * ww, self.heads, self.dim_head
+        qkv = ops.conv2d(self.norm.forward_nhwc(x), self.to_qkv.weight)            # (b,h,w,3*H*d)
+        q, k, v = (qkv[..., i * H * d:(i + 1) * H * d] for i in range(3))
+        q = ops.axpby(self.scale, ops.softmax(q.reshape(b * n * H, d)))             # softmax over d per (token, head)
+        k = ops.softmax_tokens(k.reshape(b, n, H * d))                              # softmax over tokens per channel
+        q4 = q.view(b, n, H, d).permute(0, 2, 1, 3)                                 # (b,H,n,d)
+        kt = k.view(b, n, H, d).permute(0, 2, 3, 1)                                 # (b,H,d,n)
+        v4 = v.reshape(b, n, H, d).permute(0, 2, 1, 3)                              # (b,H,n,e)
+        context = ops.bmm(kt, v4)                                                   # (b,H,d,e)
+        out = ops.bmm(q4, context, out_bmhn=True).permute(0, 2, 1, 3).reshape(b, hh, ww, H * d)
+        out = ops.conv2d(out, self.to_out[0].weight, self.to_out[0].bias)
+        return self.to_out[1].forward_nhwc(out)
+
+
+class UnetAttention(nn.Module):
+    """ref :351-380: full attention through Attend (no null key, dot product)."""
+
+    def __init__(self, dim, heads=4, dim_head=32, flash=False):
+        super().__init__()
+        self.heads, self.dim_head = heads, dim_head
+        hidden = dim_head * heads
+        self.norm = RMSNorm2d(dim)
+        self.attend = Attend(flash=flash)
+        self.to_qkv = nn.Conv2d(dim, hidden * 3, 1, bias=False)
+        self.to_out = nn.Conv2d(hidden, dim, 1)
+
+    def forward_nhwc(self, x):
+        b, hh, ww, _ = x.shape
+        n, H, d = hh * ww, self.heads, self.dim_head
+        qkv = ops.conv2d(self.norm.forward_nhwc(x), self.to_qkv.weight).view(b, n, 3 * H * d)
+        q, k, v = (qkv[..., i * H * d:(i + 1) * H * d] for i in range(3))            # strided row views
+        o = ops.fused_attention(q, k, v, None, H, d ** -0.5, l2=False)
+        return ops.conv2d(o.view(b, hh, ww, H * d), self.to_out.weight, self.to_out.bias)
+
+
+def UnetFeedForward(dim, mult=4):
+    return nn.Sequential(RMSNorm2d(dim), nn.Conv2d(dim, dim * mult, 1), nn.GELU(), nn.Conv2d(dim * mult, dim, 1))
+
+
+class UnetTransformer(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8, depth=1, flash_attn=True, ff_mult=4, linear=False):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            attn = (UnetLinearAttention(dim=dim, dim_head=dim_head, heads=heads) if linear
+                    else UnetAttention(dim=dim, dim_head=dim_head, heads=heads, flash=flash_attn))
+            self.layers.append(nn.ModuleList([attn, UnetFeedForward(dim=dim, mult=ff_mult)]))
+
+    def forward_nhwc(self, x):
+        for attn, ff in self.layers:
+            x = ops.add(attn.forward_nhwc(x), x)
+            h = ops.conv2d(ff[0].forward_nhwc(x), ff[1].weight, ff[1].bias)
+            x = ops.conv2d(ops.unary(U_GELU, h), ff[3].weight, ff[3].bias, res=x)
+        return x
+
+
+class UnetDownsample(nn.Module):
+    """conv3x3, high-frequency skip x - blur(x), 2x2 max-pool (ref :82-160)."""
+
+    def __init__(self, dim, dim_out=None, skip_downsample=False, has_temporal_layers=False):
+        super().__init__()
+        assert not has_temporal_layers
+        self.skip_downsample = skip_downsample
+        self.conv2d = nn.Conv2d(dim, dim_out if dim_out is not None else dim, 3, padding=1)
+        self.register_buffer("filter", torch.Tensor([1., 2., 1.]))
+
+    def forward_nhwc(self, x):
+        x = ops.conv2d(x, self.conv2d.weight, self.conv2d.bias, pad=1)
+        if self.skip_downsample:
+            return x, None
+        blurred = ops.ResampleFn.apply(x, ops.get_resample_op("blur", x.shape[1], x.shape[2], x.device), False)
+        return ops.maxpool2(x), ops.axpby(1.0, x, -1.0, blurred)
+
+
+class PixelShuffleUpsample(nn.Module):
+    """conv1x1 -> SiLU -> pixel shuffle x2 (ref gigagan_pytorch.py:263-287)."""
+
+    def __init__(self, dim, dim_out=None):
+        super().__init__()
+        dim_out = dim_out if dim_out is not None else dim
+        conv = nn.Conv2d(dim, dim_out * 4, 1)
+        self.net = nn.Sequential(conv, nn.SiLU(), nn.PixelShuffle(2))
+        o, i, h, w = conv.weight.shape
+        w0 = torch.empty(o // 4, i, h, w)
+        nn.init.kaiming_uniform_(w0)
+        conv.weight.data.copy_(w0.repeat_interleave(4, dim=0))
+        nn.init.zeros_(conv.bias.data)
+
+    def forward_nhwc(self, x):
+        y = ops.unary(U_SILU, ops.conv2d(x, self.net[0].weight, self.net[0].bias))
+        b, h, w, c4 = y.shape
+        c = c4 // 4                                   # channel index = c*4 + r1*2 + r2
+        return y.view(b, h, w, c, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(b, 2 * h, 2 * w, c)
+
+
+class UnetUpsampler(BaseGenerator):
+    def __init__(self, dim, *, image_size, input_image_size, init_dim=None, out_dim=None, text_encoder=None,
+                 style_network: StyleNetwork | Dict | None = None, style_network_dim=None,
+                 dim_mults=(1, 2, 4, 8, 16), channels=3, full_attn=(False, False, False, True, True),
+                 cross_attn=(False, False, False, True, True), flash_attn=True, self_attn_dim_head=64,
+                 self_attn_heads=8, self_attn_dot_product=True, self_attn_ff_mult=4, attn_depths=(1, 1, 1, 1, 1),
+                 temporal_attn_depths=(1, 1, 1, 1, 1), cross_attn_dim_head=64, cross_attn_heads=8, cross_ff_mult=4,
+                 has_temporal_layers=False, mid_attn_depth=1, num_conv_kernels=2, unconditional=True,
+                 skip_connect_scale=None):
+        super().__init__()
+        assert unconditional and text_encoder is None and not has_temporal_layers, \
+            "this build covers the unconditional image upsampler (text / video layers: DESIGN.md section 6)"
+        self.can_upsample_video = False
+        self.text_encoder = None
+        if isinstance(style_network, dict):
+            style_network = StyleNetwork(**style_network)
+        self.style_network = style_network
+        assert exists(style_network) ^ exists(style_network_dim)
+        self.unconditional = unconditional
+        assert is_power_of_two(image_size) and is_power_of_two(input_image_size) and input_image_size < image_size
+        n_no_down = int(math.log2(image_size) - math.log2(input_image_size))
+        assert n_no_down <= len(dim_mults)
+        self.image_size, self.input_image_size, self.channels = image_size, input_image_size, channels
+        split = []
+        init_dim = init_dim if init_dim is not None else dim
+        self.init_conv = nn.Conv2d(channels, init_dim, 7, padding=3)
+        dims = [init_dim, *[dim * m for m in dim_mults]]
+        mid_dim = dims[-1]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        block = partial(UnetResnetBlock, num_conv_kernels=num_conv_kernels, style_dims=split)
+        full_attn = full_attn if isinstance(full_attn, tuple) else (full_attn,) * len(dim_mults)
+        cross_attn = cross_attn if isinstance(cross_attn, tuple) else (cross_attn,) * len(dim_mults)
+        self.skip_connect_scale = skip_connect_scale if skip_connect_scale is not None else 2 ** -0.5
+
+        def attn_klass(full, *a, **k):
+            return UnetTransformer(*a, flash_attn=flash_attn, linear=not full, **k)
+
+        self.downs, self.ups = nn.ModuleList([]), nn.ModuleList([])
+        skip_dims = []
+        for ind, ((dim_in, dim_out), layer_full, layer_depth) in enumerate(zip(in_out, full_attn, attn_depths)):
+            no_down = ind < n_no_down
+            skip_dims.append(dim_in)
+            skip_dims.append(dim_in + (dim_out if not no_down else 0))
+            self.downs.append(nn.ModuleList([
+                block(dim_in, dim_in), block(dim_in, dim_in), None,
+                attn_klass(layer_full, dim_in, dim_head=self_attn_dim_head, heads=self_attn_heads, depth=layer_depth),
+                None, None, UnetDownsample(dim_in, dim_out, skip_downsample=no_down)]))
+        self.mid_block1 = block(mid_dim, mid_dim)
+        self.mid_attn = attn_klass(True, mid_dim, dim_head=self_attn_dim_head, heads=self_attn_heads, depth=mid_attn_depth)
+        self.mid_block2 = block(mid_dim, mid_dim)
+        self.mid_to_rgb = nn.Conv2d(mid_dim, channels, 1)
+        # ref :596 zips reversed(full_attn) under the name layer_cross_attn and reversed(cross_attn) under
+        # layer_full_attn (SURVEY Q7): the attention type of the `ups` therefore follows cross_attn reversed.
+        for (dim_in, dim_out), layer_full, layer_depth in zip(reversed(in_out), reversed(cross_attn), reversed(attn_depths)):
+            self.ups.append(nn.ModuleList([
+                PixelShuffleUpsample(dim_out, dim_in), UpsampleParams(), None, None, nn.Conv2d(dim_in, channels, 1),
+                block(dim_in + skip_dims.pop(), dim_in), block(dim_in + skip_dims.pop(), dim_in), None,
+                attn_klass(layer_full, dim_in, dim_head=cross_attn_dim_head, heads=self_attn_heads, depth=layer_depth),
+                None, None]))
+        self.out_dim = out_dim if out_dim is not None else channels
+        self.final_res_block = block(dim, dim)
+        self.final_to_rgb = nn.Conv2d(dim, channels, 1)
+        self.style_to_conv_modulations = nn.Linear(style_network.dim, sum(split))
+        self.style_embed_split_dims = split
+
+    @property
+    def allowable_rgb_resolutions(self):
+        a, b = int(math.log2(self.input_image_size)), int(math.log2(self.image_size))
+        return [2 ** p for p in range(a, b)]
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def total_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    def forward_nhwc(self, lowres, styles=None, noise=None):
+        """lowres (B,S,S,C) NHWC compute dtype -> (rgb NHWC, [rgbs NHWC incl. the low-res input first])."""
+        b = lowres.shape[0]
+        if not exists(styles):
+            if not exists(noise):
+                noise = torch.randn((b, self.style_network.dim), device=self.device)
+            styles = self.style_network(noise)
+        mods = ops.linear(styles.float(), self.style_to_conv_modulations.weight, self.style_to_conv_modulations.bias)
+        mods = iter(mods.split(self.style_embed_split_dims, dim=-1))
+        cp = lowres.shape[-1]
+        x = ops.conv2d(lowres, self.init_conv.weight, self.init_conv.bias, pad=3)
+        hs = []
+        for block1, block2, _, attn, _, _, down in self.downs:
+            x = block1.forward_nhwc(x, mods)
+            hs.append(x)
+            x = block2.forward_nhwc(x, mods)
+            x = attn.forward_nhwc(x)
+            skip = x
+            x, hf = down.forward_nhwc(x)
+            hs.append(skip if hf is None else torch.cat((skip, hf), dim=-1))
+        x = self.mid_block1.forward_nhwc(x, mods)
+        x = self.mid_attn.forward_nhwc(x)
+        x = self.mid_block2.forward_nhwc(x, mods)
+
+        def to_rgb(conv, t):          # channels -> padded image channel count of the compute dtype
+            w = conv.weight
+            if cp > w.shape[0]:
+                w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, cp - w.shape[0]))
+                bias = F.pad(conv.bias, (0, cp - conv.bias.shape[0]))
+            else:
+                bias = conv.bias
+            return ops.conv2d(t, w, bias)
+
+        rgb = to_rgb(self.mid_to_rgb, x)
+        rgbs = [rgb]
+        for up, _, _, _, rgb_conv, block1, block2, _, attn, _, _ in self.ups:
+            x = up.forward_nhwc(x)
+            rgb = ops.upsample2x_blur(rgb)
+            r1 = ops.axpby(self.skip_connect_scale, hs.pop())
+            r2 = ops.axpby(self.skip_connect_scale, hs.pop())
+            if x.shape[1:3] != r1.shape[1:3]:
+                r1 = ops.resize_bilinear(r1, x.shape[1])
+                r2 = ops.resize_bilinear(r2, x.shape[1])
+            x = block1.forward_nhwc(torch.cat((x, r1), dim=-1), mods)
+            x = block2.forward_nhwc(torch.cat((x, r2), dim=-1), mods)
+            x = attn.forward_nhwc(x)
+            rgb = ops.add(rgb, to_rgb(rgb_conv, x))
+            rgbs.append(rgb)
+        x = self.final_res_block.forward_nhwc(x, mods)
+        assert next(mods, None) is None
+        rgb = ops.add(rgb, to_rgb(self.final_to_rgb, x))
+        rgbs = [lowres] + [t for t in rgbs if t.shape[2] > lowres.shape[2]]
+        return rgb, rgbs
+
+    def forward(self, lowres_image_or_video=None, styles=None, noise=None, texts=None, global_text_tokens=None,
+                fine_text_tokens=None, text_mask=None, return_all_rgbs=False,
+                replace_rgb_with_input_lowres_image=True, lowres_image=None):
+        # `lowres_image=` is what GigaGAN passes (ref gigagan_pytorch.py:2212, SURVEY Q1); accept both spellings
+        x = lowres_image_or_video if lowres_image_or_video is not None else lowres_image
+        assert x is not None and x.ndim == 4 and x.shape[-2:] == (self.input_image_size,) * 2
+        assert not any(map(exists, (texts, global_text_tokens, fine_text_tokens)))
+        xn = ops.to_nhwc(x, img_cpad(self.channels), compute_dtype())
+        rgb, rgbs = self.forward_nhwc(xn, styles, noise)
+        rgb = ops.to_nchw(rgb, self.channels)
+        if not return_all_rgbs:
+            return rgb
+        return rgb, [ops.to_nchw(t, self.channels) for t in rgbs]

@@ -1010,3 +1010,55 @@ class FusedAttnFn(Function):
 def fused_attention(q, k, v, null_kv, heads, scale, l2=False):
     shared = k is q
     return FusedAttnFn.apply(q, k, v, null_kv, heads, scale, l2, shared)
+
+
+# ============================================================================= UnetUpsampler extras
+class MaxPool2Fn(Function):
+    """2x2 max-pool of an NHWC map (first-order; the upsampler is never inside the gradient penalty)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h // 2, w // 2, c), dtype=x.dtype, device=x.device)
+        call("gg_maxpool2_fwd", _p(x), _p(y), n, h, w, c, _dt(x), _st())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gy = _c(gy)
+        n, h, w, c = x.shape
+        gx = torch.empty_like(x)
+        call("gg_maxpool2_bwd", _p(x), _p(gy), _p(gx), n, h, w, c, _dt(x), _st())
+        return gx
+
+
+def maxpool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+class SoftmaxTokensFn(Function):
+    """softmax over the token axis of (B, n, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        b, n, c = x.shape
+        y = torch.empty_like(x)
+        call("gg_softmax_tokens", _p(x), _p(y), b, n, c, _dt(x), _st())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        b, n, c = p.shape
+        r = dot_sc(p, g, n, b)                                # (b, c) = sum_tokens p * g
+        return axpby(1.0, mul(p, g), -1.0, scale_channels(p, r, n, b))
+
+
+def softmax_tokens(x):
+    return SoftmaxTokensFn.apply(x)

@@ -180,7 +180,6 @@ class GigaGAN(nn.Module):
         super().__init__()
         assert vision_aided_discriminator is None, "VisionAidedDiscriminator needs CLIP weights (out of scope)"
         assert diff_augment is None, "DiffAugment is host-side and not part of this build yet"
-        assert not train_upsampler, "UnetUpsampler training is the next SURVEY 8 row (not in this build)"
         if amp:
             assert mixed_precision_type == "bf16", "B200 path computes in bf16 (set mixed_precision_type='bf16')"
             set_compute_dtype(torch.bfloat16)
@@ -188,10 +187,18 @@ class GigaGAN(nn.Module):
         self.apply_gradient_penalty_every = apply_gradient_penalty_every
         self.calc_multiscale_loss_every = calc_multiscale_loss_every
         if isinstance(generator, dict):
-            generator = Generator(**generator)
+            if train_upsampler:
+                from .modules import UnetUpsampler
+                generator = UnetUpsampler(**generator)
+            else:
+                generator = Generator(**generator)
         if isinstance(discriminator, dict):
             discriminator = Discriminator(**discriminator)
         self.G, self.D, self.VD = generator, discriminator, None
+        if train_upsampler:
+            missing = set(discriminator.multiscale_input_resolutions) - set(generator.allowable_rgb_resolutions)
+            assert not missing, (f"only multiscale input resolutions of {generator.allowable_rgb_resolutions} are allowed "
+                                 "based on the unet input and output image size")
         self.diff_augment = None
         assert generator.unconditional == discriminator.unconditional
         self.unconditional = generator.unconditional
@@ -331,7 +338,7 @@ class GigaGAN(nn.Module):
         real_n = ops.to_nhwc(real, img_cpad(D.channels), dt)
         real_rgbs = D.real_images_to_rgbs_nhwc(real_n)
         with torch.no_grad():
-            fake, rgbs = G.forward_nhwc(noise=noise)
+            fake, rgbs = self._generate(noise, real_n.detach())
         fake = fake.detach().requires_grad_(gp_on)
         rgbs = [t.detach().requires_grad_(gp_on) for t in rgbs]
         fused = False if gp_on else None      # gradient penalty needs the any-order-differentiable attention
@@ -360,8 +367,20 @@ class GigaGAN(nn.Module):
             total = ops.axpby(1.0, total, self.discr_aux_recon_loss_weight, aux_loss)
         return total, (div, ms, gp, aux_loss)
 
+    def _generate(self, noise, real_n=None):
+        """G forward in NHWC.  The upsampler sees the real batch resized (nearest, like F.interpolate's default at
+        ref gigagan_pytorch.py:2210) to its input size."""
+        if not self.train_upsampler:
+            return self.G.forward_nhwc(noise=noise)
+        f = real_n.shape[1] // self.G.input_image_size
+        lowres = real_n[:, ::f, ::f, :].contiguous()
+        return self.G.forward_nhwc(lowres, noise=noise)
+
     def _g_objective(self, noise, calc_multiscale_loss):
-        fake, rgbs = self.G.forward_nhwc(noise=noise)
+        real_n = None
+        if self.train_upsampler:
+            real_n = ops.to_nhwc(self._real_buf.detach(), img_cpad(self.D.channels), compute_dtype())
+        fake, rgbs = self._generate(noise, real_n)
         logits, ms, _ = self.D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False)
         div = generator_hinge_loss(logits)
         total, msd = div, torch.zeros((), device=noise.device)
@@ -474,6 +493,8 @@ class GigaGAN(nn.Module):
             p.requires_grad_(False)
         acc = None
         try:
+            if self.train_upsampler:                       # ref generate_kwargs (:2196): a fresh real batch per G step
+                self._stage_real(self._next_images(dl_iter))
             if grad_accum_every == 1:
                 def work():
                     self._begin_work()

@@ -133,6 +133,12 @@ int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_k
 int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr,
              float lr, float b1, float b2, float eps, float wd, float grad_scale, gg_stream_t stream);
 int gg_incr(int* p, gg_stream_t stream);
+
+/* ---- UnetUpsampler extras (unet_upsampler.py): 2x2 max-pool of NHWC maps (:158) and its gradient; softmax over the
+ * token axis of (B, n, C) maps per (sample, channel) (LinearAttention k.softmax(dim=-1), :340). */
+int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream);
+int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream);
+int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream);
 /* ---- once-per-step re-layout of all conv weights of a model from the flat fp32 master buffer (reference layout
  * [O][I][KK]) into both kernel layouts: fwd [O][KK][Ipad] and bwd [Ipad][KK reversed][O] (replaces the per-call
  * weight permutes cuDNN does internally for nn.Conv2d / F.conv2d and their autograd).

@@ -443,3 +443,162 @@ class OracleTrainer:
         g_loss.backward()
         self.opt_g.step()
         return float(d_loss.detach()), float(g_loss.detach())
+
+
+# --------------------------------------------------------------------------- #
+# UnetUpsampler (ref: unet_upsampler.py:447-898), unconditional image path
+# --------------------------------------------------------------------------- #
+
+def unet_plan(dim, image_size, input_image_size, dim_mults=(1, 2, 4, 8, 16), channels=3,
+              full_attn=(False, False, False, True, True), cross_attn=None, num_conv_kernels=2, init_dim=None,
+              self_attn_dim_head=64, self_attn_heads=8, cross_attn_dim_head=64, attn_depths=(1, 1, 1, 1, 1),
+              mid_attn_depth=1, skip_connect_scale=None, self_attn_ff_mult=4):
+    """Dimension bookkeeping of the reference constructor (unet_upsampler.py:509-640), incl. the modulation split list
+    (ResnetBlock appends [dim, n, dim_out, n] per block in construction order) and its quirk Q7: the `ups` loop zips
+    reversed(in_out) with reversed(full_attn) under swapped names, so the ups attention type follows full_attn
+    reversed through the *cross_attn* slot order (unet_upsampler.py:596)."""
+    init_dim = init_dim or dim
+    dims = [init_dim] + [dim * m for m in dim_mults]
+    in_out = list(zip(dims[:-1], dims[1:]))
+    n_no_down = int(math.log2(image_size) - math.log2(input_image_size))
+    split, skip_dims = [], []
+    nk = num_conv_kernels
+
+    def res(ci, co):
+        split.extend([ci, nk, co, nk])
+        return dict(dim_in=ci, dim_out=co)
+
+    downs = []
+    for ind, ((ci, co), fa, depth) in enumerate(zip(in_out, full_attn, attn_depths)):
+        no_down = ind < n_no_down
+        skip_dims.append(ci)
+        skip_dims.append(ci + (co if not no_down else 0))
+        downs.append(dict(block1=res(ci, ci), block2=res(ci, ci), full_attn=fa, depth=depth, dim=ci, dim_out=co,
+                          skip_downsample=no_down))
+    mid_dim = dims[-1]
+    mid = dict(block1=res(mid_dim, mid_dim), depth=mid_attn_depth, block2=None, dim=mid_dim)
+    mid["block2"] = res(mid_dim, mid_dim)
+    ups = []
+    # ref :596: zip(reversed(in_out), reversed(full_attn) [named layer_cross_attn], reversed(cross_attn) [named
+    # layer_full_attn], ...) -> with the default cross_attn == full_attn the attention type is full_attn reversed.
+    for (ci, co), fa, depth in zip(reversed(in_out), reversed(cross_attn if cross_attn is not None else full_attn),
+                                   reversed(attn_depths)):
+        b1 = res(ci + skip_dims.pop(), ci)
+        b2 = res(ci + skip_dims.pop(), ci)
+        ups.append(dict(dim_in=ci, dim_out=co, block1=b1, block2=b2, full_attn=fa, depth=depth))
+    final = res(dim, dim)
+    return dict(downs=downs, mid=mid, ups=ups, final=final, split=split, channels=channels,
+                heads=self_attn_heads, dim_head=self_attn_dim_head, up_dim_head=cross_attn_dim_head,
+                skip_scale=skip_connect_scale if skip_connect_scale is not None else 2 ** -0.5,
+                input_image_size=input_image_size, image_size=image_size)
+
+
+def unet_rmsnorm(x, gamma):
+    # ref unet_upsampler.py:224-234
+    c = x.shape[1]
+    nrm = x.pow(2).sum(dim=1, keepdim=True).sqrt().clamp(min=1e-12)
+    return x / nrm * gamma.view(1, c, 1, 1) * (c ** 0.5)
+
+
+def unet_block(sd, x, mods):
+    # ref unet_upsampler.py:238-270  AdaptiveConv -> RMSNorm -> SiLU
+    x = adaptive_conv2d_mod(sd["proj.weights"], x, mods.pop(0), mods.pop(0))
+    x = unet_rmsnorm(x, sd["norm.gamma"])
+    return x * torch.sigmoid(x)
+
+
+def unet_resnet_block(sd, x, mods):
+    # ref unet_upsampler.py:272-310
+    h = unet_block(_sub(sd, "block1."), x, mods)
+    h = unet_block(_sub(sd, "block2."), h, mods)
+    r = F.conv2d(x, sd["res_conv.weight"], sd["res_conv.bias"]) if "res_conv.weight" in sd else x
+    return h + r
+
+
+def unet_linear_attention(sd, x, heads, dim_head):
+    # ref unet_upsampler.py:312-349
+    b, c, hh, ww = x.shape
+    xn = unet_rmsnorm(x, sd["norm.gamma"])
+    q, k, v = F.conv2d(xn, sd["to_qkv.weight"]).chunk(3, dim=1)
+    q, k, v = (t.reshape(b, heads, dim_head, hh * ww) for t in (q, k, v))
+    q = q.softmax(dim=-2) * dim_head ** -0.5
+    k = k.softmax(dim=-1)
+    context = torch.einsum("bhdn,bhen->bhde", k, v)
+    out = torch.einsum("bhde,bhdn->bhen", context, q).reshape(b, heads * dim_head, hh, ww)
+    out = F.conv2d(out, sd["to_out.0.weight"], sd["to_out.0.bias"])
+    return unet_rmsnorm(out, sd["to_out.1.gamma"])
+
+
+def unet_attention(sd, x, heads, dim_head):
+    # ref unet_upsampler.py:351-380 + attend.py:99-108
+    b, c, hh, ww = x.shape
+    xn = unet_rmsnorm(x, sd["norm.gamma"])
+    q, k, v = F.conv2d(xn, sd["to_qkv.weight"]).chunk(3, dim=1)
+    q, k, v = (t.reshape(b, heads, dim_head, hh * ww).transpose(-1, -2) for t in (q, k, v))
+    attn = ((q @ k.transpose(-1, -2)) * dim_head ** -0.5).softmax(dim=-1)
+    out = (attn @ v).transpose(-1, -2).reshape(b, heads * dim_head, hh, ww)
+    return F.conv2d(out, sd["to_out.weight"], sd["to_out.bias"])
+
+
+def unet_transformer(sd, x, full, depth, heads, dim_head):
+    # ref unet_upsampler.py:395-443 (Transformer / LinearTransformer)
+    for d in range(depth):
+        a = _sub(sd, f"layers.{d}.0.")
+        x = (unet_attention if full else unet_linear_attention)(a, x, heads, dim_head) + x
+        f = _sub(sd, f"layers.{d}.1.")
+        h = unet_rmsnorm(x, f["0.gamma"])
+        h = F.conv2d(F.gelu(F.conv2d(h, f["1.weight"], f["1.bias"])), f["3.weight"], f["3.bias"])
+        x = h + x
+    return x
+
+
+def unet_downsample(sd, x, skip_downsample):
+    # ref unet_upsampler.py:82-160: conv3x3, then (x - blur(x)) as a high-frequency skip and max-pool 2
+    x = F.conv2d(x, sd["conv2d.weight"], sd["conv2d.bias"], padding=1)
+    if skip_downsample:
+        return x, x[:, 0:0]
+    return F.max_pool2d(x, 2), x - blur3(x)
+
+
+def unet_forward(sd: SD, plan: dict, lowres: Tensor, noise: Tensor, style_depth: int = 4,
+                 return_all_rgbs: bool = False):
+    """ref unet_upsampler.py:657-898 (image input, unconditional)."""
+    styles = style_network(_sub(sd, "style_network."), noise, style_depth)
+    mods = list(F.linear(styles, sd["style_to_conv_modulations.weight"],
+                         sd["style_to_conv_modulations.bias"]).split(plan["split"], dim=-1))
+    H, dh = plan["heads"], plan["dim_head"]
+    x = F.conv2d(lowres, sd["init_conv.weight"], sd["init_conv.bias"], padding=3)
+    hs = []
+    for i, L in enumerate(plan["downs"]):
+        p = f"downs.{i}."
+        x = unet_resnet_block(_sub(sd, p + "0."), x, mods)
+        hs.append(x)
+        x = unet_resnet_block(_sub(sd, p + "1."), x, mods)
+        x = unet_transformer(_sub(sd, p + "3."), x, L["full_attn"], L["depth"], H, dh)
+        skip = x
+        x, hf = unet_downsample(_sub(sd, p + "6."), x, L["skip_downsample"])
+        hs.append(torch.cat((skip, hf), dim=1))
+    x = unet_resnet_block(_sub(sd, "mid_block1."), x, mods)
+    x = unet_transformer(_sub(sd, "mid_attn."), x, True, plan["mid"]["depth"], H, dh)
+    x = unet_resnet_block(_sub(sd, "mid_block2."), x, mods)
+    rgb = F.conv2d(x, sd["mid_to_rgb.weight"], sd["mid_to_rgb.bias"])
+    rgbs = [rgb]
+    for i, L in enumerate(plan["ups"]):
+        p = f"ups.{i}."
+        x = F.pixel_shuffle(F.silu(F.conv2d(x, sd[p + "0.net.0.weight"], sd[p + "0.net.0.bias"])), 2)   # :267-273
+        rgb = upsample2x(rgb)
+        r1, r2 = hs.pop() * plan["skip_scale"], hs.pop() * plan["skip_scale"]
+        if x.shape[2:] != r1.shape[2:]:
+            r1 = F.interpolate(r1, tuple(x.shape[2:]), mode="bilinear")
+            r2 = F.interpolate(r2, tuple(x.shape[2:]), mode="bilinear")
+        x = unet_resnet_block(_sub(sd, p + "5."), torch.cat((x, r1), dim=1), mods)
+        x = unet_resnet_block(_sub(sd, p + "6."), torch.cat((x, r2), dim=1), mods)
+        x = unet_transformer(_sub(sd, p + "8."), x, L["full_attn"], L["depth"], plan["heads"], plan["up_dim_head"])
+        rgb = rgb + F.conv2d(x, sd[p + "4.weight"], sd[p + "4.bias"])
+        rgbs.append(rgb)
+    x = unet_resnet_block(_sub(sd, "final_res_block."), x, mods)
+    assert not mods
+    rgb = rgb + F.conv2d(x, sd["final_to_rgb.weight"], sd["final_to_rgb.bias"])
+    if not return_all_rgbs:
+        return rgb
+    return rgb, [lowres] + [t for t in rgbs if t.shape[-1] > lowres.shape[-1]]

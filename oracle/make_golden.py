@@ -98,6 +98,19 @@ def main():
                               gradient_penalty=gp.detach()),
                     grads={k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}),
                os.path.join(OUT, "ka5_discriminator.pt"))
+    # ---- KA6: tiny UnetUpsampler (16 -> 32) fwd + grads of mean(rgb^2)
+    ucfg = dict(dim=4, image_size=32, input_image_size=16, style_network=dict(dim=16, depth=2), dim_mults=(1, 2, 4),
+                full_attn=(False, False, True), cross_attn=(False, False, True), attn_depths=(1, 1, 1),
+                self_attn_dim_head=8, self_attn_heads=2, cross_attn_dim_head=8, unconditional=True)
+    torch.manual_seed(0)
+    U = ref.UnetUpsampler(**ucfg)
+    low = torch.rand(2, 3, 16, 16, generator=torch.Generator().manual_seed(3))
+    z = rn(1, 2, 16)
+    rgb, rgbs = U(low, noise=z, return_all_rgbs=True)
+    (rgb ** 2).mean().backward()
+    torch.save(dict(cfg=ucfg, sd=sd_of(U), low=low, z=z, rgb=rgb.detach(), rgbs=[t.detach() for t in rgbs],
+                    grads={k: p.grad.clone() for k, p in U.named_parameters() if p.grad is not None}),
+               os.path.join(OUT, "ka6_unet_upsampler.pt"))
     for f_ in sorted(os.listdir(OUT)):
         print(f_, os.path.getsize(os.path.join(OUT, f_)))
 

@@ -93,3 +93,19 @@ def test_ka5_discriminator_step_with_gradient_penalty():
     torch.testing.assert_close(gp.detach(), g["loss"]["gradient_penalty"], rtol=1e-4, atol=1e-6)
     for k, v in g["grads"].items():
         assert relerr(sd[k].grad, v) < 1e-3, k
+
+
+def test_ka6_unet_upsampler():
+    g = load("ka6_unet_upsampler.pt")
+    c = g["cfg"]
+    plan = O.unet_plan(c["dim"], c["image_size"], c["input_image_size"], c["dim_mults"], 3, c["full_attn"],
+                       c["cross_attn"], self_attn_dim_head=8, self_attn_heads=2, cross_attn_dim_head=8,
+                       attn_depths=c["attn_depths"])
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and not k.endswith(("filter", ".f"))) for k, v in g["sd"].items()}
+    rgb, rgbs = O.unet_forward(sd, plan, g["low"], g["z"], style_depth=2, return_all_rgbs=True)
+    torch.testing.assert_close(rgb, g["rgb"], **TOL)
+    for a, b in zip(rgbs, g["rgbs"]):
+        torch.testing.assert_close(a, b, **TOL)
+    (rgb ** 2).mean().backward()
+    for k, v in g["grads"].items():
+        assert relerr(sd[k].grad, v) < 2e-4, k

@@ -135,3 +135,19 @@ def test_adamw_matches_reference_optimizer():
             O.adamw_step(p, g, m, v, step)
     for (p, _, _), q in zip(mine, ps):
         torch.testing.assert_close(p, q.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_unet_upsampler():
+    ref = import_reference()
+    torch.manual_seed(0)
+    U = ref.UnetUpsampler(dim=8, image_size=64, input_image_size=16, style_network=dict(dim=64, depth=4), unconditional=True)
+    plan = O.unet_plan(8, 64, 16)
+    assert plan["split"] == U.style_embed_split_dims
+    x = torch.rand(2, 3, 16, 16, generator=torch.Generator().manual_seed(3))
+    z = rn(1, 2, 64)
+    with torch.no_grad():
+        r, rs = U(x, noise=z, return_all_rgbs=True)
+        o, os_ = O.unet_forward(dict(U.state_dict()), plan, x, z, return_all_rgbs=True)
+    torch.testing.assert_close(o, r, **TOL)
+    for a, b in zip(os_, rs):
+        torch.testing.assert_close(a, b, **TOL)
