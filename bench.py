@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "cpu-worker"])
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch")
     ap.add_argument("--image-size", type=int, default=256)
     ap.add_argument("--no-graphs", action="store_true")
@@ -91,38 +91,82 @@ def real_batch(step, world, rank, batch, size, pin=False):
 
 
 # ------------------------------------------------------------------------------------------- reference arm (CPU)
-def run_reference(args):
+CPU_THREADS_CAP = 32
+
+
+def _oracle_trainer(size):
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     from oracle import gigagan_oracle as O
     import gigagan_pytorch_b200 as g            # constructors only (CPU tensors): same seeded init as the reference
     torch.manual_seed(0)
-    gcfg, dcfg = dict(G_CFG, image_size=args.image_size), dict(D_CFG, image_size=args.image_size)
-    G, D = g.Generator(**gcfg), g.Discriminator(**dcfg)
-    plan_g = O.generator_plan(args.image_size, 8, 512, num_skip_layers_excite=4)
-    plan_d = O.discriminator_plan(args.image_size, 16, 512, num_skip_layers_excite=4)
-    tr = O.OracleTrainer(dict(G.state_dict()), plan_g, dict(D.state_dict()), plan_d)
-    cores = os.cpu_count()
+    G, D = g.Generator(**dict(G_CFG, image_size=size)), g.Discriminator(**dict(D_CFG, image_size=size))
+    return O.OracleTrainer(dict(G.state_dict()), O.generator_plan(size, 8, 512, num_skip_layers_excite=4),
+                           dict(D.state_dict()), O.discriminator_plan(size, 16, 512, num_skip_layers_excite=4))
+
+
+def cpu_worker(args):
+    """Runs in a subprocess (hard wall-clock bound from the parent): oracle G+D steps on the host cores, one JSON
+    progress line per finished step so the parent can use whatever completed."""
+    import torch
+    cores = min(os.cpu_count() or 1, CPU_THREADS_CAP)
     torch.set_num_threads(cores)
+    tr = _oracle_trainer(args.image_size)
     b = args.ref_batch
-    for s in range(args.warmup):
-        tr.step(real_batch(s, 1, 0, b, args.image_size), False)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        tr.step(real_batch(args.warmup + s, 1, 0, b, args.image_size), (s + 1) % 4 == 0)
-    dt = time.perf_counter() - t0
-    val = b * args.steps / dt
-    sample = f"{args.steps} G+D steps of batch {b} at {args.image_size}x{args.image_size}, fp32, gradient penalty every 4th"
+    print(json.dumps({"event": "ready", "cores": cores}), flush=True)
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        gp = s >= args.warmup and (s - args.warmup + 1) % 4 == 0
+        tr.step(real_batch(s, 1, 0, b, args.image_size), gp)
+        print(json.dumps({"event": "step", "index": s, "timed": s >= args.warmup, "gp": gp,
+                          "seconds": time.perf_counter() - t0}), flush=True)
+
+
+def run_cpu_steps(size, batch, warmup, steps, budget_s):
+    """-> (images/s, cores, steps used, description).  Bounded by budget_s of wall clock."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-worker", "--image-size", str(size), "--ref-batch",
+           str(batch), "--warmup", str(warmup), "--steps", str(steps)]
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    t_start, rows, cores = time.perf_counter(), [], None
+
+    def reader():
+        for line in proc.stdout:
+            try:
+                rows.append(json.loads(line))
+            except Exception:
+                pass
+    th = threading.Thread(target=reader, daemon=True)
+    th.start()
+    while proc.poll() is None and time.perf_counter() - t_start < budget_s:
+        time.sleep(0.5)
+    if proc.poll() is None:
+        proc.kill()
+    th.join(timeout=5)
+    cores = next((r["cores"] for r in rows if r.get("event") == "ready"), min(os.cpu_count() or 1, CPU_THREADS_CAP))
+    timed = [r for r in rows if r.get("event") == "step" and r["timed"]]
+    anyst = [r for r in rows if r.get("event") == "step"]
+    use = timed if timed else anyst
+    if not use:
+        dt = time.perf_counter() - t_start
+        return batch / dt, cores, 0, f"no G+D step of batch {batch} finished within the {budget_s:.0f} s budget (upper bound)"
+    secs = sum(r["seconds"] for r in use)
+    desc = (f"{len(use)} {'timed' if timed else 'warm-up'} G+D step(s) of batch {batch} at {size}x{size}, fp32 torch CPU, "
+            f"{cores} threads, {sum(1 for r in use if r['gp'])} with gradient penalty; wall budget {budget_s:.0f} s")
+    return batch * len(use) / secs, cores, len(use), desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, cores, used, desc = run_cpu_steps(args.image_size, args.ref_batch, min(args.warmup, 1), args.steps, budget_s=240.0)
     print(json.dumps({
         "impl": "reference", "metric": "images/sec, 256x256 unconditional G+D training step", "value": val,
-        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": used, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * args.ref_batch / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "GigaGAN unconditional 256x256 G+D step (README config), CPU oracle port of the reference",
-                   "global_batch": b},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+                   "global_batch": args.ref_batch},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -263,26 +307,15 @@ def run_ours(args):
 
 def cpu_baseline(size):
     """Oracle (port of the reference algorithm) on the host cores: one plain G+D step at batch 1 (bounded sample)."""
-    import torch
-    from oracle import gigagan_oracle as O
-    import gigagan_pytorch_b200 as g
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    G, D = g.Generator(**dict(G_CFG, image_size=size)), g.Discriminator(**dict(D_CFG, image_size=size))
-    tr = O.OracleTrainer(dict(G.state_dict()), O.generator_plan(size, 8, 512, num_skip_layers_excite=4),
-                         dict(D.state_dict()), O.discriminator_plan(size, 16, 512, num_skip_layers_excite=4))
-    tr.step(real_batch(0, 1, 0, 1, size), False)
-    t0 = time.perf_counter()
-    tr.step(real_batch(1, 1, 0, 1, size), False)
-    dt = time.perf_counter() - t0
-    return {"value": 1.0 / dt, "unit": "images/s", "cores": cores, "kind": "port",
-            "sample": f"1 plain G+D step, batch 1, {size}x{size}, fp32 torch CPU (after 1 warm-up step)"}
+    val, cores, used, desc = run_cpu_steps(size, 1, 0, 1, budget_s=90.0)
+    return {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": desc}
 
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.impl == "cpu-worker":
+        cpu_worker(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -10,6 +10,7 @@
 #include "tc_common.cuh"
 
 #define ATC_THREADS 192
+#define ATC_FWD_THREADS 320   // forward: TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quarter)
 #define ATC_D 64
 #define ATC_T 128          // queries per CTA == keys per tile
 
@@ -47,7 +48,7 @@ __global__ void attn_ksq_kernel(const bf16* __restrict__ k, float* __restrict__ 
   if (lane == 0) ksq[row] = s;
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+__global__ void __launch_bounds__(ATC_FWD_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const AtcP p, const float* __restrict__ null_kv,
                    const float* __restrict__ ksq, bf16* __restrict__ o, float* __restrict__ lse2) {
@@ -59,10 +60,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t sQ = base, sK = base + 16384, sV = sK + 32768, sP = sV + 32768;
   float* ksq_sm = (float*)(gbase + 147456);
   float* null_sm = (float*)(gbase + 147456 + 1024);
-  const uint32_t bars = base + 147456 + 1024 + 512;
+  float* xchg = (float*)(gbase + 147456 + 1536);              // row max / row sum exchange between the two column halves
+  const uint32_t bars = base + 147456 + 2560;
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13, P_EMPTY = 15, O_FULL = 17 };
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(gbase + 147456 + 1024 + 512 + 8 * 18);
+  uint32_t* tmem_slot = (uint32_t*)(gbase + 147456 + 2560 + 8 * 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
@@ -74,8 +76,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
       mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
-      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
-      mbar_init(bar(P_FULL + i), 4); mbar_init(bar(P_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 8);
+      mbar_init(bar(P_FULL + i), 8); mbar_init(bar(P_EMPTY + i), 1);
     }
     mbar_init(bar(O_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -84,7 +86,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x >= 64 && p.has_null) {
+  if (threadIdx.x >= 64 && threadIdx.x < 192 && p.has_null) {
     int t = threadIdx.x - 64;                       // 128 threads: k_null[64], v_null[64]
     null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
   }
@@ -160,13 +162,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       ++pc;
     }
   } else {
-    // ================================================= softmax / epilogue: thread <-> query row <-> TMEM lane
+    // ================================================= softmax / epilogue
+    // 8 warps: warp % 4 selects the TMEM lane quarter (32 query rows), (warp - 2) / 4 the 64-column half of every
+    // 128-key tile - two threads per query row, so the MUFU/FMA work of a row is issued from two schedulers.
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;
     const int r = q * 32 + lane;                      // row inside the tile
-    const int st = threadIdx.x - 64;                  // 0..127 index among the softmax threads
+    const int st = threadIdx.x - 64;                  // 0..255 index among the softmax threads
+    const int cb = hsel * 64;                         // first column of this thread's half
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r; // global token row
-    // logit of the null key from this thread's q row (read from the swizzled Q tile)
     float t_null = -INFINITY;
     mbar_wait(bar(Q_FULL), 0);
     if (p.has_null) {
@@ -188,23 +193,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     float m = t_null;
     int sc = 0, pc = 0;
-    // ---------------- pass A: row maximum
+    // ---------------- pass A: row maximum (each thread over its 64 columns)
     for (int j = 0; j < T; ++j) {
       int ss = sc & 1;
       if (p.mode == 1) {
-        ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
-        named_bar_sync(1, 128);
+        if (st < 128) ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 256);
       }
       mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
       tc_fence_after();
-#pragma unroll 2
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
-        tc_ld16(tS + ss * 128 + lane_addr + c0, v);
+        tc_ld16(tS + ss * 128 + lane_addr + cb + c0, v);
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float t = __uint_as_float(v[e]) * p.c2;
-          if (p.mode == 1) t += ksq_sm[ss * 128 + c0 + e];
+          if (p.mode == 1) t += ksq_sm[ss * 128 + cb + c0 + e];
           m = fmaxf(m, t);
         }
       }
@@ -213,28 +218,31 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) mbar_arrive(bar(S_EMPTY + ss));
       ++sc;
     }
-    // ---------------- pass B: probabilities, row sums, P tiles for the second MMA
-    float l = p.has_null ? fast_exp2(t_null - m) : 0.f;
-    const float p_null = l;
+    xchg[hsel * 128 + r] = m;
+    named_bar_sync(2, 256);
+    m = fmaxf(m, xchg[(1 - hsel) * 128 + r]);
+    // ---------------- pass B: probabilities, partial row sums, this half's P slab
+    const float p_null = p.has_null ? fast_exp2(t_null - m) : 0.f;
+    float l = hsel == 0 ? p_null : 0.f;
     for (int j = 0; j < T; ++j) {
       int ss = sc & 1, ps = pc & 1;
       if (p.mode == 1) {
-        ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
-        named_bar_sync(1, 128);
+        if (st < 128) ksq_sm[ss * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 256);
       }
       mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
       mbar_wait(bar(P_EMPTY + ps), ((pc >> 1) & 1) ^ 1u);
       tc_fence_after();
-      uint8_t* prow = gbase + (sP - base) + ps * 32768 + r * 128;
-#pragma unroll 2
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      uint8_t* prow = gbase + (sP - base) + ps * 32768 + hsel * 16384 + r * 128;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
         uint32_t v[16];
-        tc_ld16(tS + ss * 128 + lane_addr + c0, v);
+        tc_ld16(tS + ss * 128 + lane_addr + cb + c0, v);
         float pv[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           float t = __uint_as_float(v[e]) * p.c2;
-          if (p.mode == 1) t += ksq_sm[ss * 128 + c0 + e];
+          if (p.mode == 1) t += ksq_sm[ss * 128 + cb + c0 + e];
           pv[e] = fast_exp2(t - m);
           l += pv[e];
         }
@@ -246,10 +254,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           h0[e] = __floats2bfloat162_rn(pv[2 * e], pv[2 * e + 1]);
           h1[e] = __floats2bfloat162_rn(pv[8 + 2 * e], pv[8 + 2 * e + 1]);
         }
-        int slab = c0 >> 6, ch = (c0 & 63) >> 3;      // 16 columns = two 16-byte chunks ch, ch+1 of a 128-byte row
-        uint8_t* dst = prow + slab * 16384;
-        *reinterpret_cast<uint4*>(dst + (((ch) ^ (r & 7)) << 4)) = o0;
-        *reinterpret_cast<uint4*>(dst + (((ch + 1) ^ (r & 7)) << 4)) = o1;
+        int ch = c0 >> 3;                              // two 16-byte chunks ch, ch+1 of this row's 128-byte slab row
+        *reinterpret_cast<uint4*>(prow + (((ch) ^ (r & 7)) << 4)) = o0;
+        *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ (r & 7)) << 4)) = o1;
       }
       fence_async_smem();                             // generic-proxy stores -> visible to the UMMA (async proxy)
       tc_fence_before();
@@ -257,13 +264,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (lane == 0) { mbar_arrive(bar(P_FULL + ps)); mbar_arrive(bar(S_EMPTY + ss)); }
       ++sc; ++pc;
     }
-    // ---------------- epilogue: O / l (+ null value), log-sum-exp
+    named_bar_sync(2, 256);                           // pass-A exchange fully consumed before the slots are reused
+    xchg[hsel * 128 + r] = l;
+    named_bar_sync(2, 256);
+    l += xchg[(1 - hsel) * 128 + r];
+    // ---------------- epilogue: O / l (+ null value): each thread stores 32 of the 64 output columns
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
     const float inv = 1.f / l;
     bf16* orow = o + grow * p.o_rs + h * ATC_D;
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = hsel * 32; c0 < hsel * 32 + 32; c0 += 16) {
       uint32_t v[16];
       tc_ld16(tO + lane_addr + c0, v);
       float f[16];
@@ -283,7 +294,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       st_global_256(orow + c0, o0, o1);
     }
-    lse2[(long)bh * p.n + qt * ATC_T + r] = m + log2f(l);
+    if (hsel == 0) lse2[(long)bh * p.n + qt * ATC_T + r] = m + log2f(l);
   }
   tc_fence_before();
   __syncthreads();
@@ -321,14 +332,14 @@ int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* nu
     long rows = (long)B * heads * nk;
     attn_ksq_kernel<<<gg_cdiv(rows, 8), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
   }
-  size_t smem = 1024 + 147456 + 1024 + 512 + 8 * 18 + 16;
+  size_t smem = 1024 + 147456 + 2560 + 8 * 18 + 16;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   int grid = B * heads * p.tiles;
-  attn_fwd_tc_kernel<<<grid, ATC_THREADS, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
+  attn_fwd_tc_kernel<<<grid, ATC_FWD_THREADS, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
   return gg_check_launch("attn_fwd_tc");
 }
 

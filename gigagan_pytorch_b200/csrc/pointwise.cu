@@ -844,20 +844,37 @@ int ggi_incr(int* p, cudaStream_t st) { incr_kernel<<<1, 1, 0, st>>>(p); return 
 // For every registered conv weight (fp32 master, reference layout [O][I][KK]) write BOTH kernel layouts in bf16/fp32:
 //   fwd[o][kk][ipad]            (K-major B operand of the forward implicit GEMM, input channels zero-padded)
 //   bwd[ipad][KK-1-kk][o]       (flipped + in/out swapped: the data gradient runs as a forward convolution)
-// entries: int64 x 8 = {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32 x 4 = {entry, start, count, 0}
+// entries: int64 x 8 = {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32 x 4 = {entry, o0, i0, TI}:
+// one block moves the (32 output channels) x (TI input channels) x KK tile through shared memory so that the master
+// read ([o][i][kk]: runs of TI*KK floats) and both writes (runs of TI along i / 32 along o) are contiguous.
+#define WP_MAX_ROW 380
 template <typename T>
 __global__ void weight_prep_multi_kernel(const float* __restrict__ master, const long* __restrict__ entries,
                                          const int4* __restrict__ chunks, T* __restrict__ fwd, T* __restrict__ bwd) {
-  int4 ch = chunks[blockIdx.x];
+  __shared__ float s[32 * (WP_MAX_ROW + 1)];
+  const int4 ch = chunks[blockIdx.x];
   const long* e = entries + (long)ch.x * 8;
-  const long src = e[0], O = e[1], I = e[2], KK = e[3], Ip = e[4], fo = e[5], bo = e[6];
-  for (int t = threadIdx.x; t < ch.z; t += blockDim.x) {
-    long idx = (long)ch.y + t;                 // linear index in the fwd layout [o][kk][ipad]
-    long i = idx % Ip, r = idx / Ip;
-    long kk = r % KK, o = r / KK;
-    float v = i < I ? master[src + (o * I + i) * KK + kk] : 0.f;
-    stf(fwd + fo + idx, v);
-    stf(bwd + bo + (i * KK + (KK - 1 - kk)) * O + o, v);
+  const long src = e[0], fo = e[5], bo = e[6];
+  const int O = (int)e[1], I = (int)e[2], KK = (int)e[3], Ip = (int)e[4];
+  const int o0 = ch.y, i0 = ch.z, TI = ch.w;
+  const int no = min(32, O - o0), ni = min(TI, Ip - i0);        // tile extents (ni counts padded channels too)
+  const int nir = max(0, min(ni, I - i0));                       // channels that exist in the master
+  const int pitch = TI * KK + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ol = warp; ol < no; ol += 8) {
+    const float* row = master + src + ((long)(o0 + ol) * I + i0) * KK;
+    for (int j = lane; j < ni * KK; j += 32) s[ol * pitch + j] = j < nir * KK ? row[j] : 0.f;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < no * KK * ni; t += blockDim.x) {           // fwd[o][kk][i]
+    int il = t % ni, r = t / ni;
+    int kk = r % KK, ol = r / KK;
+    stf(fwd + fo + ((long)(o0 + ol) * KK + kk) * Ip + i0 + il, s[ol * pitch + il * KK + kk]);
+  }
+  for (int t = threadIdx.x; t < ni * KK * no; t += blockDim.x) {           // bwd[i][KK-1-kk][o]
+    int ol = t % no, r = t / no;
+    int kk = r % KK, il = r / KK;
+    stf(bwd + bo + ((long)(i0 + il) * KK + (KK - 1 - kk)) * O + o0 + ol, s[ol * pitch + il * KK + kk]);
   }
 }
 int ggi_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,

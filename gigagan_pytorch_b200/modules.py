@@ -320,8 +320,6 @@ class Generator(BaseGenerator):
                  cross_attn_ff_mult=4, num_conv_kernels=2, num_skip_layers_excite=0, unconditional=False,
                  pixel_shuffle_upsample=False):
         super().__init__()
-        assert unconditional and text_encoder is None, \
-            "this build covers the unconditional training path (text conditioning: SURVEY.md 8f item 2)"
         assert not pixel_shuffle_upsample, "pixel_shuffle_upsample is outside the hot path"
         self.channels = channels
         if isinstance(style_network, dict):
@@ -331,8 +329,14 @@ class Generator(BaseGenerator):
         if not exists(style_network_dim):
             style_network_dim = style_network.dim
         self.style_network_dim = style_network_dim
-        self.text_encoder = None
+        if isinstance(text_encoder, dict):
+            text_encoder = TextEncoder(**text_encoder)
+        self.text_encoder = text_encoder
         self.unconditional = unconditional
+        assert not (unconditional and exists(text_encoder))
+        assert not (unconditional and exists(style_network) and style_network.dim_text_latent > 0)
+        assert unconditional or (exists(text_encoder) and text_encoder.dim == style_network.dim_text_latent), \
+            "the `dim_text_latent` on your StyleNetwork must be equal to the `dim` set for the TextEncoder"
         assert is_power_of_two(image_size)
         num_layers = int(math.log2(image_size) - 1)
         self.num_layers = num_layers
@@ -363,12 +367,15 @@ class Generator(BaseGenerator):
             to_rgb = AdaptiveConv2DMod(dim_out, channels, 1, num_conv_kernels=1, demod=False)
             upsample = UpsampleParams(dim_in) if not is_first else None
             rgb_upsample = UpsampleParams(channels) if not is_last else None
-            self_attn = None
+            self_attn = cross_attn = None
             if resolution in self_attn_resolutions:
                 self_attn = SelfAttentionBlock(dim_out, dim_head=self_attn_dim_head, heads=self_attn_heads,
                                                ff_mult=self_attn_ff_mult, dot_product=self_attn_dot_product)
+            if resolution in cross_attn_resolutions and not unconditional:
+                cross_attn = CrossAttentionBlock(dim_out, dim_context=text_encoder.dim, dim_head=cross_attn_dim_head,
+                                                 heads=cross_attn_heads, ff_mult=cross_attn_ff_mult)
             split.extend([dim_in, dim_kernel_mod, dim_out, dim_kernel_mod, dim_out, 0])
-            self.layers.append(nn.ModuleList([se, resnet_block, to_rgb, self_attn, None, upsample, rgb_upsample]))
+            self.layers.append(nn.ModuleList([se, resnet_block, to_rgb, self_attn, cross_attn, upsample, rgb_upsample]))
 
         self.style_to_conv_modulations = nn.Linear(style_network_dim, sum(split))
         self.style_embed_split_dims = split
@@ -387,7 +394,20 @@ class Generator(BaseGenerator):
     def device(self):
         return next(self.parameters()).device
 
-    def forward_nhwc(self, styles=None, noise=None, batch_size=1, layer_noises=None):
+    def encode_text(self, texts=None, text_encodings=None, global_text_tokens=None, fine_text_tokens=None, text_mask=None):
+        """-> (global, fine, mask) or (None, None, None) for the unconditional generator (ref :1156-1170)."""
+        if self.unconditional:
+            assert not any(map(exists, (texts, text_encodings, global_text_tokens, fine_text_tokens)))
+            return None, None, None
+        if exists(texts) or exists(text_encodings):
+            assert exists(texts) ^ exists(text_encodings)
+            return self.text_encoder(texts=texts, text_encodings=text_encodings)
+        assert all(map(exists, (global_text_tokens, fine_text_tokens, text_mask))), \
+            "raw text or text embeddings were not passed in for conditional training"
+        return global_text_tokens, fine_text_tokens, text_mask
+
+    def forward_nhwc(self, styles=None, noise=None, batch_size=1, layer_noises=None, global_text_tokens=None,
+                     fine_text_tokens=None, text_mask=None):
         """-> (rgb NHWC, [rgbs NHWC]) in the compute dtype.  Per-layer noise images are drawn with torch.randn in
         the reference's order (ref :938) unless ``layer_noises`` supplies them."""
         dt = compute_dtype()
@@ -395,7 +415,7 @@ class Generator(BaseGenerator):
             assert exists(self.style_network)
             if not exists(noise):
                 noise = torch.randn((batch_size, self.style_network_dim), device=self.device)
-            styles = self.style_network(noise)
+            styles = self.style_network(noise, global_text_tokens)
         mods = ops.linear(styles.float(), self.style_to_conv_modulations.weight, self.style_to_conv_modulations.bias)
         mods = iter(mods.split(self.style_embed_split_dims, dim=-1))
         b = styles.shape[0]
@@ -411,7 +431,7 @@ class Generator(BaseGenerator):
                 return ln.pop(0)
             return torch.randn(t.shape[0], 1, t.shape[1], t.shape[2], device=t.device)
 
-        for se, (conv1, noise1, _, conv2, noise2, _), to_rgb, self_attn, _, upsample, upsample_rgb in self.layers:
+        for se, (conv1, noise1, _, conv2, noise2, _), to_rgb, self_attn, cross_attn, upsample, upsample_rgb in self.layers:
             if exists(upsample):
                 x = ops.upsample2x_blur(x)
             if exists(se):
@@ -425,6 +445,8 @@ class Generator(BaseGenerator):
             x = ops.NoiseActFn.apply(x, noise_img(x), noise2.weight)
             if exists(self_attn):
                 x = self_attn.forward_nhwc(x)
+            if exists(cross_attn):
+                x = cross_attn.forward_nhwc(x, fine_text_tokens, text_mask)
             layer_rgb = to_rgb.forward_nhwc(x, next(mods), next(mods), out_pad=img_cpad(self.channels))
             rgb = layer_rgb if rgb is None else ops.add(rgb, layer_rgb)
             rgbs.append(rgb)
@@ -435,8 +457,8 @@ class Generator(BaseGenerator):
 
     def forward(self, styles=None, noise=None, texts=None, text_encodings=None, global_text_tokens=None,
                 fine_text_tokens=None, text_mask=None, batch_size=1, return_all_rgbs=False):
-        assert not any(map(exists, (texts, text_encodings, global_text_tokens, fine_text_tokens)))
-        rgb, rgbs = self.forward_nhwc(styles, noise, batch_size)
+        g, f, tm = self.encode_text(texts, text_encodings, global_text_tokens, fine_text_tokens, text_mask)
+        rgb, rgbs = self.forward_nhwc(styles, noise, batch_size, None, g, f, tm)
         rgb = ops.to_nchw(rgb, self.channels)
         if return_all_rgbs:
             return rgb, [ops.to_nchw(t, self.channels) for t in rgbs]
@@ -510,22 +532,31 @@ class SimpleDecoder(nn.Module):
 class Predictor(nn.Module):
     def __init__(self, dim, depth=4, num_conv_kernels=2, unconditional=False):
         super().__init__()
-        assert unconditional, "text-conditioned predictors are outside this build (SURVEY.md 8f item 2)"
         self.unconditional = unconditional
         self.residual_fn = nn.Conv2d(dim, dim, 1)
         self.residual_scale = 2 ** -0.5
         self.layers = nn.ModuleList([])
         for _ in range(depth):
-            self.layers.append(nn.ModuleList([nn.Conv2d(dim, dim, 3, padding=1), nn.LeakyReLU(0.2),
-                                              nn.Conv2d(dim, dim, 3, padding=1), nn.LeakyReLU(0.2)]))
+            if unconditional:
+                c1, c2 = nn.Conv2d(dim, dim, 3, padding=1), nn.Conv2d(dim, dim, 3, padding=1)
+                self.layers.append(nn.ModuleList([c1, nn.LeakyReLU(0.2), c2, nn.LeakyReLU(0.2)]))
+            else:      # text-conditioned: per-sample modulated filters (ref :1459)
+                c1 = AdaptiveConv2DMod(dim, dim, 3, num_conv_kernels=num_conv_kernels)
+                l1 = nn.LeakyReLU(0.2)
+                c2 = AdaptiveConv2DMod(dim, dim, 3, num_conv_kernels=num_conv_kernels)
+                self.layers.append(nn.ModuleList([c1, l1, c2, nn.LeakyReLU(0.2)]))
         self.to_logits = nn.Conv2d(dim, 1, 1)
 
-    def forward_nhwc(self, x):
+    def forward_nhwc(self, x, mod=None, kernel_mod=None):
         residual = ops.conv2d(x, self.residual_fn.weight, self.residual_fn.bias)
         for conv1, _, conv2, _ in self.layers:
             inner = x
-            x = ops.conv2d(x, conv1.weight, conv1.bias, pad=1, act=1)
-            x = ops.conv2d(x, conv2.weight, conv2.bias, pad=1, act=1)
+            if self.unconditional:
+                x = ops.conv2d(x, conv1.weight, conv1.bias, pad=1, act=1)
+                x = ops.conv2d(x, conv2.weight, conv2.bias, pad=1, act=1)
+            else:
+                x = ops.leaky_relu(conv1.forward_nhwc(x, mod, kernel_mod))
+                x = ops.leaky_relu(conv2.forward_nhwc(x, mod, kernel_mod))
             x = ops.axpby(self.residual_scale, x, self.residual_scale, inner)
         x = ops.add(x, residual)
         n, h, w, c = x.shape
@@ -548,10 +579,9 @@ class Discriminator(nn.Module):
                  aux_recon_fmap_dropout: float = 0.5, resize_mode="bilinear", num_conv_kernels=2,
                  num_skip_layers_excite=0, unconditional=False, predictor_depth=2):
         super().__init__()
-        assert unconditional and text_encoder is None, \
-            "this build covers the unconditional training path (text conditioning: SURVEY.md 8f item 2)"
         assert resize_mode == "bilinear"
         self.unconditional = unconditional
+        assert not (unconditional and exists(text_encoder))
         self.channels = channels
         assert is_power_of_two(image_size)
         if filter_input_resolutions:
@@ -577,6 +607,8 @@ class Discriminator(nn.Module):
         self.residual_scale = 2 ** -0.5
         self.layers = nn.ModuleList([])
         upsample_dims = []
+        predictor_dims = []
+        dim_kernel_attn = num_conv_kernels if num_conv_kernels > 1 else 0
         for ind, ((dim_in, dim_out), resolution) in enumerate(zip(dim_pairs, resolutions)):
             is_first, is_last = ind == 0, (ind + 1) == len(dim_pairs)
             should_downsample = not is_last
@@ -591,6 +623,7 @@ class Discriminator(nn.Module):
             predictor = None
             if resolution in ms_out:
                 predictor = Predictor(dim_out, num_conv_kernels=num_conv_kernels, depth=2, unconditional=unconditional)
+                predictor_dims.extend([dim_out, dim_kernel_attn])
             decoder = None
             if resolution in aux_recon_resolutions:
                 patch_dim, frac = self.aux_recon_resolutions_to_patches[resolution]
@@ -604,7 +637,14 @@ class Discriminator(nn.Module):
                                               DownsampleParams(dim_out) if should_downsample else None]))
         self.to_logits = nn.Sequential(nn.Conv2d(dim_last, dim_last, 3, padding=1), nn.Identity(),
                                        nn.Linear(dim_last * (4 ** 2), 1), nn.Identity())
-        self.text_encoder = None
+        assert unconditional or (exists(text_dim) ^ exists(text_encoder))
+        if not unconditional:
+            if isinstance(text_encoder, dict):
+                text_encoder = TextEncoder(**text_encoder)
+            self.text_dim = text_dim if exists(text_dim) else text_encoder.dim
+            self.predictor_dims = predictor_dims
+            self.text_to_conv_conditioning = nn.Linear(self.text_dim, sum(predictor_dims))
+        self.text_encoder = text_encoder
         self.apply(self.init_)
 
     def init_(self, m):
@@ -630,8 +670,19 @@ class Discriminator(nn.Module):
     def real_images_to_rgbs_nhwc(self, images_nhwc):
         return [ops.resize_bilinear(images_nhwc, r) for r in self.multiscale_input_resolutions]
 
+    def encode_text(self, texts=None, text_encodings=None, text_embeds=None):
+        """-> text_embeds (b, text_dim) for the predictors, None when unconditional (ref :1709-1726)."""
+        if self.unconditional:
+            assert not any(map(exists, (texts, text_embeds)))
+            return None
+        assert (exists(texts) ^ exists(text_encodings)) ^ exists(text_embeds)
+        if exists(texts) or exists(text_encodings):
+            assert exists(self.text_encoder)
+            text_embeds, *_ = self.text_encoder(texts=texts, text_encodings=text_encodings)
+        return text_embeds
+
     def forward_nhwc(self, images, rgbs: List[torch.Tensor], return_multiscale_outputs=True, calc_aux_loss=True,
-                     fused_attention=None):
+                     fused_attention=None, text_embeds=None):
         """images (B,S,S,C) NHWC compute dtype; rgbs: NHWC maps.  -> (logits (s,B) fp32, [ms logits NHWC], [aux])."""
         x = images
         batch = x.shape[0]
@@ -640,6 +691,11 @@ class Discriminator(nn.Module):
         missing = set(self.multiscale_input_resolutions) - set(by_res.keys())
         assert not missing, f"rgbs of necessary resolution {self.multiscale_input_resolutions} were not passed in"
         ms_outputs, aux_losses = [], []
+        conv_mods = None
+        if not self.unconditional:
+            assert exists(text_embeds), "text embeddings were not passed into the discriminator"
+            cm = ops.linear(text_embeds.float(), self.text_to_conv_conditioning.weight, self.text_to_conv_conditioning.bias)
+            conv_mods = iter(cm.split(self.predictor_dims, dim=-1))
         excitations = [None] * (self.num_skip_layers_excite + 1)
         for se, from_rgb, block, residual_fn, attn, predictor, decoder, downsample in self.layers:
             resolution = x.shape[2]
@@ -661,8 +717,10 @@ class Discriminator(nn.Module):
             x = ops.conv2d(x, block[2].weight, block[2].bias, pad=1, act=1)
             if exists(attn):
                 x = attn.forward_nhwc(x, fused=fused_attention)
-            if exists(predictor) and return_multiscale_outputs:
-                ms_outputs.append(predictor.forward_nhwc(x[:prev]))
+            if exists(predictor):
+                pk = dict(mod=next(conv_mods), kernel_mod=next(conv_mods)) if exists(conv_mods) else {}
+                if return_multiscale_outputs:
+                    ms_outputs.append(predictor.forward_nhwc(x[:prev], **pk))
             if exists(downsample):     # pixel-unshuffle + 1x1 == 2x2 stride-2 conv (ref :289-293)
                 w = downsample[1].weight
                 w2 = w.view(w.shape[0], w.shape[1] // 4, 2, 2)
@@ -682,11 +740,11 @@ class Discriminator(nn.Module):
 
     def forward(self, images, rgbs: List[torch.Tensor], texts=None, text_encodings=None, text_embeds=None,
                 real_images=None, return_multiscale_outputs=True, calc_aux_loss=True):
-        assert not any(map(exists, (texts, text_encodings, text_embeds)))
+        te = self.encode_text(texts, text_encodings, text_embeds)
         dt = compute_dtype()
         x = ops.to_nhwc(images, img_cpad(self.channels), dt)
         r = [ops.to_nhwc(t, img_cpad(self.channels), dt) for t in rgbs]
-        logits, ms, aux = self.forward_nhwc(x, r, return_multiscale_outputs, calc_aux_loss)
+        logits, ms, aux = self.forward_nhwc(x, r, return_multiscale_outputs, calc_aux_loss, text_embeds=te)
         return logits, [ops.to_nchw(m, 1) for m in ms], aux
 
 
@@ -1011,3 +1069,159 @@ class UnetUpsampler(BaseGenerator):
         if not return_all_rgbs:
             return rgb
         return rgb, [ops.to_nchw(t, self.channels) for t in rgbs]
+
+
+# ============================================================================= text conditioning (ref :234-242, :596-867)
+NEG_MASK = -1e30          # additive logit for masked / padded keys (the reference fills -finfo.max; both give p = 0)
+
+
+class RMSNorm(nn.Module):
+    """last-axis RMSNorm for token sequences (ref :234-242); fp32 rows."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.scale = dim ** 0.5
+        self.gamma = nn.Parameter(torch.ones(dim))
+
+    def forward_rows(self, x2d):
+        inv = ops.unary(U_INVNORM, ops.rowdot(x2d, x2d))
+        g = ops.axpby(self.scale, self.gamma.reshape(1, -1))
+        return ops.scale_channels(ops.scale_rows(x2d, inv), g, x2d.shape[0], 1)
+
+
+def _masked_attention(q, k, v, bias, heads, scale, rows_per_sample_factor=1):
+    """q (b,nq,h*d), k/v (b,L,h*d) same dtype, bias fp32 (b,L) added to every query row of sample b -> (b,nq,h*d).
+    Composed from the closed primitives (works for fp32 token sequences and bf16 feature maps alike)."""
+    b, nq, hd = q.shape
+    L, d = k.shape[1], hd // heads
+    q4 = q.reshape(b, nq, heads, d).permute(0, 2, 1, 3)
+    kt = k.reshape(b, L, heads, d).permute(0, 2, 3, 1)
+    v4 = v.reshape(b, L, heads, d).permute(0, 2, 1, 3)
+    s = ops.bmm(q4, kt, alpha=scale)                                   # (b,h,nq,L)
+    p = ops.softmax(s, bias, heads * nq, b) if bias is not None else ops.softmax(s)
+    o = ops.bmm(p, v4, out_bmhn=True)                                  # physical (b,nq,h,d)
+    return o.permute(0, 2, 1, 3).reshape(b, nq, hd)
+
+
+class TextAttention(nn.Module):
+    def __init__(self, dim, dim_head=64, heads=8):
+        super().__init__()
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        inner = dim_head * heads
+        self.norm = RMSNorm(dim)
+        self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
+        self.null_kv = nn.Parameter(torch.randn(2, heads, dim_head))
+        self.to_out = nn.Linear(inner, dim, bias=False)
+
+    def forward_tokens(self, x, mask=None):
+        b, n, dim = x.shape
+        inner = self.heads * self.dim_head
+        qkv = ops.linear(self.norm.forward_rows(x.reshape(b * n, dim)), self.to_qkv.weight).view(b, n, 3 * inner)
+        q, k, v = (qkv[..., i * inner:(i + 1) * inner] for i in range(3))
+        nk = self.null_kv[0].reshape(1, 1, inner).expand(b, 1, inner)
+        nv = self.null_kv[1].reshape(1, 1, inner).expand(b, 1, inner)
+        k, v = torch.cat((nk, k), dim=1), torch.cat((nv, v), dim=1)
+        bias = None
+        if exists(mask):
+            m = F.pad(mask, (1, 0), value=True)
+            bias = torch.zeros(m.shape, dtype=torch.float32, device=x.device).masked_fill_(~m, NEG_MASK)
+        o = _masked_attention(q.contiguous(), k, v, bias, self.heads, self.scale)
+        return ops.linear(o.reshape(b * n, inner), self.to_out.weight).view(b, n, dim)
+
+
+def TokenFeedForward(dim, mult=4):
+    return nn.Sequential(RMSNorm(dim), nn.Linear(dim, int(dim * mult)), nn.GELU(), nn.Linear(int(dim * mult), dim))
+
+
+class Transformer(nn.Module):
+    def __init__(self, dim, depth, dim_head=64, heads=8, ff_mult=4):
+        super().__init__()
+        self.layers = nn.ModuleList([])
+        for _ in range(depth):
+            self.layers.append(nn.ModuleList([TextAttention(dim=dim, dim_head=dim_head, heads=heads),
+                                              TokenFeedForward(dim=dim, mult=ff_mult)]))
+        self.norm = RMSNorm(dim)
+
+    def forward_tokens(self, x, mask=None):
+        b, n, dim = x.shape
+        for attn, ff in self.layers:
+            x = ops.add(attn.forward_tokens(x, mask), x)
+            h = ops.linear(ff[0].forward_rows(x.reshape(b * n, dim)), ff[1].weight, ff[1].bias)
+            h = ops.linear(ops.unary(U_GELU, h), ff[3].weight, ff[3].bias).view(b, n, dim)
+            x = ops.add(h, x)
+        return self.norm.forward_rows(x.reshape(b * n, dim)).view(b, n, dim)
+
+
+class TextEncoder(nn.Module):
+    """Learned transformer over CLIP token encodings (ref :808-867).  The frozen OpenCLIP tower is third-party with
+    weights that are not available offline: pass pre-encoded ``text_encodings`` (b, n, clip_dim_latent); zeros mark
+    padding exactly as in the reference (mask = (encodings != 0).any(-1))."""
+
+    def __init__(self, *, dim, depth, clip=None, dim_head=64, heads=8, clip_dim_latent=512):
+        super().__init__()
+        self.dim = dim
+        self.clip = clip
+        dim_latent = clip.dim_latent if exists(clip) else clip_dim_latent
+        self.learned_global_token = nn.Parameter(torch.randn(dim))
+        self.project_in = nn.Linear(dim_latent, dim) if dim_latent != dim else nn.Identity()
+        self.transformer = Transformer(dim=dim, depth=depth, dim_head=dim_head, heads=heads)
+
+    def forward(self, texts=None, text_encodings=None):
+        assert exists(texts) ^ exists(text_encodings)
+        if not exists(text_encodings):
+            assert exists(self.clip), "raw texts need an OpenClipAdapter (not available offline); pass text_encodings"
+            with torch.no_grad():
+                _, text_encodings = self.clip.embed_texts(texts)
+        enc = text_encodings.float()
+        mask = (enc != 0.).any(dim=-1)
+        b, n, _ = enc.shape
+        x = enc
+        if not isinstance(self.project_in, nn.Identity):
+            x = ops.linear(enc.reshape(b * n, -1), self.project_in.weight, self.project_in.bias).view(b, n, self.dim)
+        g = self.learned_global_token.reshape(1, 1, -1).expand(b, 1, self.dim)
+        x = torch.cat((g, x), dim=1)
+        x = self.transformer.forward_tokens(x, F.pad(mask, (1, 0), value=True))
+        return x[:, 0], x[:, 1:], mask
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, dim, dim_context, dim_head=64, heads=8):
+        super().__init__()
+        self.heads, self.dim_head, self.scale = heads, dim_head, dim_head ** -0.5
+        inner = dim_head * heads
+        kv_in = dim_context if exists(dim_context) else dim
+        self.norm = ChannelRMSNorm(dim)
+        self.norm_context = RMSNorm(kv_in)
+        self.to_q = nn.Conv2d(dim, inner, 1, bias=False)
+        self.to_kv = nn.Linear(kv_in, inner * 2, bias=False)
+        self.to_out = nn.Conv2d(inner, dim, 1, bias=False)
+
+    def forward_nhwc(self, x, context, mask=None, residual=None):
+        b, hh, ww, _ = x.shape
+        inner = self.heads * self.dim_head
+        nctx = context.shape[1]
+        q = ops.conv2d(self.norm.forward_nhwc(x), self.to_q.weight).view(b, hh * ww, inner)
+        ctx = self.norm_context.forward_rows(context.float().reshape(b * nctx, -1))
+        kv = ops.linear(ctx, self.to_kv.weight).view(b, nctx, 2 * inner).to(x.dtype)
+        lp = (nctx + 15) // 16 * 16                       # key axis padded to 16 tokens (aligned rows for the TMA GEMMs)
+        if lp > nctx:
+            kv = torch.cat((kv, torch.zeros((b, lp - nctx, 2 * inner), dtype=kv.dtype, device=kv.device)), dim=1)
+        k, v = kv[..., :inner].contiguous(), kv[..., inner:].contiguous()
+        bias = torch.zeros((b, lp), dtype=torch.float32, device=x.device)
+        if exists(mask):
+            bias[:, :nctx].masked_fill_(~mask, NEG_MASK)
+        bias[:, nctx:] = NEG_MASK
+        o = _masked_attention(q, k, v, bias, self.heads, self.scale)
+        return ops.conv2d(o.view(b, hh, ww, inner), self.to_out.weight, res=residual)
+
+
+class CrossAttentionBlock(nn.Module):
+    def __init__(self, dim, dim_context, dim_head=64, heads=8, ff_mult=4):
+        super().__init__()
+        self.attn = CrossAttention(dim=dim, dim_context=dim_context, dim_head=dim_head, heads=heads)
+        self.ff = FeedForwardParams(dim, ff_mult)
+
+    def forward_nhwc(self, x, context, mask=None):
+        x = self.attn.forward_nhwc(x, context, mask, residual=x)
+        h = ops.conv2d(self.ff[0].forward_nhwc(x), self.ff[1].weight, self.ff[1].bias)
+        return ops.conv2d(ops.unary(U_GELU, h), self.ff[3].weight, self.ff[3].bias, res=x)

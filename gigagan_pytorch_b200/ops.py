@@ -75,8 +75,6 @@ class WeightBank:
     """Both kernel layouts of every 4-D conv weight (and every filter of the 5-D AdaptiveConv banks) of a module
     whose parameters live in one flat fp32 buffer, refreshed by ONE kernel launch per optimiser step."""
 
-    CHUNK = 1 << 14
-
     def __init__(self, flat, params, dtype, cin_pad):
         dev = flat.device
         self.flat, self.dtype = flat, dtype
@@ -91,8 +89,10 @@ class WeightBank:
             n = O * KH * KW * ipad
             eid = len(entries)
             entries.append([(ptr - base) // 4, O, I, KH * KW, ipad, fo, bo, 0])
-            for s in range(0, n, self.CHUNK):
-                chunks.append([eid, s, min(self.CHUNK, n - s), 0])
+            ti = max(1, min(32, 380 // (KH * KW)))      # (32 o) x (ti i) x taps tile per block, <= 380 floats per row
+            for o0 in range(0, O, 32):
+                for i0 in range(0, ipad, ti):
+                    chunks.append([eid, o0, i0, ti])
             self.views[(ptr, (O, I, KH, KW), ipad)] = (fo, (O, KH, KW, ipad), bo, (ipad, KH, KW, O))
             fo += (n + 7) // 8 * 8
             bo += (n + 7) // 8 * 8

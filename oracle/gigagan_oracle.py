@@ -35,7 +35,8 @@ SD = Dict[str, Tensor]
 
 def generator_plan(image_size: int, dim_capacity: int = 16, dim_max: int = 2048, dim_latent: int = 512,
                    num_skip_layers_excite: int = 0, self_attn_resolutions=(32, 16), num_conv_kernels: int = 2,
-                   self_attn_heads: int = 8, self_attn_dim_head: int = 64):
+                   self_attn_heads: int = 8, self_attn_dim_head: int = 64, unconditional: bool = True,
+                   cross_attn_resolutions=(32, 16), cross_attn_heads: int = 8, cross_attn_dim_head: int = 64):
     n = int(math.log2(image_size)) - 1
     res = [image_size // (2 ** (n - 1 - i)) for i in range(n)]
     dims = [min((2 ** (i + 1)) * dim_capacity, dim_max) for i in range(n)][::-1]
@@ -48,9 +49,11 @@ def generator_plan(image_size: int, dim_capacity: int = 16, dim_max: int = 2048,
         split += [ci, kmod, co, kmod, co, 0]
         layers.append(dict(index=i, dim_in=ci, dim_out=co, resolution=r, upsample=i > 0, upsample_rgb=i + 1 < n,
                            squeeze_excite=num_skip_layers_excite > 0 and i + num_skip_layers_excite < n,
-                           self_attn=r in self_attn_resolutions))
+                           self_attn=r in self_attn_resolutions,
+                           cross_attn=(r in cross_attn_resolutions) and not unconditional))
     return dict(layers=layers, split=split, num_skip_layers_excite=num_skip_layers_excite, dim_latent=dim_latent,
-                heads=self_attn_heads, dim_head=self_attn_dim_head)
+                heads=self_attn_heads, dim_head=self_attn_dim_head, cross_heads=cross_attn_heads,
+                cross_dim_head=cross_attn_dim_head)
 
 
 def discriminator_plan(image_size: int, dim_capacity: int = 16, dim_max: int = 2048, channels: int = 3,
@@ -142,9 +145,11 @@ def adaptive_conv2d_mod(weights: Tensor, fmap: Tensor, mod: Tensor, kernel_mod: 
     return y.reshape(b, o, *y.shape[2:])
 
 
-def style_network(sd: SD, z: Tensor, depth: int, lr_mul: float = 0.1) -> Tensor:
+def style_network(sd: SD, z: Tensor, depth: int, lr_mul: float = 0.1, text_latent: Optional[Tensor] = None) -> Tensor:
     # ref: gigagan_pytorch.py:871-887 EqualLinear, :910-921 StyleNetwork.forward
     x = z / z.pow(2).sum(dim=1, keepdim=True).sqrt().clamp(min=1e-12)
+    if text_latent is not None:                                    # ref :917-919
+        x = torch.cat((x, text_latent), dim=-1)
     for d in range(depth):
         x = leaky(F.linear(x, sd[f"net.{2 * d}.weight"] * lr_mul, sd[f"net.{2 * d}.bias"] * lr_mul))
     return x
@@ -192,11 +197,12 @@ def self_attention_block(sd: SD, x: Tensor, dot_product: bool, heads: int = 8, d
 
 def generator_forward(sd: SD, plan: dict, noise: Tensor, style_depth: int = 4,
                       layer_noises: Optional[Sequence[Tensor]] = None, return_all_rgbs: bool = False,
-                      self_attn_dot_product: bool = True):
+                      self_attn_dot_product: bool = True, global_text_tokens: Optional[Tensor] = None,
+                      fine_text_tokens: Optional[Tensor] = None, text_mask: Optional[Tensor] = None):
     """``layer_noises``: the 2*num_layers per-layer noise images (b,1,h,w); when None they are drawn with
     torch.randn in the reference's order (ref :938) so that a shared manual_seed reproduces the reference."""
     b = noise.shape[0]
-    styles = style_network(_sub(sd, "style_network."), noise, style_depth)
+    styles = style_network(_sub(sd, "style_network."), noise, style_depth, text_latent=global_text_tokens)
     mods = F.linear(styles, sd["style_to_conv_modulations.weight"], sd["style_to_conv_modulations.bias"])
     mods = list(mods.split(plan["split"], dim=-1))                 # ref :1184-1186
 
@@ -230,6 +236,9 @@ def generator_forward(sd: SD, plan: dict, noise: Tensor, style_depth: int = 4,
         x = leaky(x + sd[p + "1.4.weight"][None] * noise_img(x))
         if L["self_attn"]:
             x = self_attention_block(_sub(sd, p + "3."), x, self_attn_dot_product, plan["heads"], plan["dim_head"])
+        if L.get("cross_attn"):                                    # ref :1231-1232
+            x = cross_attention_block(_sub(sd, p + "4."), x, fine_text_tokens, text_mask, plan["cross_heads"],
+                                      plan["cross_dim_head"])
         rgb = rgb + adaptive_conv2d_mod(sd[p + "2.weights"], x, nxt(), nxt(), demod=False)   # ref :1234-1236
         rgbs.append(rgb)
         if L["upsample_rgb"]:
@@ -299,7 +308,17 @@ def real_images_to_rgbs(images: Tensor, plan: dict) -> List[Tensor]:
 
 def discriminator_forward(sd: SD, plan: dict, images: Tensor, rgbs: Sequence[Tensor],
                           return_multiscale_outputs: bool = True, calc_aux_loss: bool = True,
-                          training: bool = True, recon_dropout_mask=None, recon_patch_indices=None):
+                          training: bool = True, recon_dropout_mask=None, recon_patch_indices=None,
+                          text_embeds: Optional[Tensor] = None, num_conv_kernels: int = 2):
+    """``text_embeds`` (b, text_dim): global text tokens for the text-conditioned predictors (ref :1709-1723)."""
+    conv_mods = None
+    if text_embeds is not None:
+        dims = []
+        for L in plan["layers"]:
+            if L["predictor"]:
+                dims.extend([L["dim_out"], num_conv_kernels if num_conv_kernels > 1 else 0])
+        conv_mods = list(F.linear(text_embeds, sd["text_to_conv_conditioning.weight"],
+                                  sd["text_to_conv_conditioning.bias"]).split(dims, dim=-1))
     x = images
     batch = x.shape[0]
     by_res = {t.shape[-1]: t for t in rgbs}
@@ -323,8 +342,13 @@ def discriminator_forward(sd: SD, plan: dict, images: Tensor, rgbs: Sequence[Ten
         x = leaky(F.conv2d(x, sd[p + "2.2.weight"], sd[p + "2.2.bias"], padding=1))
         if L["attn"]:
             x = self_attention_block(_sub(sd, p + "4."), x, False, plan["heads"], plan["dim_head"])
-        if L["predictor"] and return_multiscale_outputs:
-            ms_out.append(predictor(_sub(sd, p + "5."), x[:prev]))         # ref :1803-1804
+        if L["predictor"]:
+            if conv_mods is not None:
+                mod, kmod = conv_mods.pop(0), conv_mods.pop(0)             # ref :1799-1800 (consumed even if unused)
+                if return_multiscale_outputs:
+                    ms_out.append(predictor_conditional(_sub(sd, p + "5."), x[:prev], mod, kmod))
+            elif return_multiscale_outputs:
+                ms_out.append(predictor(_sub(sd, p + "5."), x[:prev]))     # ref :1803-1804
         if L["downsample"]:                                                # ref :289-293 pixel-unshuffle + 1x1
             x = F.conv2d(F.pixel_unshuffle(x, 2), sd[p + "7.1.weight"], sd[p + "7.1.bias"])
         x = (x + residual) * (2 ** -0.5)                                   # ref :1809-1810
@@ -602,3 +626,100 @@ def unet_forward(sd: SD, plan: dict, lowres: Tensor, noise: Tensor, style_depth:
     if not return_all_rgbs:
         return rgb
     return rgb, [lowres] + [t for t in rgbs if t.shape[-1] > lowres.shape[-1]]
+
+
+# --------------------------------------------------------------------------- #
+# text conditioning (ref: gigagan_pytorch.py:234-242 RMSNorm, :596-722 attention, :780-867 Transformer/TextEncoder)
+# on pre-encoded CLIP token sequences (`text_encodings`); the CLIP tower itself is third-party and absent here
+# --------------------------------------------------------------------------- #
+
+def rmsnorm_last(x, gamma):
+    # ref :234-242
+    d = x.shape[-1]
+    return x / x.pow(2).sum(dim=-1, keepdim=True).sqrt().clamp(min=1e-12) * (d ** 0.5) * gamma
+
+
+def _heads(t, h):      # 'b n (h d) -> (b h) n d'
+    b, n, hd = t.shape
+    return t.reshape(b, n, h, hd // h).permute(0, 2, 1, 3).reshape(b * h, n, hd // h)
+
+
+def text_attention(sd, x, mask, heads, dim_head):
+    # ref :678-722 (dot product, null key/value, key padding mask)
+    b, n, _ = x.shape
+    xn = rmsnorm_last(x, sd["norm.gamma"])
+    q, k, v = F.linear(xn, sd["to_qkv.weight"]).chunk(3, dim=-1)
+    q, k, v = _heads(q, heads), _heads(k, heads), _heads(v, heads)
+    nk = sd["null_kv"][0][None].expand(b, heads, dim_head).reshape(b * heads, 1, dim_head)
+    nv = sd["null_kv"][1][None].expand(b, heads, dim_head).reshape(b * heads, 1, dim_head)
+    k, v = torch.cat((nk, k), dim=1), torch.cat((nv, v), dim=1)
+    sim = (q @ k.transpose(1, 2)) * dim_head ** -0.5
+    if mask is not None:
+        m = F.pad(mask, (1, 0), value=True)
+        m = m[:, None, None, :].expand(b, heads, 1, n + 1).reshape(b * heads, 1, n + 1)
+        sim = sim.masked_fill(~m, -torch.finfo(sim.dtype).max)
+    out = sim.softmax(dim=-1) @ v
+    out = out.reshape(b, heads, n, dim_head).permute(0, 2, 1, 3).reshape(b, n, heads * dim_head)
+    return F.linear(out, sd["to_out.weight"])
+
+
+def text_transformer(sd, x, mask, depth, heads, dim_head):
+    # ref :780-803
+    for d in range(depth):
+        x = text_attention(_sub(sd, f"layers.{d}.0."), x, mask, heads, dim_head) + x
+        f = _sub(sd, f"layers.{d}.1.")
+        h = rmsnorm_last(x, f["0.gamma"])
+        x = F.linear(F.gelu(F.linear(h, f["1.weight"], f["1.bias"])), f["3.weight"], f["3.bias"]) + x
+    return rmsnorm_last(x, sd["norm.gamma"])
+
+
+def text_encoder(sd, text_encodings, depth, heads=8, dim_head=64):
+    # ref :842-867 with text_encodings given -> (global tokens (b,d), fine tokens (b,n,d), mask (b,n))
+    mask = (text_encodings != 0.).any(dim=-1)
+    x = text_encodings
+    if "project_in.weight" in sd:
+        x = F.linear(x, sd["project_in.weight"], sd["project_in.bias"])
+    b = x.shape[0]
+    g = sd["learned_global_token"][None, None].expand(b, 1, -1)
+    x = torch.cat((g, x), dim=1)
+    x = text_transformer(_sub(sd, "transformer."), x, F.pad(mask, (1, 0), value=True), depth, heads, dim_head)
+    return x[:, 0], x[:, 1:], mask
+
+
+def cross_attention(sd, fmap, context, mask, heads=8, dim_head=64):
+    # ref :617-655
+    b, _, hh, ww = fmap.shape
+    x = channel_rmsnorm(fmap, sd["norm.gamma"])
+    ctx = rmsnorm_last(context, sd["norm_context.gamma"])
+    q = F.conv2d(x, sd["to_q.weight"])
+    k, v = F.linear(ctx, sd["to_kv.weight"]).chunk(2, dim=-1)
+    k, v = _heads(k, heads), _heads(v, heads)
+    q = q.reshape(b, heads, dim_head, hh * ww).permute(0, 1, 3, 2).reshape(b * heads, hh * ww, dim_head)
+    sim = (q @ k.transpose(1, 2)) * dim_head ** -0.5
+    if mask is not None:
+        n = mask.shape[-1]
+        m = mask[:, None, None, :].expand(b, heads, 1, n).reshape(b * heads, 1, n)
+        sim = sim.masked_fill(~m, -torch.finfo(sim.dtype).max)
+    out = sim.softmax(dim=-1) @ v
+    out = out.reshape(b, heads, hh * ww, dim_head).permute(0, 1, 3, 2).reshape(b, heads * dim_head, hh, ww)
+    return F.conv2d(out, sd["to_out.weight"])
+
+
+def cross_attention_block(sd, x, context, mask, heads=8, dim_head=64):
+    # ref :762-778
+    x = cross_attention(_sub(sd, "attn."), x, context, mask, heads, dim_head) + x
+    h = channel_rmsnorm(x, sd["ff.0.gamma"])
+    h = F.conv2d(F.gelu(F.conv2d(h, sd["ff.1.weight"], sd["ff.1.bias"])), sd["ff.3.weight"], sd["ff.3.bias"])
+    return h + x
+
+
+def predictor_conditional(sd, x, mod, kernel_mod, depth=2):
+    # ref :1472-1498 with AdaptiveConv2DMod layers (text-conditioned discriminator)
+    residual = F.conv2d(x, sd["residual_fn.weight"], sd["residual_fn.bias"])
+    for d in range(depth):
+        inner = x
+        x = leaky(adaptive_conv2d_mod(sd[f"layers.{d}.0.weights"], x, mod, kernel_mod))
+        x = leaky(adaptive_conv2d_mod(sd[f"layers.{d}.2.weights"], x, mod, kernel_mod))
+        x = (x + inner) * (2 ** -0.5)
+    x = x + residual
+    return F.conv2d(x, sd["to_logits.weight"], sd["to_logits.bias"])

@@ -111,6 +111,46 @@ def main():
     torch.save(dict(cfg=ucfg, sd=sd_of(U), low=low, z=z, rgb=rgb.detach(), rgbs=[t.detach() for t in rgbs],
                     grads={k: p.grad.clone() for k, p in U.named_parameters() if p.grad is not None}),
                os.path.join(OUT, "ka6_unet_upsampler.pt"))
+    # ---- KA7: text-conditioned generator + discriminator (TextEncoder on given CLIP-style encodings; the
+    #      CLIP tower itself is a third-party dependency outside the path, so text_encodings are the boundary)
+    from gigagan_pytorch.gigagan_pytorch import TextEncoder as RefTextEncoder
+    from gigagan_pytorch.open_clip import OpenClipAdapter
+
+    class _NoClip(OpenClipAdapter):                       # only .dim_latent is consulted when encodings are given
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+
+        @property
+        def dim_latent(self):
+            return 32
+
+    tecfg = dict(dim=24, depth=1, dim_head=8, heads=2)
+    gcfg7 = dict(dim_capacity=2, style_network=dict(dim=16, depth=2, dim_text_latent=24), image_size=32, dim_max=16,
+                 dim_latent=16, num_skip_layers_excite=2, self_attn_resolutions=(16,), self_attn_dim_head=8,
+                 self_attn_heads=2, cross_attn_resolutions=(16, 8), cross_attn_dim_head=8, cross_attn_heads=2,
+                 unconditional=False)
+    dcfg7 = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, attn_resolutions=(8,),
+                 attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8), unconditional=False)
+    torch.manual_seed(0)
+    G7 = ref.Generator(text_encoder=RefTextEncoder(clip=_NoClip(), **tecfg), **gcfg7)
+    torch.manual_seed(1)
+    D7 = ref.Discriminator(text_encoder=RefTextEncoder(clip=_NoClip(), **tecfg), **dcfg7)
+    enc = rn(5, 2, 6, 32)
+    enc[1, 4:] = 0.                                        # padded tokens -> mask False (ref :851)
+    z = rn(1, 2, 16)
+    torch.manual_seed(2)
+    rgb, rgbs = G7(noise=z, text_encodings=enc, return_all_rgbs=True)
+    (rgb ** 2).mean().backward()
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    real_rgbs = D7.real_images_to_rgbs(img)
+    logits, ms, _ = D7(img, real_rgbs, text_encodings=enc, return_multiscale_outputs=True, calc_aux_loss=False)
+    (logits.sum() + sum((m_ ** 2).sum() for m_ in ms)).backward()
+    torch.save(dict(te_cfg=dict(clip_dim_latent=32, **tecfg), gcfg=gcfg7, dcfg=dcfg7, gsd=sd_of(G7), dsd=sd_of(D7),
+                    enc=enc, z=z, noise_seed=2, rgb=rgb.detach(), rgbs=[t.detach() for t in rgbs], img=img,
+                    logits=logits.detach(), ms=[t.detach() for t in ms],
+                    ggrads={k: p.grad.clone() for k, p in G7.named_parameters() if p.grad is not None},
+                    dgrads={k: p.grad.clone() for k, p in D7.named_parameters() if p.grad is not None}),
+               os.path.join(OUT, "ka7_text_conditional.pt"))
     for f_ in sorted(os.listdir(OUT)):
         print(f_, os.path.getsize(os.path.join(OUT, f_)))
 

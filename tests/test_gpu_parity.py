@@ -545,3 +545,70 @@ def test_trainer_steps_run_and_cuda_graph_replay_matches_eager(upsampler, amp):
         assert torch.isfinite(res[-1]).all()
     # identical RNG streams are not guaranteed between eager and captured randn; require the same scale of update
     assert (res[0] - res[1]).abs().max().item() < 0.05
+
+
+# ------------------------------------------------------------------ text-conditioned path
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 5e-2)])
+def test_ka7_text_conditional(dtype, tol):
+    """TextEncoder + cross attention in G, text-modulated predictors in D, against the reference's outputs and grads"""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    fx = load("ka7_text_conditional.pt")
+    g.set_compute_dtype(dtype)
+    G = g.Generator(text_encoder=g.TextEncoder(**fx["te_cfg"]), **fx["gcfg"]).to(dev())
+    G.load_state_dict(fx["gsd"])
+    enc = fx["enc"].to(dev())
+    gt, ft, tm = G.encode_text(text_encodings=enc)
+    assert tm.tolist() == [[True] * 6, [True] * 4 + [False] * 2]
+    torch.manual_seed(fx["noise_seed"])
+    noises = []
+    for r in [4, 8, 16, 32]:
+        for _ in range(2):
+            noises.append(torch.randn(2, 1, r, r).to(dev()))
+    rgb, rgbs = G.forward_nhwc(noise=fx["z"].to(dev()), layer_noises=noises, global_text_tokens=gt,
+                               fine_text_tokens=ft, text_mask=tm)
+    out = ops.to_nchw(rgb, 3)
+    assert relmax(out, fx["rgb"].to(dev())) < tol
+    for a, b in zip(rgbs, fx["rgbs"]):
+        assert relmax(ops.to_nchw(a, 3), b.to(dev())) < tol
+    (out ** 2).mean().backward()
+    named = dict(G.named_parameters())
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["ggrads"].items())
+    assert worst[0] < tol * 5, worst
+    D = g.Discriminator(text_encoder=g.TextEncoder(**fx["te_cfg"]), **fx["dcfg"]).to(dev())
+    D.load_state_dict(fx["dsd"])
+    img = fx["img"].to(dev())
+    lo, ms, _ = D(img, D.real_images_to_rgbs(img), text_encodings=enc, calc_aux_loss=False)
+    assert relmax(lo, fx["logits"].to(dev())) < tol
+    for a, b in zip(ms, fx["ms"]):
+        assert relmax(a, b.to(dev())) < tol
+    (lo.sum() + sum((m ** 2).sum() for m in ms)).backward()
+    named = dict(D.named_parameters())
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["dgrads"].items())
+    assert worst[0] < tol * 10, worst
+
+
+def test_weight_bank_layouts():
+    """one-launch re-layout of every conv weight of a flat parameter buffer: forward (O,KH,KW,Ipad) and flipped /
+    swapped (Ipad,KH,KW,O) kernel layouts against torch permutes, including odd channel counts and 5-D filter banks"""
+    from gigagan_pytorch_b200 import ops
+    shapes = [(3, 64, 1, 1), (32, 3, 3, 3), (40, 3, 7, 7), (64, 32, 3, 3), (1, 48, 1, 1), (96, 160, 2, 2),
+              (2, 33, 16, 3, 3), (16, 16, 4, 4)]
+    import math
+    n = sum(math.prod(s) for s in shapes)
+    flat = torch.randn(n + 8, device=dev())
+    params, off = [], 0
+    for s in shapes:
+        k = math.prod(s)
+        params.append(flat[off:off + k].view(s))
+        off += k
+    pad = lambda c: 16 if c < 16 else (c + 15) // 16 * 16
+    for dt in (torch.bfloat16, torch.float32):
+        bank = ops.WeightBank(flat, params, dt, pad)
+        bank.refresh()
+        for p in params:
+            for w in (p.unbind(0) if p.ndim == 5 else [p]):
+                f, b = bank.lookup(w, pad(w.shape[1]), dt)
+                ref = torch.nn.functional.pad(w.permute(0, 2, 3, 1), (0, pad(w.shape[1]) - w.shape[1])).to(dt)
+                assert torch.equal(f, ref), (tuple(w.shape), dt)
+                assert torch.equal(b, ref.flip((1, 2)).permute(3, 1, 2, 0)), (tuple(w.shape), dt)

@@ -109,3 +109,40 @@ def test_ka6_unet_upsampler():
     (rgb ** 2).mean().backward()
     for k, v in g["grads"].items():
         assert relerr(sd[k].grad, v) < 2e-4, k
+
+
+def test_ka7_text_conditional_generator_and_discriminator():
+    """text-conditioned path: TextEncoder -> StyleNetwork concat + cross attention in G,
+    text-modulated predictors in D; fixture from the unmodified reference (oracle/make_golden.py KA7)."""
+    g = load("ka7_text_conditional.pt")
+    c, te = g["gcfg"], g["te_cfg"]
+    plan = O.generator_plan(c["image_size"], c["dim_capacity"], c["dim_max"], c["dim_latent"],
+                            c["num_skip_layers_excite"], c["self_attn_resolutions"], 2, 2, 8, unconditional=False,
+                            cross_attn_resolutions=c["cross_attn_resolutions"], cross_attn_heads=2,
+                            cross_attn_dim_head=8)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["gsd"].items()}
+    gt, ft, tm = O.text_encoder(O._sub(sd, "text_encoder."), g["enc"], te["depth"], te["heads"], te["dim_head"])
+    assert tm.tolist() == [[True] * 6, [True] * 4 + [False] * 2]
+    torch.manual_seed(g["noise_seed"])
+    rgb, rgbs = O.generator_forward(sd, plan, g["z"], style_depth=2, return_all_rgbs=True, global_text_tokens=gt,
+                                    fine_text_tokens=ft, text_mask=tm)
+    torch.testing.assert_close(rgb, g["rgb"], **TOL)
+    for a, b in zip(rgbs, g["rgbs"]):
+        torch.testing.assert_close(a, b, **TOL)
+    (rgb ** 2).mean().backward()
+    for k, v in g["ggrads"].items():
+        assert relerr(sd[k].grad, v) < 2e-4, k
+    c = g["dcfg"]
+    dplan = O.discriminator_plan(c["image_size"], c["dim_capacity"], c["dim_max"], 3, c["attn_resolutions"],
+                                 c["multiscale_input_resolutions"], 1, (8,),
+                                 num_skip_layers_excite=c["num_skip_layers_excite"], attn_heads=2, attn_dim_head=8)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["dsd"].items()}
+    emb, _, _ = O.text_encoder(O._sub(sd, "text_encoder."), g["enc"], te["depth"], te["heads"], te["dim_head"])
+    lo, ms, _ = O.discriminator_forward(sd, dplan, g["img"], O.real_images_to_rgbs(g["img"], dplan), True, False,
+                                        text_embeds=emb)
+    torch.testing.assert_close(lo, g["logits"], **TOL)
+    for a, b in zip(ms, g["ms"]):
+        torch.testing.assert_close(a, b, **TOL)
+    (lo.sum() + sum((m ** 2).sum() for m in ms)).backward()
+    for k, v in g["dgrads"].items():
+        assert relerr(sd[k].grad, v) < 2e-4, k
