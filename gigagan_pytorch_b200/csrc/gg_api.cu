@@ -46,7 +46,11 @@ static int conv_fprop_any(const void* x, const void* w, const float* bias, const
                           float gain, const long* ystr, int dtype, cudaStream_t st) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    int r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, st);
+    int r = 1;
+    if (!ystr && !(g_flags & 2))           // thin 128^2 / 256^2 layers: input rows staged once, all taps from shared memory
+      r = ggi_tc_conv_thin(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, st);
+    if (r <= 0) return r;
+    r = ggi_tc_conv_fprop(x, w, bias, res, y, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, act, gain, ystr, st);
     if (r <= 0) return r;
     if (dbg_fallback()) fprintf(stderr, "[gg] FFMA fprop: N%d H%d W%d Cin%d -> OH%d OW%d Cout%d k%dx%d s%d p%d ps%d\n", N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w);
   }
@@ -173,6 +177,9 @@ int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W
   return ggi_maxpool2_bwd(x, gy, gx, N, H, W, C, dtype, ST);
 }
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream) { return ggi_softmax_tokens(x, y, B, n, C, dtype, ST); }
+int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, gg_stream_t stream) {
+  return ggi_wgrad_sink(dw, dst, O, I, KK, Ipad, ST);
+}
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream) {
   return ggi_weight_prep_multi(master, entries, chunks, nchunks, fwd, bwd, dtype, ST);

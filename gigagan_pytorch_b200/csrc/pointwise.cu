@@ -883,6 +883,32 @@ int ggi_weight_prep_multi(const float* master, const void* entries, const void* 
   return gg_check_launch("weight_prep_multi");
 }
 
+// Weight-gradient sink: the kernel-layout fp32 gradient dw[o][kk][ipad] produced by the wgrad kernels is ACCUMULATED into
+// the master-layout gradient buffer dst[o][i][kk] (the optimiser's flat .grad view) in one pass: replaces a permute
+// copy plus the autograd engine's separate accumulation kernel.  One block = one output channel x 128 input channels.
+__global__ void wgrad_sink_kernel(const float* __restrict__ dw, float* __restrict__ dst, int O, int I, int KK, int Ipad) {
+  extern __shared__ float sk[];                     // [KK][129]
+  const int o = blockIdx.y, i0 = blockIdx.x * 128;
+  const int ni = min(128, I - i0);
+  const float* src = dw + (long)o * KK * Ipad + i0;
+  for (int t = threadIdx.x; t < KK * 128; t += blockDim.x) {
+    int il = t & 127, kk = t >> 7;
+    if (il < ni) sk[kk * 129 + il] = src[(long)kk * Ipad + il];
+  }
+  __syncthreads();
+  float* d = dst + ((long)o * I + i0) * KK;
+  for (int t = threadIdx.x; t < ni * KK; t += blockDim.x) {
+    int il = t / KK, kk = t - il * KK;
+    d[t] += sk[kk * 129 + il];
+  }
+}
+int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, cudaStream_t st) {
+  if (KK > 64) return gg_fail("wgrad_sink: filter too large");
+  dim3 grid((I + 127) / 128, O);
+  wgrad_sink_kernel<<<grid, 256, KK * 129 * sizeof(float), st>>>(dw, dst, O, I, KK, Ipad);
+  return gg_check_launch("wgrad_sink");
+}
+
 // ------------------------------------------------------------------ UnetUpsampler extras (unet_upsampler.py)
 // 2x2 max-pool of NHWC maps (ref :158 F.max_pool2d) and its gradient (first maximum in row-major order wins, as ATen)
 template <typename T>

@@ -283,7 +283,8 @@ class Conv2dFn(Function):
         if ctx.needs_input_grad[0]:
             gx = ConvDgradFn.apply(gy, weight, pg, tuple(x.shape), ctx.master)
         if ctx.needs_input_grad[1] and not _skip_param_grads():
-            gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
+            if not (ctx.master and _wgrad_to_sink(x, gy, pg, weight)):
+                gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
         if ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads():
             gb = dot_sc(gy, None, gy.numel() // gy.shape[-1], 1).reshape(-1)
         return gx, gw, gb, gres, None, None
@@ -306,8 +307,24 @@ class ConvDgradFn(Function):
         if ctx.needs_input_grad[0]:
             d_gy = Conv2dFn.apply(ggx, weight, None, None, g, ctx.master)
         if ctx.needs_input_grad[1] and not _skip_param_grads():
-            d_w = ConvWgradFn.apply(ggx, gy, g, weight if ctx.master else None)
+            if not (ctx.master and _wgrad_to_sink(ggx, gy, g, weight)):
+                d_w = ConvWgradFn.apply(ggx, gy, g, weight if ctx.master else None)
         return d_gy, d_w, None, None, None
+
+
+def _wgrad_to_sink(x, gy, geom, weight):
+    """Terminal (no higher-order graph) weight gradient of a parameter whose .grad is a view of an optimiser's flat
+    gradient buffer (FlatAdamW marks those with ``_gg_sink``): run the wgrad kernel and accumulate its kernel-layout
+    result straight into that buffer.  Returns False when the ordinary autograd route must be used."""
+    if torch.is_grad_enabled() or not getattr(weight, "_gg_sink", False):
+        return False
+    dst = weight.grad
+    if dst is None or dst.dtype != torch.float32 or not dst.is_contiguous():
+        return False
+    dw = _conv_wgrad_raw(_c(x), _c(gy), geom)                       # (O, KH, KW, Ipad) fp32
+    O, KH, KW, ipad = dw.shape
+    call("gg_wgrad_sink", _p(dw), _p(dst), O, weight.shape[1], KH * KW, ipad, _st())
+    return True
 
 
 class ConvWgradFn(Function):

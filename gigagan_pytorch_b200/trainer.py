@@ -119,6 +119,7 @@ class FlatAdamW:
             self.flat[off:off + n].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + n].view(p.shape)
             p.grad = self.grad[off:off + n].view(p.shape)
+            p._gg_sink = p.ndim == 4            # conv weights: wgrad kernels accumulate straight into the flat gradient
             decay = 1 if p.ndim >= 2 else 0
             for s in range(0, n, self.CHUNK):
                 o = off + s

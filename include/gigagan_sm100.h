@@ -25,7 +25,9 @@ const char* gg_last_error(void);
 int gg_version(void);
 /* 1 when this build contains the tcgen05/TMA kernels (always, for sm_100a). */
 int gg_has_tcgen05(void);
-/* bit 0: route every convolution to the FFMA kernels (testing the tcgen05 path against them). Returns old flags. */
+/* bit 0: route every convolution to the FFMA kernels (testing the tcgen05 path against them);
+ * bit 1: disable the thin-layer ring kernel (conv_thin_tc.cu) so those shapes take the generic tcgen05 kernel.
+ * Returns old flags. */
 int gg_set_flags(int flags);
 
 /* ---- convolution family (replaces F.conv2d / nn.Conv2d: gigagan_pytorch.py:402-409 grouped per-sample conv of
@@ -139,10 +141,16 @@ int gg_incr(int* p, gg_stream_t stream);
 int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream);
+/* Accumulate a kernel-layout fp32 weight gradient dw[O][KK][Ipad] (output of gg_conv2d_wgrad) into the master-layout
+ * gradient buffer dst[O][I][KK] (+=): the .grad accumulation of nn.Conv2d weights (torch autograd AccumulateGrad under
+ * gigagan_pytorch.py:2113 / :2207 accelerator.backward). */
+int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, gg_stream_t stream);
+
 /* ---- once-per-step re-layout of all conv weights of a model from the flat fp32 master buffer (reference layout
  * [O][I][KK]) into both kernel layouts: fwd [O][KK][Ipad] and bwd [Ipad][KK reversed][O] (replaces the per-call
  * weight permutes cuDNN does internally for nn.Conv2d / F.conv2d and their autograd).
- * entries: int64[8] {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32[4] {entry, start, count, 0}. */
+ * entries: int64[8] {src_off, O, I, KK, Ipad, fwd_off, bwd_off, 0}; chunks: int32[4] {entry, o0, i0, TI}:
+ * one block re-lays the (32 output channels) x (TI input channels) x KK tile through shared memory. */
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream);
 
