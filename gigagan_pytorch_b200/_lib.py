@@ -46,6 +46,8 @@ def lib():
         for name, (ret, argtypes) in parse_header().items():
             fn = getattr(L, name)          # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = ret, argtypes
+        if os.environ.get("GG_FLAGS"):            # A/B switches for benchmarking (see gg_set_flags in the header)
+            L.gg_set_flags(int(os.environ["GG_FLAGS"]))
         _lib = L
     return _lib
 

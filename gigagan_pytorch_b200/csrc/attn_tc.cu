@@ -32,20 +32,25 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// |k_j|^2 per (b, h, token): one warp per row
+// |k_j|^2 per (b, h, token): 8 lanes per 64-element row (one 16-byte load each), 4 rows per warp
 __global__ void attn_ksq_kernel(const bf16* __restrict__ k, float* __restrict__ ksq, int B, int n, int heads, long k_rs) {
-  long row = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);     // row = (b*heads + h)*n + j
-  if (row >= (long)B * heads * n) return;
-  int lane = threadIdx.x & 31;
-  int j = (int)(row % n);
-  long bh = row / n;
-  int h = (int)(bh % heads);
-  long b = bh / heads;
-  const bf16* p = k + (b * n + j) * k_rs + h * ATC_D + lane * 2;
-  __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(p);
-  float2 f = __bfloat1622float2(v);
-  float s = warp_sum(f.x * f.x + f.y * f.y);
-  if (lane == 0) ksq[row] = s;
+  const long total = (long)B * heads * n;
+  const int sub = threadIdx.x & 7;
+  for (long row = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 3; row < total; row += ((long)gridDim.x * blockDim.x) >> 3) {
+    int j = (int)(row % n);                               // row = (b*heads + h)*n + j
+    long bh = row / n;
+    int h = (int)(bh % heads);
+    long b = bh / heads;
+    uint4 v = *reinterpret_cast<const uint4*>(k + (b * n + j) * k_rs + h * ATC_D + sub * 8);
+    const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&v);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(hv[i]); s = fmaf(f.x, f.x, fmaf(f.y, f.y, s)); }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0) ksq[row] = s;
+  }
 }
 
 __global__ void __launch_bounds__(ATC_FWD_THREADS, 1)
@@ -66,7 +71,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(gbase + 147456 + 2560 + 8 * 18);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
   const int b = bh / p.heads, h = bh % p.heads;
   const int T = p.tiles;
@@ -100,27 +105,29 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0) {
     // ================================================= TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(bar(Q_FULL), 16384);
-      tma_load_4d(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b);
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
+      mbar_expect_tx_el(bar(Q_FULL), 16384, el);
+      tma_load_4d_el(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
       int kc = 0, vc = 0;
       for (int pass = 0; pass < 2; ++pass)
         for (int j = 0; j < T; ++j) {
           int s = kc & 1;
           mbar_wait(bar(K_EMPTY + s), ((kc >> 1) & 1) ^ 1u);
-          mbar_expect_tx(bar(K_FULL + s), 16384);
-          tma_load_4d(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b);
+          mbar_expect_tx_el(bar(K_FULL + s), 16384, el);
+          tma_load_4d_el(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b, el);
           ++kc;
           if (pass == 1) {
             int sv = vc & 1;
             mbar_wait(bar(V_EMPTY + sv), ((vc >> 1) & 1) ^ 1u);
-            mbar_expect_tx(bar(V_FULL + sv), 16384);
-            tma_load_4d(sV + sv * 16384, &tmV, bar(V_FULL + sv), 0, j * ATC_T, h, b);
+            mbar_expect_tx_el(bar(V_FULL + sv), 16384, el);
+            tma_load_4d_el(sV + sv * 16384, &tmV, bar(V_FULL + sv), 0, j * ATC_T, h, b, el);
             ++vc;
           }
         }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     // ================================================= MMA issuer
     int kc = 0, sc = 0, pc = 0;
     auto issue_S = [&]() {
@@ -128,12 +135,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar(K_FULL + ks), (kc >> 1) & 1);
       mbar_wait(bar(S_EMPTY + ss), ((sc >> 1) & 1) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
         uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + ks * 16384, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tS + ss * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u);
-        tc_commit(bar(K_EMPTY + ks));
-        tc_commit(bar(S_FULL + ss));
+        for (int k = 0; k < 4; ++k) tc_mma_f16_el(tS + ss * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_qk, k ? 1u : 0u, el);
+        tc_commit_el(bar(K_EMPTY + ks), el);
+        tc_commit_el(bar(S_FULL + ss), el);
       }
       __syncwarp();
       ++kc; ++sc;
@@ -147,16 +154,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar(P_FULL + ps), (pc >> 1) & 1);
       mbar_wait(bar(V_FULL + ps), (pc >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t da = make_smem_desc(sP + ps * 32768 + (k >> 2) * 16384, 1024, 2) + (uint64_t)(2 * (k & 3));
           uint64_t db = make_smem_desc_mn(sV + ps * 16384 + k * 2048, 0, 1024);
-          tc_mma_f16(tO, da, db, idesc_pv, (j | k) ? 1u : 0u);
+          tc_mma_f16_el(tO, da, db, idesc_pv, (j | k) ? 1u : 0u, el);
         }
-        tc_commit(bar(P_EMPTY + ps));
-        tc_commit(bar(V_EMPTY + ps));
-        if (j == T - 1) tc_commit(bar(O_FULL));
+        tc_commit_el(bar(P_EMPTY + ps), el);
+        tc_commit_el(bar(V_EMPTY + ps), el);
+        if (j == T - 1) tc_commit_el(bar(O_FULL), el);
       }
       __syncwarp();
       ++pc;
@@ -330,7 +337,7 @@ int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* nu
   if (make_qkv_map(&tmQ, q, B, nq, heads, q_rs) || make_qkv_map(&tmK, k, B, nk, heads, k_rs) || make_qkv_map(&tmV, v, B, nk, heads, v_rs)) return -1;
   if (mode == 1) {
     long rows = (long)B * heads * nk;
-    attn_ksq_kernel<<<gg_cdiv(rows, 8), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
+    attn_ksq_kernel<<<gg_blocks(rows * 8, 256, 148 * 16), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
   }
   size_t smem = 1024 + 147456 + 2560 + 8 * 18 + 16;
   static bool attr_set = false;
@@ -414,7 +421,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
          DS_FULL = 15, DS_EMPTY = 17, DQ_FULL = 19, NBAR = 20 };
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(gbase + 166400 + 8 * NBAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
   const int b = bh / p.heads, h = bh % p.heads;
   const int T = p.tiles;
@@ -446,32 +453,34 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const uint32_t idesc_dq = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar(Q_FULL), 32768);
-      tma_load_4d(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b);
-      tma_load_4d(sDO, &tmDO, bar(Q_FULL), 0, qt * ATC_T, h, b);
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
+      mbar_expect_tx_el(bar(Q_FULL), 32768, el);
+      tma_load_4d_el(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
+      tma_load_4d_el(sDO, &tmDO, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
       for (int j = 0; j < T; ++j) {
         int s = j & 1;
         uint32_t par = ((j >> 1) & 1) ^ 1u;
         mbar_wait(bar(K_EMPTY + s), par);
-        mbar_expect_tx(bar(K_FULL + s), 16384);
-        tma_load_4d(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b);
+        mbar_expect_tx_el(bar(K_FULL + s), 16384, el);
+        tma_load_4d_el(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b, el);
         mbar_wait(bar(V_EMPTY + s), par);
-        mbar_expect_tx(bar(V_FULL + s), 16384);
-        tma_load_4d(sV + s * 16384, &tmV, bar(V_FULL + s), 0, j * ATC_T, h, b);
+        mbar_expect_tx_el(bar(V_FULL + s), 16384, el);
+        tma_load_4d_el(sV + s * 16384, &tmV, bar(V_FULL + s), 0, j * ATC_T, h, b, el);
       }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     auto issue_S = [&](int j) {
       int s = j & 1;
       mbar_wait(bar(K_FULL + s), (j >> 1) & 1);
       mbar_wait(bar(S_EMPTY + s), ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
         uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + s * 16384, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tS + s * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        tc_commit(bar(S_FULL + s));
+        for (int k = 0; k < 4; ++k) tc_mma_f16_el(tS + s * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
+        tc_commit_el(bar(S_FULL + s), el);
       }
       __syncwarp();
     };
@@ -480,12 +489,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(bar(V_FULL + s), (j >> 1) & 1);
       mbar_wait(bar(DP_EMPTY), (j & 1) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
         uint64_t da = make_smem_desc(sDO, 1024, 2), db = make_smem_desc(sV + s * 16384, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        tc_commit(bar(DP_FULL));
-        tc_commit(bar(V_EMPTY + s));
+        for (int k = 0; k < 4; ++k) tc_mma_f16_el(tDP, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
+        tc_commit_el(bar(DP_FULL), el);
+        tc_commit_el(bar(V_EMPTY + s), el);
       }
       __syncwarp();
     };
@@ -497,16 +506,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       int s = j & 1;
       mbar_wait(bar(DS_FULL + s), (j >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t da = make_smem_desc(sDS + s * 32768 + (k >> 2) * 16384, 1024, 2) + (uint64_t)(2 * (k & 3));
           uint64_t db = make_smem_desc_mn(sK + s * 16384 + k * 2048, 0, 1024);
-          tc_mma_f16(tDQ, da, db, idesc_dq, (j | k) ? 1u : 0u);
+          tc_mma_f16_el(tDQ, da, db, idesc_dq, (j | k) ? 1u : 0u, el);
         }
-        tc_commit(bar(DS_EMPTY + s));
-        tc_commit(bar(K_EMPTY + s));
-        if (j == T - 1) tc_commit(bar(DQ_FULL));
+        tc_commit_el(bar(DS_EMPTY + s), el);
+        tc_commit_el(bar(K_EMPTY + s), el);
+        if (j == T - 1) tc_commit_el(bar(DQ_FULL), el);
       }
       __syncwarp();
       if (j + 1 < T) issue_dP(j + 1);
@@ -624,7 +633,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   enum { KV_FULL = 0, QO_FULL = 1, QO_EMPTY = 3, SDP_FULL = 5, SDP_EMPTY = 6, PDS_FULL = 7, PDS_EMPTY = 8, OUT_FULL = 9, NBAR = 10 };
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(gbase + 197120 + 8 * NBAR);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int kt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
   const int b = bh / p.heads, h = bh % p.heads;
   const int T = p.tiles;
@@ -658,32 +667,34 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t idesc_dk = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(80 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
   if (warp == 0) {
-    if (lane == 0) {
-      mbar_expect_tx(bar(KV_FULL), 32768);
-      tma_load_4d(sK, &tmK, bar(KV_FULL), 0, kt * ATC_T, h, b);
-      tma_load_4d(sV, &tmV, bar(KV_FULL), 0, kt * ATC_T, h, b);
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
+      mbar_expect_tx_el(bar(KV_FULL), 32768, el);
+      tma_load_4d_el(sK, &tmK, bar(KV_FULL), 0, kt * ATC_T, h, b, el);
+      tma_load_4d_el(sV, &tmV, bar(KV_FULL), 0, kt * ATC_T, h, b, el);
       for (int i = 0; i < T; ++i) {
         int s = i & 1;
         mbar_wait(bar(QO_EMPTY + s), ((i >> 1) & 1) ^ 1u);
-        mbar_expect_tx(bar(QO_FULL + s), 32768);
-        tma_load_4d(sQO + s * 32768, &tmQ, bar(QO_FULL + s), 0, i * ATC_T, h, b);
-        tma_load_4d(sDO + s * 16384, &tmDO, bar(QO_FULL + s), 0, i * ATC_T, h, b);
+        mbar_expect_tx_el(bar(QO_FULL + s), 32768, el);
+        tma_load_4d_el(sQO + s * 32768, &tmQ, bar(QO_FULL + s), 0, i * ATC_T, h, b, el);
+        tma_load_4d_el(sDO + s * 16384, &tmDO, bar(QO_FULL + s), 0, i * ATC_T, h, b, el);
       }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     auto issue_SdP = [&](int i) {
       int s = i & 1;
       mbar_wait(bar(QO_FULL + s), (i >> 1) & 1);
       mbar_wait(bar(SDP_EMPTY), (i & 1) ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {
         uint64_t dq_ = make_smem_desc(sQO + s * 32768, 1024, 2), dk_ = make_smem_desc(sK, 1024, 2);
         uint64_t do_ = make_smem_desc(sDO + s * 16384, 1024, 2), dv_ = make_smem_desc(sV, 1024, 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tS, dq_ + (uint64_t)(2 * k), dk_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_f16_el(tS, dq_ + (uint64_t)(2 * k), dk_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16(tDP, do_ + (uint64_t)(2 * k), dv_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u);
-        tc_commit(bar(SDP_FULL));
+        for (int k = 0; k < 4; ++k) tc_mma_f16_el(tDP, do_ + (uint64_t)(2 * k), dv_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
+        tc_commit_el(bar(SDP_FULL), el);
       }
       __syncwarp();
     };
@@ -693,22 +704,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       int s = i & 1;
       mbar_wait(bar(PDS_FULL), i & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {      // K axis = the 128 queries of this tile, 16 per step
           uint64_t ap = make_smem_desc_mn(sP + k * 2048, 16384, 1024);
           uint64_t bo = make_smem_desc_mn(sDO + s * 16384 + k * 2048, 0, 1024);
-          tc_mma_f16(tDV, ap, bo, idesc_dv, (i | k) ? 1u : 0u);
+          tc_mma_f16_el(tDV, ap, bo, idesc_dv, (i | k) ? 1u : 0u, el);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t as_ = make_smem_desc_mn(sDS + k * 2048, 16384, 1024);
           uint64_t bq = make_smem_desc_mn(sQO + s * 32768 + k * 2048, 16384, 1024);
-          tc_mma_f16(tDK, as_, bq, idesc_dk, (i | k) ? 1u : 0u);
+          tc_mma_f16_el(tDK, as_, bq, idesc_dk, (i | k) ? 1u : 0u, el);
         }
-        tc_commit(bar(PDS_EMPTY));
-        tc_commit(bar(QO_EMPTY + s));
-        if (i == T - 1) tc_commit(bar(OUT_FULL));
+        tc_commit_el(bar(PDS_EMPTY), el);
+        tc_commit_el(bar(QO_EMPTY + s), el);
+        if (i == T - 1) tc_commit_el(bar(OUT_FULL), el);
       }
       __syncwarp();
       if (i + 1 < T) issue_SdP(i + 1);
@@ -786,23 +797,35 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 __global__ void attn_null_grad_kernel(const bf16* __restrict__ q, const bf16* __restrict__ go, const float* __restrict__ nullrow,
                                       const float* __restrict__ null_kv, float* __restrict__ dnull, int B, int n, int heads,
                                       long q_rs, int mode, int rows_per_block) {
-  __shared__ float sm[4][128];
-  const int h = blockIdx.y, c = threadIdx.x & 63, rl = threadIdx.x >> 6;        // 256 threads: 4 row lanes x 64 columns
+  __shared__ float sm[32][129];
+  const int h = blockIdx.y, oct = threadIdx.x & 7, rl = threadIdx.x >> 3;       // 256 threads: 32 row lanes x 8 column octets
   const long total = (long)B * n, r0 = (long)blockIdx.x * rows_per_block;
   const long r1 = min(total, r0 + rows_per_block);
-  const float kn = mode == 1 ? null_kv[h * ATC_D + c] : 0.f;
-  float gk = 0.f, gv = 0.f;
-  for (long row = r0 + rl; row < r1; row += 4) {
+  float kn[8], gk[8], gv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { kn[e] = mode == 1 ? null_kv[h * ATC_D + oct * 8 + e] : 0.f; gk[e] = 0.f; gv[e] = 0.f; }
+  for (long row = r0 + rl; row < r1; row += 32) {
     long b = row / n, i = row - b * n;
     long srow = (b * heads + h) * (long)n + i;
     float dsn = nullrow[srow], pn = nullrow[(long)B * heads * n + srow];
-    gk = fmaf(dsn, __bfloat162float(q[row * q_rs + h * ATC_D + c]) - kn, gk);
-    gv = fmaf(pn, __bfloat162float(go[row * (long)(heads * ATC_D) + h * ATC_D + c]), gv);
+    uint4 qv = *reinterpret_cast<const uint4*>(q + row * q_rs + h * ATC_D + oct * 8);
+    uint4 gov = *reinterpret_cast<const uint4*>(go + row * (long)(heads * ATC_D) + h * ATC_D + oct * 8);
+    const __nv_bfloat162* qh = reinterpret_cast<const __nv_bfloat162*>(&qv);
+    const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 qf = __bfloat1622float2(qh[e]), gf = __bfloat1622float2(gh[e]);
+      gk[2 * e] = fmaf(dsn, qf.x - kn[2 * e], gk[2 * e]); gk[2 * e + 1] = fmaf(dsn, qf.y - kn[2 * e + 1], gk[2 * e + 1]);
+      gv[2 * e] = fmaf(pn, gf.x, gv[2 * e]); gv[2 * e + 1] = fmaf(pn, gf.y, gv[2 * e + 1]);
+    }
   }
-  sm[rl][c] = gk; sm[rl][64 + c] = gv;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sm[rl][oct * 8 + e] = gk[e]; sm[rl][64 + oct * 8 + e] = gv[e]; }
   __syncthreads();
   if (threadIdx.x < 128) {
-    float t = sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x];
+    float t = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
     int cc = threadIdx.x & 63;
     atomicAdd(dnull + (threadIdx.x < 64 ? h * ATC_D + cc : (heads + h) * ATC_D + cc), t);
   }
@@ -831,7 +854,7 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
       make_qkv_map(&tmV, v, B, nk, heads, v_rs) || make_qkv_map(&tmDO, go, B, nq, heads, hd)) return -1;
   if (mode == 1) {
     long rows = (long)B * heads * nk;
-    attn_ksq_kernel<<<gg_cdiv(rows, 8), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
+    attn_ksq_kernel<<<gg_blocks(rows * 8, 256, 148 * 16), 256, 0, st>>>((const bf16*)k, ksq_ws, B, nk, heads, k_rs);
   }
   if (p.has_null) cudaMemsetAsync(dnull_kv, 0, sizeof(float) * 2 * heads * ATC_D, st);
   static bool attr_set = false;

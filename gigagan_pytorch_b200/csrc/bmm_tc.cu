@@ -29,7 +29,7 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
   uint32_t* tmem_slot = (uint32_t*)(gen_base + p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
@@ -46,7 +46,8 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int tiles_per_batch = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int z = tile / tiles_per_batch, r = tile - z * tiles_per_batch;
@@ -55,21 +56,22 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         int m0 = mt * 128, n0 = nt * p.Ntile;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
+          mbar_expect_tx_el(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes), el);
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
-          if (!p.a_mn) tma_load_4d(sa, &tmA, full_bar(stage), kb * 64, m0, z2, z1);
+          if (!p.a_mn) tma_load_4d_el(sa, &tmA, full_bar(stage), kb * 64, m0, z2, z1, el);
           else {
-            tma_load_4d(sa, &tmA, full_bar(stage), m0, kb * 64, z2, z1);
-            tma_load_4d(sa + 8192, &tmA, full_bar(stage), m0 + 64, kb * 64, z2, z1);
+            tma_load_4d_el(sa, &tmA, full_bar(stage), m0, kb * 64, z2, z1, el);
+            tma_load_4d_el(sa + 8192, &tmA, full_bar(stage), m0 + 64, kb * 64, z2, z1, el);
           }
-          if (!p.b_mn) tma_load_4d(sb, &tmB, full_bar(stage), kb * 64, n0, z2, z1);
+          if (!p.b_mn) tma_load_4d_el(sb, &tmB, full_bar(stage), kb * 64, n0, z2, z1, el);
           else
-            for (int s = 0; s < p.nsub_b; ++s) tma_load_4d(sb + s * 8192, &tmB, full_bar(stage), n0 + s * 64, kb * 64, z2, z1);
+            for (int s = 0; s < p.nsub_b; ++s) tma_load_4d_el(sb + s * 8192, &tmB, full_bar(stage), n0 + s * 64, kb * 64, z2, z1, el);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -78,16 +80,16 @@ bmm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             uint64_t da = p.a_mn ? make_smem_desc_mn(sa + k * 2048, 8192, 1024) : make_smem_desc(sa, 1024, 2) + (uint64_t)(k * 2);
             uint64_t db = p.b_mn ? make_smem_desc_mn(sb + k * 2048, 8192, 1024) : make_smem_desc(sb, 1024, 2) + (uint64_t)(k * 2);
-            tc_mma_f16(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16_el(d_tmem, da, db, p.idesc, (kb | k) != 0 ? 1u : 0u, el);
           }
-          tc_commit(empty_bar(stage));
-          if (kb == p.kblocks - 1) tc_commit(tfull_bar(acc));
+          tc_commit_el(empty_bar(stage), el);
+          if (kb == p.kblocks - 1) tc_commit_el(tfull_bar(acc), el);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }

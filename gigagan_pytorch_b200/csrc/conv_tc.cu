@@ -42,7 +42,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
   uint32_t* tmem_slot = (uint32_t*)(gen_base + p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
@@ -60,7 +60,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt = tile % p.n_tiles_n, mp = tile / p.n_tiles_n;
@@ -75,7 +76,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
         for (int kb = 0; kb < kblocks; ++kb) {
           int tap0 = (kb / p.cchunks) * p.ts, cc = kb % p.cchunks;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)(nA * p.a_bytes + p.ts * p.b_bytes));
+          mbar_expect_tx_el(full_bar(stage), (uint32_t)(nA * p.a_bytes + p.ts * p.b_bytes), el);
           uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + nA * p.a_bytes;
           for (int t = 0; t < p.ts; ++t) {
             int tap = tap0 + t;
@@ -84,19 +85,20 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
               uint32_t sa = sa0 + (t * p.mdual + d) * p.a_bytes;
               if (p.stride == 1) {
                 int ky = tap / p.KW, kx = tap - ky * p.KW;
-                tma_load_4d(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0[d] + kx - p.pad, oy0[d] + ky - p.pad, n0[d]);
+                tma_load_4d_el(sa, &tmA0, full_bar(stage), cc * p.chunk, ox0[d] + kx - p.pad, oy0[d] + ky - p.pad, n0[d], el);
               } else {
                 const CUtensorMap* m = tap == 0 ? &tmA0 : tap == 1 ? &tmA1 : tap == 2 ? &tmA2 : &tmA3;
-                tma_load_4d(sa, m, full_bar(stage), cc * p.chunk, ox0[d], oy0[d], n0[d]);
+                tma_load_4d_el(sa, m, full_bar(stage), cc * p.chunk, ox0[d], oy0[d], n0[d], el);
               }
             }
-            tma_load_4d(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0[0] : 0);
+            tma_load_4d_el(sb, &tmB, full_bar(stage), cc * p.chunk, tap, co0, p.per_sample ? n0[0] : 0, el);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     // ===================================================== MMA issuer
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     const int nacc = p.mdual == 2 ? 1 : 2;                 // dual-M uses all 512 TMEM columns for one tile pair
@@ -108,7 +110,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           uint32_t sa0 = base + stage * p.stage_bytes, sb0 = sa0 + nA * p.a_bytes;
           int ksteps = p.chunk >> 4;
           for (int t = 0; t < p.ts; ++t) {
@@ -116,11 +118,11 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
             for (int d = 0; d < p.mdual; ++d) {
               uint64_t da = make_smem_desc(sa0 + (t * p.mdual + d) * p.a_bytes, p.sbo, p.layout_type);
               for (int k = 0; k < ksteps; ++k)
-                tc_mma_f16(d_tmem + d * p.Ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | t | k) != 0 ? 1u : 0u);
+                tc_mma_f16_el(d_tmem + d * p.Ntile, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, (kb | t | k) != 0 ? 1u : 0u, el);
             }
           }
-          tc_commit(empty_bar(stage));
-          if (kb == kblocks - 1) tc_commit(tfull_bar(acc));
+          tc_commit_el(empty_bar(stage), el);
+          if (kb == kblocks - 1) tc_commit_el(tfull_bar(acc), el);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -368,7 +370,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_MAX_STAGES + 2 + a); };
   uint32_t* tmem_slot = (uint32_t*)(gen_base + p.stages * p.stage_bytes + 8 * (2 * TC_MAX_STAGES + 4));
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
@@ -397,7 +399,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
   };
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
+      const uint32_t el = tc_elect_one();          // convergent producer: only the TMA / expect_tx instructions are predicated
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         int cob, cib, tap, img, t0, t1;
@@ -407,16 +410,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
           int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, tn = t / (p.tiles_w * p.tiles_h);
           int ox0 = tw * p.Wt, oy0 = th * p.Ht, n0 = tn * p.Nt;
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes));
+          mbar_expect_tx_el(full_bar(stage), (uint32_t)(p.a_bytes + p.b_bytes), el);
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
           for (int s = 0; s < p.nsub_a; ++s)
-            tma_load_4d(sa + s * (p.pix * 128), &tmDY, full_bar(stage), cob * 128 + s * 64, ox0, oy0, n0);
+            tma_load_4d_el(sa + s * (p.pix * 128), &tmDY, full_bar(stage), cob * 128 + s * 64, ox0, oy0, n0, el);
           for (int s = 0; s < p.nsub_b; ++s) {
             int c0 = cib * p.Ntile + s * 64;
-            if (p.stride == 1) tma_load_4d(sb + s * (p.pix * 128), &tmX0, full_bar(stage), c0, ox0 + kx - p.pad, oy0 + ky - p.pad, n0);
+            if (p.stride == 1) tma_load_4d_el(sb + s * (p.pix * 128), &tmX0, full_bar(stage), c0, ox0 + kx - p.pad, oy0 + ky - p.pad, n0, el);
             else {
               const CUtensorMap* m = tap == 0 ? &tmX0 : tap == 1 ? &tmX1 : tap == 2 ? &tmX2 : &tmX3;
-              tma_load_4d(sb + s * (p.pix * 128), m, full_bar(stage), c0, ox0, oy0, n0);
+              tma_load_4d_el(sb + s * (p.pix * 128), m, full_bar(stage), c0, ox0, oy0, n0, el);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -424,6 +427,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
       }
     }
   } else if (warp == 1) {
+    const uint32_t el = tc_elect_one();            // the lane that issues tcgen05.mma / commit (warp stays convergent)
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
     const uint32_t lbo_a = p.nsub_a > 1 ? p.pix * 128 : 0, lbo_b = p.pix * 128;
     const int ksteps = p.pix / 16;
@@ -436,14 +440,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0, const __grid_cons
       for (int t = t0; t < t1; ++t) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           uint32_t sa = base + stage * p.stage_bytes, sb = sa + p.a_bytes;
           for (int k = 0; k < ksteps; ++k) {
             uint64_t da = make_smem_desc_mn(sa + k * 2048, lbo_a, 1024), db = make_smem_desc_mn(sb + k * 2048, lbo_b, 1024);
-            tc_mma_f16(d_tmem, da, db, p.idesc, (t > t0 || k > 0) ? 1u : 0u);
+            tc_mma_f16_el(d_tmem, da, db, p.idesc, (t > t0 || k > 0) ? 1u : 0u, el);
           }
-          tc_commit(empty_bar(stage));
-          if (t == t1 - 1) tc_commit(tfull_bar(acc));
+          tc_commit_el(empty_bar(stage), el);
+          if (t == t1 - 1) tc_commit_el(tfull_bar(acc), el);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }

@@ -77,7 +77,10 @@ int gg_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int 
                     int KH, int KW, int stride, int pad, int per_sample_w, int dtype, gg_stream_t stream) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    int r = ggi_tc_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, ST);
+    int r = 1;
+    if (!(g_flags & 6)) r = ggi_tc_conv_thin_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, ST);
+    if (r <= 0) return r;
+    r = ggi_tc_conv_wgrad(x, dy, dw, N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w, ST);
     if (r <= 0) return r;
     if (dbg_fallback()) fprintf(stderr, "[gg] FFMA wgrad: N%d H%d W%d Cin%d -> OH%d OW%d Cout%d k%dx%d s%d p%d ps%d\n", N, H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, per_sample_w);
   }
@@ -177,6 +180,14 @@ int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W
   return ggi_maxpool2_bwd(x, gy, gx, N, H, W, C, dtype, ST);
 }
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream) { return ggi_softmax_tokens(x, y, B, n, C, dtype, ST); }
+int gg_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, int64_t R, int C, float s, int dtype, gg_stream_t stream) {
+  return ggi_rmsnorm_fwd(x, gamma, y, inv, (long)R, C, s, dtype, ST);
+}
+int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, int64_t R, int C,
+                   float s, int dtype, gg_stream_t stream) {
+  return ggi_rmsnorm_bwd(x, gamma, inv, gy, gx, dgamma, (long)R, C, s, dtype, ST);
+}
+int gg_debug_thin_trace(void* buf) { return ggi_debug_thin_trace((unsigned long long*)buf); }
 int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, gg_stream_t stream) {
   return ggi_wgrad_sink(dw, dst, O, I, KK, Ipad, ST);
 }

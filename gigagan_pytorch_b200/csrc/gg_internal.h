@@ -41,6 +41,12 @@ int ggi_adamw(float* p, const float* g, float* m, float* v, const void* chunks, 
 int ggi_incr(int* p, cudaStream_t st);
 
 // tcgen05 path (conv_tc.cu).  Return 1 when the shape is not eligible (caller falls through to FFMA), 0 ok, <0 error.
+int ggi_tc_conv_thin_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int OH, int OW, int Cout,
+                           int KH, int KW, int stride, int pad, int per_sample_w, cudaStream_t st);
+int ggi_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, long R, int C, float s, int dtype, cudaStream_t st);
+int ggi_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, long R, int C,
+                    float s, int dtype, cudaStream_t st);
+int ggi_debug_thin_trace(unsigned long long* buf);
 int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, cudaStream_t st);
 int ggi_tc_conv_thin(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W, int Cin,
                      int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act, float gain,

@@ -294,12 +294,57 @@ __global__ void dot_sc_vec_kernel(const T* __restrict__ a, const T* __restrict__
     }
   }
 }
+// narrow maps (C/V = 1..32 channel vectors, a power of two): the 256 threads tile (256/nvec row lanes) x nvec vectors, so
+// consecutive threads read consecutive 16-byte pieces of the row-major stream (bias gradients of the 16-64 channel
+// 128^2 / 256^2 layers left 28 of 32 lanes idle in the kernel above)
+template <typename T>
+__global__ void dot_sc_flat_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ out, int C, int P,
+                                   int Ns, long rows_per_out, int splits, int nvec) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sm[256 * V];
+  const int t = threadIdx.x, cv = t & (nvec - 1), rl = t / nvec, lanes = 256 / nvec;
+  const int ns = blockIdx.y;
+  long chunk = (rows_per_out + splits - 1) / splits;
+  long j0 = blockIdx.x * chunk, j1 = min(rows_per_out, j0 + chunk);
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (long j = j0 + rl; j < j1; j += lanes) {
+    long rep = j / P, pp = j - rep * P;
+    long r = (rep * Ns + ns) * P + pp;
+    float av[V], bv[V];
+    ldv(a + r * C + cv * V, av);
+    if (b) {
+      ldv(b + r * C + cv * V, bv);
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = fmaf(av[k], bv[k], acc[k]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] += av[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) sm[rl * C + cv * V + k] = acc[k];
+  __syncthreads();
+  if (t < C) {
+    float sres = 0.f;
+    for (int i = 0; i < lanes; ++i) sres += sm[i * C + t];
+    atomicAdd(out + (long)ns * C + t, sres);
+  }
+}
 int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int dtype, cudaStream_t st) {
   long N = R / P;
   long rows_per_out = (N / Ns) * P;
   cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Ns * C, st);
   int V = dtype == GG_F32 ? 4 : 8;
   dim3 block(32, 8);
+  if (C % V == 0 && al16(a) && (!b || al16(b)) && C / V <= 32 && ((C / V) & (C / V - 1)) == 0 && C <= 256) {
+    int nvec = C / V, splits = 1;
+    while (Ns * splits < 148 * 8 && rows_per_out / (splits * 2) >= 4 * (256 / nvec)) splits *= 2;
+    dim3 grid(splits, Ns);
+    GG_DISPATCH(dtype, (dot_sc_flat_kernel<T><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, out, C, P, Ns, rows_per_out, splits, nvec)));
+    return gg_check_launch("dot_sc_flat");
+  }
   if (C % V == 0 && al16(a) && (!b || al16(b))) {
     int gx = gg_cdiv(C, 32 * V);
     int base = gx * Ns, splits = 1;
@@ -907,6 +952,113 @@ int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, 
   dim3 grid((I + 127) / 128, O);
   wgrad_sink_kernel<<<grid, 256, KK * 129 * sizeof(float), st>>>(dw, dst, O, I, KK, Ipad);
   return gg_check_launch("wgrad_sink");
+}
+
+// ------------------------------------------------------------------ fused ChannelRMSNorm (gigagan_pytorch.py:224-232)
+// y[r,c] = x[r,c] * inv[r] * s * gamma[c],  inv[r] = 1 / max(||x[r,:]||, 1e-12);  one warp per pixel row, 16-byte
+// accesses, x read twice (second time from L1/L2).  First-order fast path of the composed rowdot/invnorm/bcast chain.
+template <typename T>
+__global__ void rmsnorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, T* __restrict__ y,
+                                   float* __restrict__ inv, long R, int C, float s) {
+  constexpr int V = VecN<T>::N;
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long r = warp0; r < R; r += nwarps) {
+    const T* xr = x + r * C;
+    float ss = 0.f;
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float v[V];
+      ldv<T>(xr + c, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ss += v[i] * v[i];
+    }
+    ss = warp_sum(ss);
+    const float iv = ss <= 1e-24f ? 1e12f : rsqrtf(ss);
+    if (lane == 0) inv[r] = iv;
+    T* yr = y + r * C;
+    for (int c = lane * V; c < C; c += 32 * V) {
+      float v[V], o[V];
+      ldv<T>(xr + c, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = v[i] * iv * (s * __ldg(gamma + c + i));
+      stv<T>(yr + c, o);
+    }
+  }
+}
+// gx = inv * (t - xh * dot(t, xh)),  t = gy * s * gamma,  xh = x * inv;   dgamma[c] += sum_r gy * xh * s
+template <typename T>
+__global__ void rmsnorm_bwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ inv,
+                                   const T* __restrict__ gy, T* __restrict__ gx, float* __restrict__ dgamma, long R, int C,
+                                   float s) {
+  constexpr int V = VecN<T>::N;
+  extern __shared__ float dg[];                                    // [C] per-block partial of dgamma
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dg[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long warp0 = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  float acc[4][V];                                                 // this lane's columns: lane*V + k*32*V, k < 4
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[k][i] = 0.f;
+  for (long r = warp0; r < R; r += nwarps) {
+    const T* xr = x + r * C;
+    const T* gr = gy + r * C;
+    const float iv = inv[r];
+    const bool clamped = iv >= 1e12f;                              // ||x|| below eps: y = x / eps, no projection term
+    float dot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane * V + k * 32 * V;
+      if (c < C) {
+        float v[V], g[V];
+        ldv<T>(xr + c, v); ldv<T>(gr + c, g);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          float xh = v[i] * iv;
+          dot += g[i] * s * __ldg(gamma + c + i) * xh;
+          acc[k][i] += g[i] * xh * s;
+        }
+      }
+    }
+    dot = clamped ? 0.f : warp_sum(dot);
+    T* or_ = gx + r * C;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane * V + k * 32 * V;
+      if (c < C) {
+        float v[V], g[V], o[V];
+        ldv<T>(xr + c, v); ldv<T>(gr + c, g);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = iv * (g[i] * s * __ldg(gamma + c + i) - v[i] * iv * dot);
+        stv<T>(or_ + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane * V + k * 32 * V;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) atomicAdd(&dg[c + i], acc[k][i]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dgamma + c, dg[c]);
+}
+int ggi_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, long R, int C, float s, int dtype, cudaStream_t st) {
+  if (C % 8 || !al16(x) || !al16(y)) return gg_fail("rmsnorm_fwd: C %% 8 != 0 or unaligned");
+  int blocks = gg_blocks(R * 32, 256, 148 * 8);
+  GG_DISPATCH(dtype, (rmsnorm_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, gamma, (T*)y, inv, R, C, s)));
+  return gg_check_launch("rmsnorm_fwd");
+}
+int ggi_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, long R, int C,
+                    float s, int dtype, cudaStream_t st) {
+  if (C % 8 || C > (dtype == GG_BF16 ? 1024 : 512) || !al16(x) || !al16(gy) || !al16(gx))
+    return gg_fail("rmsnorm_bwd: needs C %% 8 == 0, C <= 1024 (bf16) / 512 (fp32), 16-byte aligned tensors");
+  int blocks = gg_blocks(R * 32, 256, 148 * 4);
+  GG_DISPATCH(dtype, (rmsnorm_bwd_kernel<T><<<blocks, 256, C * sizeof(float), st>>>((const T*)x, gamma, inv, (const T*)gy, (T*)gx, dgamma, R, C, s)));
+  return gg_check_launch("rmsnorm_bwd");
 }
 
 // ------------------------------------------------------------------ UnetUpsampler extras (unet_upsampler.py)

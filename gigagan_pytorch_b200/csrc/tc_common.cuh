@@ -44,6 +44,39 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t da, uint64_
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- warp-uniform issue path.  tcgen05.mma / tcgen05.commit take their operands from UNIFORM registers: when the
+// descriptors are computed inside an `if (lane == 0)` branch they live in vector registers and every UTCHMMA is
+// preceded by ~7 R2UR(.BROADCAST) + ELECT (about 100 issue cycles per MMA, measured).  Here the whole warp runs the
+// issue loop convergently on warp-uniform values (warp index via shfl, see tc_warp_idx) and only the instruction is
+// predicated on the elected lane.
+__device__ __forceinline__ int tc_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t tc_elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void tc_mma_f16_el(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                              uint32_t elected) {
+  asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %4, 0;\nsetp.ne.b32 q, %5, 0;\n"
+               "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void tc_commit_el(uint32_t bar, uint32_t elected) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %1, 0;\n"
+               "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar), "r"(elected) : "memory");
+}
+// convergent TMA producer: same idea for cp.async.bulk.tensor (UTMALDG reads map address, coordinates, shared address
+// and barrier from uniform registers)
+__device__ __forceinline__ void mbar_expect_tx_el(uint32_t bar, uint32_t bytes, uint32_t elected) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %2, 0;\n@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n}"
+               ::"r"(bar), "r"(bytes), "r"(elected) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_el(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               uint32_t elected) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.b32 q, %7, 0;\n"
+               "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n}"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(elected) : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),

@@ -46,9 +46,13 @@ def img_cpad(c):
 
 
 # ----------------------------------------------------------------------------- small functional blocks (NHWC)
-def channel_rmsnorm(x, gamma):
-    """ref :224-232.  x NHWC; gamma (C,1,1)."""
+def channel_rmsnorm(x, gamma, fused=None):
+    """ref :224-232.  x NHWC; gamma (C,1,1).  ``fused`` (default: the fused-attention switch): one first-order
+    kernel pair instead of the any-order differentiable composition."""
     c = x.shape[-1]
+    fused = _COMPUTE["fused_attention"] if fused is None else fused
+    if fused and ops.rmsnorm_fused_ok(x):
+        return ops.rmsnorm_fused(x, gamma, c ** 0.5)
     ss = ops.rowdot(x, x)
     inv = ops.unary(U_INVNORM, ss)
     y = ops.scale_rows(x, inv)
@@ -94,8 +98,8 @@ class ChannelRMSNorm(nn.Module):
         self.scale = dim ** 0.5
         self.gamma = nn.Parameter(torch.ones(dim, 1, 1))
 
-    def forward_nhwc(self, x):
-        return channel_rmsnorm(x, self.gamma)
+    def forward_nhwc(self, x, fused=None):
+        return channel_rmsnorm(x, self.gamma, fused)
 
 
 # ----------------------------------------------------------------------------- AdaptiveConv2DMod (ref :315-409)
@@ -192,7 +196,7 @@ class SelfAttention(nn.Module):
         n, hh, ww, _ = x.shape
         seq, heads, d = hh * ww, self.heads, self.dim_head
         fused = _COMPUTE["fused_attention"] if fused is None else fused
-        xn = self.norm.forward_nhwc(x)
+        xn = self.norm.forward_nhwc(x, fused)
         q = ops.conv2d(xn, self.to_q.weight)
         v = ops.conv2d(xn, self.to_v.weight)
         k = ops.conv2d(xn, self.to_k.weight) if exists(self.to_k) else q
@@ -257,7 +261,7 @@ class SelfAttentionBlock(nn.Module):
 
     def forward_nhwc(self, x, fused=None):
         x = self.attn.forward_nhwc(x, residual=x, fused=fused)
-        h = self.ff[0].forward_nhwc(x)
+        h = self.ff[0].forward_nhwc(x, fused)
         h = ops.conv2d(h, self.ff[1].weight, self.ff[1].bias)
         h = ops.unary(U_GELU, h)
         return ops.conv2d(h, self.ff[3].weight, self.ff[3].bias, res=x)
@@ -524,9 +528,15 @@ class SimpleDecoder(nn.Module):
         x = ops.conv2d(fmap, self.net[0].weight, self.net[0].bias, pad=1)
         for blk in list(self.net)[1:]:
             x = ops.upsample2x_blur(x)
-            x = ops.conv2d(x, blk[1].weight, blk[1].bias, pad=1, act=1)
-        d = ops.axpby(1.0, x, -1.0, image_nhwc)
-        return ops.axpby(1.0 / d.numel(), ops.sum_all(ops.mul(d, d)))
+            wgt, bias = blk[1].weight, blk[1].bias
+            cpad = image_nhwc.shape[-1]
+            if wgt.shape[0] < cpad:          # image-like output: zero filters up to the padded channel count (tcgen05 tiles)
+                wgt = F.pad(wgt, (0, 0, 0, 0, 0, 0, 0, cpad - wgt.shape[0]))
+                bias = F.pad(bias, (0, cpad - bias.shape[0]))
+            x = ops.conv2d(x, wgt, bias, pad=1, act=1)
+        d = ops.axpby(1.0, x, -1.0, image_nhwc)                  # padded channels are 0 - 0
+        real_numel = d.numel() // d.shape[-1] * list(self.net)[-1][1].weight.shape[0]
+        return ops.axpby(1.0 / real_numel, ops.sum_all(ops.mul(d, d)))
 
 
 class Predictor(nn.Module):
@@ -728,8 +738,7 @@ class Discriminator(nn.Module):
             else:
                 x = ops.axpby(self.residual_scale, x, self.residual_scale, residual)
             if exists(decoder) and calc_aux_loss:                 # ref :1812-1827 (post-downsample x, first B rows)
-                img3 = images if images.shape[-1] == self.channels else images[..., : self.channels].contiguous()
-                aux_losses.append(decoder.forward_nhwc(x[:batch], img3))
+                aux_losses.append(decoder.forward_nhwc(x[:batch], images))   # images keep their zero pad channels
         x = ops.conv2d(x, self.to_logits[0].weight, self.to_logits[0].bias, pad=1)
         lw = self.to_logits[2].weight                                                   # (1, c*h*w) in (c h w) order
         c = x.shape[-1]

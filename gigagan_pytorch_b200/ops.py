@@ -1030,6 +1030,44 @@ def fused_attention(q, k, v, null_kv, heads, scale, l2=False):
 
 
 # ============================================================================= UnetUpsampler extras
+class RMSNormFn(Function):
+    """Fused ChannelRMSNorm over the last axis (first-order only; the composed rowdot/invnorm/broadcast chain in
+    modules.channel_rmsnorm is the any-order differentiable form used on gradient-penalty steps)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, scale):
+        x = _c(x)
+        C = x.shape[-1]
+        R = x.numel() // C
+        g = _c(gamma.detach().reshape(-1).float())
+        y = torch.empty_like(x)
+        inv = torch.empty(R, dtype=torch.float32, device=x.device)
+        call("gg_rmsnorm_fwd", _p(x), _p(g), _p(y), _p(inv), R, C, float(scale), _dt(x), _st())
+        ctx.save_for_backward(x, g, inv)
+        ctx.scale, ctx.gshape = float(scale), tuple(gamma.shape)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, g, inv = ctx.saved_tensors
+        gy = _c(gy)
+        C = x.shape[-1]
+        gx = torch.empty_like(x)
+        dg = torch.zeros(C, dtype=torch.float32, device=x.device)
+        call("gg_rmsnorm_bwd", _p(x), _p(g), _p(inv), _p(gy), _p(gx), _p(dg), x.numel() // C, C, ctx.scale, _dt(x), _st())
+        return gx, dg.reshape(ctx.gshape), None
+
+
+def rmsnorm_fused_ok(x):
+    c = x.shape[-1]
+    return c % 8 == 0 and c <= (1024 if x.dtype == torch.bfloat16 else 512)
+
+
+def rmsnorm_fused(x, gamma, scale):
+    return RMSNormFn.apply(x, gamma, scale)
+
+
 class MaxPool2Fn(Function):
     """2x2 max-pool of an NHWC map (first-order; the upsampler is never inside the gradient penalty)."""
 

@@ -26,7 +26,8 @@ int gg_version(void);
 /* 1 when this build contains the tcgen05/TMA kernels (always, for sm_100a). */
 int gg_has_tcgen05(void);
 /* bit 0: route every convolution to the FFMA kernels (testing the tcgen05 path against them);
- * bit 1: disable the thin-layer ring kernel (conv_thin_tc.cu) so those shapes take the generic tcgen05 kernel.
+ * bit 1: disable the thin-layer ring kernels (conv_thin_tc.cu) so those shapes take the generic tcgen05 kernels;
+ * bit 2: disable only the thin-layer weight-gradient kernel.
  * Returns old flags. */
 int gg_set_flags(int flags);
 
@@ -141,6 +142,17 @@ int gg_incr(int* p, gg_stream_t stream);
 int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream);
+/* Debug only: point the thin-layer convolution kernel (conv_thin_tc.cu) at a device buffer of 16384 uint64; CTA 0 then
+ * appends (tag, clock64) pairs per pipeline event (tools/trace_thin.py decodes them).  NULL switches tracing off. */
+int gg_debug_thin_trace(void* buf);
+
+/* ---- fused ChannelRMSNorm (gigagan_pytorch.py:224-232  F.normalize(x, dim=1) * sqrt(C) * gamma) over NHWC rows:
+ * y[r,c] = x[r,c] * inv[r] * s * gamma[c], inv[r] = 1/max(|x[r,:]|, 1e-12) (saved, fp32).  bwd writes gx and ADDS the
+ * gamma gradient into dgamma (fp32 [C], zero-filled by the caller).  First-order only; C % 8 == 0. */
+int gg_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, int64_t R, int C, float s, int dtype, gg_stream_t stream);
+int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, int64_t R, int C,
+                   float s, int dtype, gg_stream_t stream);
+
 /* Accumulate a kernel-layout fp32 weight gradient dw[O][KK][Ipad] (output of gg_conv2d_wgrad) into the master-layout
  * gradient buffer dst[O][I][KK] (+=): the .grad accumulation of nn.Conv2d weights (torch autograd AccumulateGrad under
  * gigagan_pytorch.py:2113 / :2207 accelerator.backward). */

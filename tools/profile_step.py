@@ -51,3 +51,14 @@ for name, gp in (("plain", False), ("gp", True)):
     print(f"===== {name} step: kernels/ops by launch count (count, self CUDA ms, name)")
     for r in rows:
         print(f"{r[0]:6d} {r[1]:9.3f}  {r[2]}")
+# where do torch's own copy / cast / accumulate kernels come from?  (input shapes of the plain step)
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
+    gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=False)
+    gan.train_generator_step(batch_size=B, dl_iter=it)
+    torch.cuda.synchronize()
+print("===== plain step: aten copy/cast/add/fill by input shape (count, CUDA ms, op, shapes)")
+rows = [(k.count, k.device_time_total / 1e3, k.key, str(k.input_shapes)[:110]) for k in prof.key_averages(group_by_input_shape=True)
+        if k.key in ("aten::copy_", "aten::_to_copy", "aten::add_", "aten::add", "aten::fill_", "aten::cat", "aten::contiguous",
+                     "aten::clone", "aten::zeros", "aten::zero_", "aten::mul", "aten::pad", "aten::constant_pad_nd")]
+for r in sorted(rows, key=lambda r: -r[1])[:40]:
+    print(f"{r[0]:6d} {r[1]:9.3f}  {r[2]:22s} {r[3]}")
