@@ -80,6 +80,7 @@ conv_thin_tc_kernel(const ThP p, const bf16* __restrict__ x, const bf16* __restr
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * TH_SLOTS + 4 + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * TH_SLOTS + 4 + TH_MAXACC + a); };
   uint32_t* tmem_slot = (uint32_t*)(gen_base + p.slots * p.slot_bytes + p.w_slots * p.w_bytes + 8 * (2 * TH_SLOTS + 4 + 2 * TH_MAXACC));
+  float* bias_sm = (float*)(tmem_slot + 4);                   // Cout <= 64 floats, filled before the role split
 
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -92,6 +93,7 @@ conv_thin_tc_kernel(const ThP p, const bf16* __restrict__ x, const bf16* __restr
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (bias && threadIdx.x >= 64 && threadIdx.x < 64 + p.Cout) bias_sm[threadIdx.x - 64] = bias[threadIdx.x - 64];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -144,12 +146,13 @@ conv_thin_tc_kernel(const ThP p, const bf16* __restrict__ x, const bf16* __restr
         const bool rowok = iy >= 0 && iy < p.H;
         const bf16* src_row = x + ((long)n * p.H + (rowok ? iy : 0)) * p.W * p.Cin;
         const uint32_t dst_row = base + s * p.slot_bytes;
-        const int pieces = 130 * p.planes;
-        for (int id = lane; id < pieces; id += 32) {
-          int j = id / p.planes, c8 = id - j * p.planes;
-          int xx = x0 - 1 + j;
-          bool ok = rowok && xx >= 0 && xx < p.W;
-          th_cp16(dst_row + c8 * TH_PLANE + j * 16, ok ? (const void*)(src_row + (long)xx * p.Cin + c8 * 8) : (const void*)x, ok ? 16 : 0);
+        for (int j = lane; j < 130; j += 32) {                       // one pixel per lane and pass, all its channel octets
+          const int xx = x0 - 1 + j;
+          const bool ok = rowok && xx >= 0 && xx < p.W;
+          const bf16* src = ok ? src_row + (long)xx * p.Cin : x;
+          const uint32_t dst = dst_row + j * 16;
+          const int nb = ok ? 16 : 0;
+          for (int c8 = 0; c8 < p.planes; ++c8) th_cp16(dst + c8 * TH_PLANE, src + (ok ? c8 * 8 : 0), nb);
         }
         th_commit_group();
         th_trace(10 + lw, c, 2);
@@ -239,10 +242,11 @@ conv_thin_tc_kernel(const ThP p, const bf16* __restrict__ x, const bf16* __restr
     const int q = warp & 3;
     const int m = q * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
+    int yy = r_begin % p.H, t = r_begin / p.H;
     for (int r = r_begin; r < r_end; ++r) {
-      const int yy = r % p.H, t = r / p.H;
       const int strip = t % p.strips, n = t / p.strips;
       const long pix = (((long)n * p.H + yy) * p.W + strip * 128 + m) * p.Cout;
+      if (++yy == p.H) { yy = 0; ++t; }
       th_trace(2 + q, r, 0);
       mbar_wait(tfull_bar(acc), acc_phase);
       th_trace(2 + q, r, 1);
@@ -256,7 +260,10 @@ conv_thin_tc_kernel(const ThP p, const bf16* __restrict__ x, const bf16* __restr
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]);
         if (bias) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_sm + c0 + j);
+            v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
+          }
         }
         if (p.act == 1) {
 #pragma unroll
@@ -308,7 +315,7 @@ int ggi_tc_conv_thin(const void* x, const void* w, const float* bias, const void
   p.planes = Cin / 8; p.slot_bytes = p.planes * TH_PLANE;
   p.tap_bytes = Cin * Cout * 2; p.w_bytes = KH * KW * p.tap_bytes; p.w_slots = per_sample_w ? 2 : 1;
   p.slots = Cin > 32 ? 6 : TH_SLOTS;
-  size_t smem = 128 + (size_t)p.slots * p.slot_bytes + (size_t)p.w_slots * p.w_bytes + 8 * (2 * TH_SLOTS + 4 + 2 * TH_MAXACC) + 16;
+  size_t smem = 128 + (size_t)p.slots * p.slot_bytes + (size_t)p.w_slots * p.w_bytes + 8 * (2 * TH_SLOTS + 4 + 2 * TH_MAXACC) + 16 + 64 * 4;
   if (smem > 200 * 1024) return 1;
   int per_sm = smem <= 100 * 1024 ? 2 : 1;
   int grid = tc_num_sms() * per_sm;
