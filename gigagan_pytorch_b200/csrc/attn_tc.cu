@@ -11,6 +11,7 @@
 
 #define ATC_THREADS 192
 #define ATC_FWD_THREADS 320   // forward: TMA warp + MMA warp + 8 softmax warps (two per TMEM lane quarter)
+#define ATC_BWD_THREADS 320   // backward kernels: same split (each softmax thread owns 64 of the 128 tile columns)
 #define ATC_D 64
 #define ATC_T 128          // queries per CTA == keys per tile
 
@@ -403,7 +404,7 @@ __device__ __forceinline__ void store_row16(bf16* dst, const float* f) {
   st_global_256(dst, o0, o1);
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+__global__ void __launch_bounds__(ATC_BWD_THREADS, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AtbP p,
                       const float* __restrict__ null_kv, const float* __restrict__ ksq, const bf16* __restrict__ o,
@@ -430,10 +431,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
       mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
-      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 4);
-      mbar_init(bar(DS_FULL + i), 4); mbar_init(bar(DS_EMPTY + i), 1);
+      mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), 8);
+      mbar_init(bar(DS_FULL + i), 8); mbar_init(bar(DS_EMPTY + i), 1);
     }
-    mbar_init(bar(DP_FULL), 1); mbar_init(bar(DP_EMPTY), 4); mbar_init(bar(DQ_FULL), 1);
+    mbar_init(bar(DP_FULL), 1); mbar_init(bar(DP_EMPTY), 8); mbar_init(bar(DQ_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -442,7 +443,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (threadIdx.x >= 64) {
     int t = threadIdx.x - 64;
-    if (p.has_null) null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
+    if (p.has_null && t < 128) null_sm[t] = t < 64 ? null_kv[h * ATC_D + t] : null_kv[(p.heads + h) * ATC_D + (t - 64)];
   }
   tc_fence_before();
   __syncthreads();
@@ -521,7 +522,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (j + 1 < T) issue_dP(j + 1);
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                            // TMEM lane quarter; two warps per quarter split the tile columns
+    const int hsel = (warp - 2) >> 2, cb = hsel * 64;
     const int r = q * 32 + lane;
     const int st = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -556,21 +558,23 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
     }
-    delta[srow] = dl;
+    if (hsel == 0) delta[srow] = dl;
     const float L2 = lse2[srow];
     float ds_null = 0.f, p_null = 0.f;
     if (p.has_null) {
       float tn = dot * p.c2 + (p.mode == 1 ? p.kb2 * kn2 : 0.f);
       p_null = fast_exp2(tn - L2);
       ds_null = p_null * (dpn - dl) * p.ls;
-      nullrow[srow] = ds_null;                         // consumed by attn_null_grad_kernel
-      nullrow[(long)p.B * p.heads * p.n + srow] = p_null;
+      if (hsel == 0) {
+        nullrow[srow] = ds_null;                       // consumed by attn_null_grad_kernel
+        nullrow[(long)p.B * p.heads * p.n + srow] = p_null;
+      }
     }
     for (int j = 0; j < T; ++j) {
       int s = j & 1;
       if (p.mode == 1) {
-        ksq_sm[s * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
-        named_bar_sync(1, 128);
+        if (st < 128) ksq_sm[s * 128 + st] = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2;
+        named_bar_sync(1, 256);
       }
       mbar_wait(bar(S_FULL + s), (j >> 1) & 1);
       mbar_wait(bar(DP_FULL), j & 1);
@@ -578,7 +582,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_after();
       uint8_t* dstile = gbase + (sDS - base) + s * 32768;
 #pragma unroll 2
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      for (int c0 = cb; c0 < cb + 64; c0 += 16) {
         uint32_t sv[16], dv[16];
         tc_ld16(tS + s * 128 + lane_addr + c0, sv);
         tc_ld16(tDP + lane_addr + c0, dv);
@@ -600,7 +604,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc_fence_after();
     bf16* dqrow = dq + grow * (long)(p.heads * ATC_D) + h * ATC_D;
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
+    for (int c0 = hsel * 32; c0 < hsel * 32 + 32; c0 += 16) {
       uint32_t v[16];
       tc_ld16(tDQ + lane_addr + c0, v);
       float f[16];
@@ -617,7 +621,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+__global__ void __launch_bounds__(ATC_BWD_THREADS, 1)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AtbP p,
                        const float* __restrict__ ksq, const float* __restrict__ lse2, const float* __restrict__ delta,
@@ -640,8 +644,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (threadIdx.x == 0) {
     mbar_init(bar(KV_FULL), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(bar(QO_FULL + i), 1); mbar_init(bar(QO_EMPTY + i), 1); }
-    mbar_init(bar(SDP_FULL), 1); mbar_init(bar(SDP_EMPTY), 4);
-    mbar_init(bar(PDS_FULL), 4); mbar_init(bar(PDS_EMPTY), 1); mbar_init(bar(OUT_FULL), 1);
+    mbar_init(bar(SDP_FULL), 1); mbar_init(bar(SDP_EMPTY), 8);
+    mbar_init(bar(PDS_FULL), 8); mbar_init(bar(PDS_EMPTY), 1); mbar_init(bar(OUT_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -650,13 +654,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
   {   // the two "ones" slabs (bf16 1.0 everywhere; swizzle-invariant)
     uint4 one4 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    for (int i = threadIdx.x; i < 2 * 1024; i += ATC_THREADS) {
+    for (int i = threadIdx.x; i < 2 * 1024; i += ATC_BWD_THREADS) {
       int buf = i >> 10, off = (i & 1023) << 4;
       *reinterpret_cast<uint4*>(gbase + (sQO - base) + buf * 32768 + 16384 + off) = one4;
     }
     fence_async_smem();
   }
-  if (threadIdx.x >= 64 && p.mode == 1) ksq_sm[threadIdx.x - 64] = ksq[(long)bh * p.n + kt * ATC_T + (threadIdx.x - 64)] * p.kb2;
+  if (threadIdx.x >= 64 && threadIdx.x < 192 && p.mode == 1) ksq_sm[threadIdx.x - 64] = ksq[(long)bh * p.n + kt * ATC_T + (threadIdx.x - 64)] * p.kb2;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -726,6 +730,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     }
   } else {
     const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2, cb = hsel * 64;   // two warps per TMEM lane quarter: columns [cb, cb + 64)
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint8_t* ptile = gbase + (sP - base);
@@ -737,7 +742,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(bar(PDS_EMPTY), (i & 1) ^ 1u);
       tc_fence_after();
 #pragma unroll 2
-      for (int c0 = 0; c0 < 128; c0 += 16) {
+      for (int c0 = cb; c0 < cb + 64; c0 += 16) {
         uint32_t sv[16], dv_[16];
         tc_ld16(tS + lane_addr + c0, sv);
         tc_ld16(tDP + lane_addr + c0, dv_);
@@ -763,26 +768,34 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const long grow = (long)b * p.n + kt * ATC_T + r;
     bf16* dvrow = dv + grow * (long)(p.heads * ATC_D) + h * ATC_D;
     bf16* dkrow = dk + grow * (long)(p.heads * ATC_D) + h * ATC_D;
-    float csum = 0.f;
-    float krow[64];
-    if (p.mode == 1) {
-      uint32_t v[16];
-      tc_ld16(tDK + lane_addr + 64, v);
-      csum = __uint_as_float(v[0]);
-      read_tile_row(gbase + (sK - base), r, krow);
-    }
+    if (hsel == 0) {                                   // first warp of the quarter stores dV, the second dK
 #pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 16) {
-      uint32_t v[16];
-      float f[16];
-      tc_ld16(tDV + lane_addr + c0, v);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        float f[16];
+        tc_ld16(tDV + lane_addr + c0, v);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
-      store_row16(dvrow + c0, f);
-      tc_ld16(tDK + lane_addr + c0, v);
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+        store_row16(dvrow + c0, f);
+      }
+    } else {
+      float csum = 0.f;
+      float krow[64];
+      if (p.mode == 1) {
+        uint32_t v[16];
+        tc_ld16(tDK + lane_addr + 64, v);
+        csum = __uint_as_float(v[0]);
+        read_tile_row(gbase + (sK - base), r, krow);
+      }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) - (p.mode == 1 ? csum * krow[c0 + e] : 0.f);
-      store_row16(dkrow + c0, f);
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        uint32_t v[16];
+        float f[16];
+        tc_ld16(tDK + lane_addr + c0, v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) - (p.mode == 1 ? csum * krow[c0 + e] : 0.f);
+        store_row16(dkrow + c0, f);
+      }
     }
   }
   tc_fence_before();
@@ -866,12 +879,12 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
   int grid = B * heads * p.tiles;
   size_t smem1 = 1024 + 166400 + 8 * 20 + 16, smem2 = 1024 + 197120 + 8 * 10 + 16;
   float* nullrow = delta_ws + (size_t)B * heads * nq;
-  attn_bwd_dq_tc_kernel<<<grid, ATC_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);
+  attn_bwd_dq_tc_kernel<<<grid, ATC_BWD_THREADS, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);
   if (p.has_null) {
     int rpb = 128;
     dim3 g2(gg_cdiv((long)B * nq, rpb), heads);
     attn_null_grad_kernel<<<g2, 256, 0, st>>>((const bf16*)q, (const bf16*)go, nullrow, null_kv, dnull_kv, B, nq, heads, q_rs, mode, rpb);
   }
-  attn_bwd_dkv_tc_kernel<<<grid, ATC_THREADS, smem2, st>>>(tmQ, tmK, tmV, tmDO, p, ksq_ws, lse2, delta_ws, (bf16*)dk, (bf16*)dv);
+  attn_bwd_dkv_tc_kernel<<<grid, ATC_BWD_THREADS, smem2, st>>>(tmQ, tmK, tmV, tmDO, p, ksq_ws, lse2, delta_ws, (bf16*)dk, (bf16*)dv);
   return gg_check_launch("attn_bwd_tc");
 }

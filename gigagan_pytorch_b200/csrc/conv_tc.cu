@@ -510,34 +510,43 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
   else if (stride == 2) { if (pad != 0 || KH != KW || KH > 2 || H != 2 * OH || W != 2 * OW) return 1; }
   else return 1;
   if ((OW & (OW - 1)) || (OH & (OH - 1)) || OW < 2 || OH < 2) return 1;
-  int nsub_a_ = Cout > 64 ? 2 : 1, nsub_b_ = ((Cin > 256 ? 256 : Cin) + 63) / 64;
-  int pix = 64;                                       // bigger pixel slabs for thin layers: ~48-64 KB per stage
-  while (pix < WG_PIX_MAX && (nsub_a_ + nsub_b_) * (pix * 2) * 128 <= 64 * 1024 && (long)OH * OW * (per_sample_w ? 1 : N) >= 4L * pix * 2) pix *= 2;
-  int Wt = OW < 16 ? OW : 16;
-  int Ht = OH < pix / Wt ? OH : pix / Wt;
-  int Nt = pix / (Wt * Ht);
-  if (Wt * Ht * Nt != pix) return 1;
-  if (per_sample_w && Nt != 1) return 1;
-  if (N % Nt) return 1;                               // zero-filled phantom images would be harmless, keep it exact
   if (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) return 1;
   WgP p;
   p.N = N; p.OH = OH; p.OW = OW; p.Cout = Cout; p.Cin = Cin; p.taps = KH * KW; p.KW = KW; p.pad = pad; p.stride = stride;
+  p.co_blocks = (Cout + 127) / 128;
+  p.nsub_a = Cout > 64 ? 2 : 1;
+  p.per_sample = per_sample_w;
+  // Work decomposition: item = (co block, ci block of Ntile channels, tap, [image], pixel-range split).  The widest ci
+  // block (256) is the most efficient MMA shape, but a layer with few pixels and few (co, ci, tap) items cannot be
+  // split into enough CTAs along the pixel axis (every split pays a 128 x Ntile fp32 red.add epilogue worth ~60-100
+  // pipeline stages): such layers (stride-2 / 1x1 convolutions of the 8^2-32^2 maps) narrow the ci block instead.
+  int best_items = -1, base_items = 0, splits = 1, pix = 64, Wt = 0, Ht = 0, Nt = 0;
+  for (int ntile = Cin > 256 ? 256 : Cin; ntile >= 64 || ntile == Cin; ntile /= 2) {
+    if (Cin % ntile || (ntile > 64 && ntile % 64)) { if (ntile <= 64) break; continue; }
+    int nsub_b_ = (ntile + 63) / 64;
+    int pix_ = 64;                                    // bigger pixel slabs for thin layers: ~48-64 KB per stage
+    while (pix_ < WG_PIX_MAX && (p.nsub_a + nsub_b_) * (pix_ * 2) * 128 <= 64 * 1024 && (long)OH * OW * (per_sample_w ? 1 : N) >= 4L * pix_ * 2) pix_ *= 2;
+    int Wt_ = OW < 16 ? OW : 16;
+    int Ht_ = OH < pix_ / Wt_ ? OH : pix_ / Wt_;
+    int Nt_ = pix_ / (Wt_ * Ht_);
+    if (Wt_ * Ht_ * Nt_ != pix_ || (per_sample_w && Nt_ != 1) || N % Nt_) { if (ntile <= 64) break; continue; }
+    int base_ = p.co_blocks * (Cin / ntile) * p.taps * (per_sample_w ? N : 1);
+    int ntiles_ = per_sample_w ? (OW / Wt_) * (OH / Ht_) : (OW / Wt_) * (OH / Ht_) * (N / Nt_);
+    int splits_ = 1;
+    int min_stages = ntile * 3 / 8 > 8 ? ntile * 3 / 8 : 8;          // epilogue cost scales with the accumulator width
+    while (base_ * splits_ < 2 * tc_num_sms() && ntiles_ / (splits_ * 2) >= min_stages) splits_ *= 2;
+    int items_ = base_ * splits_;
+    if (items_ > best_items) {
+      best_items = items_; p.Ntile = ntile; base_items = base_; splits = splits_; pix = pix_; Wt = Wt_; Ht = Ht_; Nt = Nt_;
+    }
+    if (items_ >= tc_num_sms() || ntile <= 64) break;                // enough CTAs: keep the widest block that fills the GPU
+  }
+  if (best_items < 0) return 1;
   p.Wt = Wt; p.Ht = Ht; p.Nt = Nt; p.tiles_w = OW / Wt; p.tiles_h = OH / Ht; p.tiles_n = N / Nt;
   p.pix_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   p.tiles_per_image = p.tiles_w * p.tiles_h;
-  p.co_blocks = (Cout + 127) / 128;
-  p.Ntile = Cin > 256 ? 256 : Cin;
   p.ci_blocks = Cin / p.Ntile;
-  p.nsub_a = Cout > 64 ? 2 : 1;
   p.nsub_b = (p.Ntile + 63) / 64;
-  p.per_sample = per_sample_w;
-  int base_items = p.co_blocks * p.ci_blocks * p.taps * (per_sample_w ? N : 1);
-  int ntiles = per_sample_w ? p.tiles_per_image : p.pix_tiles;
-  // split the pixel reduction only while every item keeps a long MMA chain: the fp32 red.add epilogue of one item
-  // (128 x Ntile values) costs as much as ~60-100 pipeline stages, so short items must not be split further
-  int splits = 1;
-  int min_stages = p.Ntile * 3 / 8 > 8 ? p.Ntile * 3 / 8 : 8;       // epilogue cost scales with the accumulator width
-  while (base_items * splits < 2 * tc_num_sms() && ntiles / (splits * 2) >= min_stages) splits *= 2;
   p.splits = splits;
   p.total_items = base_items * splits;
   p.pix = pix;
