@@ -92,6 +92,9 @@ def real_batch(step, world, rank, batch, size, pin=False):
 
 # ------------------------------------------------------------------------------------------- reference arm (CPU)
 CPU_THREADS_CAP = 32
+# DRAM traffic of the dominant kernel class per launch, from the ncu launch list of one plain step
+# (profiles/r01_ncu_step_launches.txt: 503 x 22.26 MB conv_fprop_tc + 34 x 45.09 MB conv_thin_tc)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 23.7e6
 
 
 def _oracle_trainer(size):
@@ -279,8 +282,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     tc = prof.summary()
     roof = {"bound": "tensor", "achieved": tc["tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
-            "frac": tc["tflops"] / pk["tflops"] if tc["tflops"] else None, "traffic": None,
-            "kernel": "conv_fprop_tc_kernel (tcgen05 implicit GEMM, fprop+dgrad)", "launches": tc["launches"],
+            "frac": tc["tflops"] / pk["tflops"] if tc["tflops"] else None, "traffic": NCU_CONV_DRAM_BYTES_PER_LAUNCH,
+            "traffic_source": "ncu dram__bytes_read+write per launch, averaged over the same launches of one plain "
+                              "step (profiles/r01_ncu_step_launches.txt)",
+            "kernel": "convolution fprop+dgrad launches of one plain step: conv_fprop_tc_kernel (tcgen05 implicit GEMM) "
+                      "+ conv_thin_tc_kernel (128^2/256^2 layers)", "launches": tc["launches"],
             "kernel_ms_per_step": tc["ms"], "peak_source": pk["src"],
             "step_useful_tflops": FLOP_PER_IMG_CYCLE * B * args.steps / (ms / 1e3) / 1e12 / 1.0}
 

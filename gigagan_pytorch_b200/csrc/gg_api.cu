@@ -188,6 +188,9 @@ int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const vo
   return ggi_rmsnorm_bwd(x, gamma, inv, gy, gx, dgamma, (long)R, C, s, dtype, ST);
 }
 int gg_debug_thin_trace(void* buf) { return ggi_debug_thin_trace((unsigned long long*)buf); }
+int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int dtype, gg_stream_t stream) {
+  return ggi_lrelu_bwd_bias(y, gy, out, dbias, (long)R, C, dtype, ST);
+}
 int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, gg_stream_t stream) {
   return ggi_wgrad_sink(dw, dst, O, I, KK, Ipad, ST);
 }

@@ -954,6 +954,49 @@ int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, 
   return gg_check_launch("wgrad_sink");
 }
 
+// ------------------------------------------------------------------ LeakyReLU backward fused with the bias gradient
+// out = gy * lrelu'(y)  and  dbias[c] += sum_rows out[r, c]  in ONE pass over the activation gradient (the separate
+// column reduction re-read the whole map).  nvec = C / V channel vectors (a power of two <= 256): the 256 threads tile
+// (256 / nvec row lanes) x nvec vectors, every thread keeps its V column sums in registers.
+template <typename T>
+__global__ void lrelu_bwd_bias_kernel(const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ out,
+                                      float* __restrict__ dbias, long R, int C, int nvec) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sm[256 * V];
+  const int t = threadIdx.x, cv = t & (nvec - 1), rl = t / nvec, lanes = 256 / nvec;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (long r = (long)blockIdx.x * lanes + rl; r < R; r += (long)gridDim.x * lanes) {
+    float yv[V], gv[V], ov[V];
+    ldv(y + r * C + cv * V, yv);
+    ldv(gy + r * C + cv * V, gv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { ov[k] = yv[k] > 0.f ? gv[k] : 0.2f * gv[k]; acc[k] += ov[k]; }
+    stv(out + r * C + cv * V, ov);
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) sm[rl * (nvec * V) + cv * V + k] = acc[k];
+  __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    float sres = 0.f;
+    for (int i = 0; i < lanes; ++i) sres += sm[i * C + c];
+    atomicAdd(dbias + c, sres);
+  }
+}
+// returns 1 when the shape is not covered (caller composes unary + dot_sc)
+int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int dtype, cudaStream_t st) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V || !al16(y) || !al16(gy) || !al16(out)) return 1;
+  int nvec = C / V;
+  if (nvec > 256 || (nvec & (nvec - 1))) return 1;
+  cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
+  int lanes = 256 / nvec;
+  int blocks = gg_blocks((R + lanes - 1) / lanes * 256, 256, 148 * 8);
+  GG_DISPATCH(dtype, (lrelu_bwd_bias_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, (const T*)gy, (T*)out, dbias, R, C, nvec)));
+  return gg_check_launch("lrelu_bwd_bias");
+}
+
 // ------------------------------------------------------------------ fused ChannelRMSNorm (gigagan_pytorch.py:224-232)
 // y[r,c] = x[r,c] * inv[r] * s * gamma[c],  inv[r] = 1 / max(||x[r,:]||, 1e-12);  one warp per pixel row, 16-byte
 // accesses, x read twice (second time from L1/L2).  First-order fast path of the composed rowdot/invnorm/bcast chain.

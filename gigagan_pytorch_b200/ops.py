@@ -108,6 +108,7 @@ class WeightBank:
         self.bwd = torch.empty(max(bo, 8), dtype=dtype, device=dev)
         self.entries = torch.tensor(entries, dtype=torch.int64, device=dev)
         self.chunks = torch.tensor(chunks, dtype=torch.int32, device=dev)
+        self.dirty = True                  # layouts not built yet / parameters changed since the last refresh
 
     def refresh(self):
         call("gg_weight_prep_multi", _p(self.flat), _p(self.entries), _p(self.chunks), self.chunks.shape[0],
@@ -142,20 +143,22 @@ def _bank_lookup(weight, cin, dtype):
 def prep_weight(weight, cin, dtype):
     """fp32 master (O,I,KH,KW) -> kernel layout (O,KH,KW,cin) in the compute dtype, zero-padding I up to cin."""
     base = weight._base if weight._base is not None else weight
+    ver = -1 if base.is_inference() else base._version     # inference-mode temporaries carry no version: never cached
     key = (weight.data_ptr(), tuple(weight.shape), cin, dtype, "f")
     hit = _WCACHE.get(key)
-    if hit is not None and hit[1] is base and hit[2] == base._version:     # same storage owner, not modified since
+    if hit is not None and hit[1] is base and hit[2] == ver and ver >= 0:  # same storage owner, not modified since
         return hit[0]
     r = _bank_lookup(weight, cin, dtype)
     if r is not None:
-        _WCACHE[key] = (r[0], base, base._version)
+        _WCACHE[key] = (r[0], base, ver)
         _WCACHE[(r[0].data_ptr(), tuple(r[0].shape), r[0].dtype, "t")] = (r[0], r[1])
         return r[0]
     w = weight.detach().permute(0, 2, 3, 1)
     if w.shape[-1] != cin:
         w = torch.nn.functional.pad(w, (0, cin - w.shape[-1]))
     w = w.to(dtype).contiguous()
-    _WCACHE[key] = (w, base, base._version)
+    if ver >= 0:
+        _WCACHE[key] = (w, base, ver)
     return w
 
 
@@ -276,16 +279,20 @@ class Conv2dFn(Function):
         if g.gain != 1.0:
             gy = axpby(g.gain, gy)
         gres = gy if ctx.has_res else None
-        if g.act:
-            gy = Unary1Fn.apply(U_LRELU, y, gy)
         gx = gw = gb = None
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads()
+        if g.act:
+            if want_gb and not torch.is_grad_enabled() and _lrelu_bias_fusable(y):
+                gy, gb = _lrelu_bwd_bias(y, gy)             # one pass: activation gradient + bias gradient
+            else:
+                gy = Unary1Fn.apply(U_LRELU, y, gy)
         pg = g.plain()
         if ctx.needs_input_grad[0]:
             gx = ConvDgradFn.apply(gy, weight, pg, tuple(x.shape), ctx.master)
         if ctx.needs_input_grad[1] and not _skip_param_grads():
             if not (ctx.master and _wgrad_to_sink(x, gy, pg, weight)):
                 gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
-        if ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads():
+        if want_gb and gb is None:
             gb = dot_sc(gy, None, gy.numel() // gy.shape[-1], 1).reshape(-1)
         return gx, gw, gb, gres, None, None
 
@@ -310,6 +317,21 @@ class ConvDgradFn(Function):
             if not (ctx.master and _wgrad_to_sink(ggx, gy, g, weight)):
                 d_w = ConvWgradFn.apply(ggx, gy, g, weight if ctx.master else None)
         return d_gy, d_w, None, None, None
+
+
+def _lrelu_bias_fusable(y):
+    nvec = y.shape[-1] // (8 if y.dtype == torch.bfloat16 else 4)
+    return y.shape[-1] % (8 if y.dtype == torch.bfloat16 else 4) == 0 and 0 < nvec <= 256 and (nvec & (nvec - 1)) == 0
+
+
+def _lrelu_bwd_bias(y, gy):
+    """terminal backward of a bias + LeakyReLU conv epilogue: (gy * lrelu'(y), column sums of it)"""
+    y, gy = _c(y), _c(gy)
+    C = y.shape[-1]
+    out = torch.empty_like(gy)
+    gb = torch.empty(C, dtype=torch.float32, device=y.device)
+    call("gg_lrelu_bwd_bias", _p(y), _p(gy), _p(out), _p(gb), y.numel() // C, C, _dt(y), _st())
+    return out, gb
 
 
 def _wgrad_to_sink(x, gy, geom, weight):

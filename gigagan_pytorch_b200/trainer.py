@@ -144,6 +144,8 @@ class FlatAdamW:
 
     def step(self, grad_scale=1.0):
         ops.clear_weight_cache()
+        if getattr(self, "bank", None) is not None:
+            self.bank.dirty = True
         if self.flat.device.type != "cuda":
             raise RuntimeError("FlatAdamW.step needs the parameters on the GPU (no CPU path)")
         call("gg_incr", _p(self.step_t), _st())
@@ -267,10 +269,12 @@ class GigaGAN(nn.Module):
             self.D_opt = FlatAdamW(self.D, lr=self.learning_rate, betas=self.betas)
             self._banks = []
             if compute_dtype() == torch.bfloat16:
-                for opt in (self.G_opt, self.D_opt):
+                for opt, mod in ((self.G_opt, self.G), (self.D_opt, self.D)):
                     bank = ops.WeightBank(opt.flat, opt.params, torch.bfloat16, img_cpad)
                     ops.register_weight_bank(bank)
                     self._banks.append(bank)
+                    opt.bank = bank                  # the optimiser marks it stale after every parameter update
+                    mod.register_load_state_dict_post_hook(lambda m, keys, bank=bank: setattr(bank, "dirty", True))
 
     def create_ema_generator(self, update_every=10, update_after_step=100, decay=0.995):
         if not self.is_main:
@@ -304,6 +308,7 @@ class GigaGAN(nn.Module):
     def generate(self, *args, **kwargs):
         model = self.G_ema if self.has_ema_generator else self.G
         model.eval()
+        self._begin_work(self._stale_banks())       # kernel-layout weights follow the latest optimiser step
         return model(*args, **kwargs)
 
     def save(self, path, overwrite=True):
@@ -419,12 +424,22 @@ class GigaGAN(nn.Module):
         self.graph_kernel_launches += n
         return outs
 
-    def _begin_work(self):
-        """start of a fwd+bwd pass over fresh parameters: drop cached layouts, re-lay-out all conv weights (1 launch
-        per model)."""
+    def _stale_banks(self):
+        """host bookkeeping BEFORE a (possibly graph-replayed) pass: which kernel-layout weight banks must be rebuilt
+        (those whose parameters changed since their last refresh); part of the CUDA-graph key."""
+        banks = getattr(self, "_banks", [])
+        mask = tuple(bool(b.dirty) for b in banks)
+        for b in banks:
+            b.dirty = False
+        return mask
+
+    def _begin_work(self, stale):
+        """start of a fwd+bwd pass: drop cached layouts, re-lay-out the conv weights of every model whose parameters
+        changed (1 launch per model; in the alternating D/G schedule that is the model the previous half-step updated)."""
         ops.clear_weight_cache()
-        for bank in getattr(self, "_banks", []):
-            bank.refresh()
+        for bank, d in zip(getattr(self, "_banks", []), stale):
+            if d:
+                bank.refresh()
 
     def _stage_real(self, real):
         if self._real_buf is None or self._real_buf.shape != real.shape:
@@ -455,9 +470,10 @@ class GigaGAN(nn.Module):
         acc = None
         if grad_accum_every == 1:
             self._stage_real(self._next_images(dl_iter))
+            stale = self._stale_banks()
 
             def work():
-                self._begin_work()
+                self._begin_work(stale)
                 self.D_opt.zero_grad()
                 real = self._real_buf.detach()
                 noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
@@ -465,9 +481,9 @@ class GigaGAN(nn.Module):
                 total.backward(inputs=d_params)
                 return [p.detach() for p in parts]
 
-            acc = self._run(("D", bool(apply_gradient_penalty), bool(calc_multiscale_loss)), work)
+            acc = self._run(("D", bool(apply_gradient_penalty), bool(calc_multiscale_loss), stale), work)
         else:
-            self._begin_work()
+            self._begin_work(self._stale_banks())
             self.D_opt.zero_grad()
             for _ in range(grad_accum_every):
                 real = self._next_images(dl_iter)
@@ -497,17 +513,19 @@ class GigaGAN(nn.Module):
             if self.train_upsampler:                       # ref generate_kwargs (:2196): a fresh real batch per G step
                 self._stage_real(self._next_images(dl_iter))
             if grad_accum_every == 1:
+                stale = self._stale_banks()
+
                 def work():
-                    self._begin_work()
+                    self._begin_work(stale)
                     self.G_opt.zero_grad()
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
                     total, parts = self._g_objective(noise, calc_multiscale_loss)
                     total.backward(inputs=g_params)
                     return [p.detach() for p in parts]
 
-                acc = self._run(("G", batch_size, bool(calc_multiscale_loss)), work)
+                acc = self._run(("G", batch_size, bool(calc_multiscale_loss), stale), work)
             else:
-                self._begin_work()
+                self._begin_work(self._stale_banks())
                 self.G_opt.zero_grad()
                 for _ in range(grad_accum_every):
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)

@@ -153,6 +153,12 @@ int gg_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, int64
 int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, int64_t R, int C,
                    float s, int dtype, gg_stream_t stream);
 
+/* Backward of the conv epilogue "bias + LeakyReLU(0.2)" (nn.Conv2d followed by leaky_relu, gigagan_pytorch.py:1608-1620,
+ * :1454-1470): out = gy * lrelu'(y) and dbias[c] = sum over rows of out (fp32, overwritten) in one pass.
+ * Returns 1 (nothing done) when C / (16-byte vector) is not a power of two <= 256: the caller then composes
+ * gg_pw_unary(level 1) + gg_red_dot_sc. */
+int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int dtype, gg_stream_t stream);
+
 /* Accumulate a kernel-layout fp32 weight gradient dw[O][KK][Ipad] (output of gg_conv2d_wgrad) into the master-layout
  * gradient buffer dst[O][I][KK] (+=): the .grad accumulation of nn.Conv2d weights (torch autograd AccumulateGrad under
  * gigagan_pytorch.py:2113 / :2207 accelerator.backward). */

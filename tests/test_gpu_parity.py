@@ -680,3 +680,57 @@ def test_dot_sc_channel_reductions(dtype, tol, c, ns, p):
     assert relmax(out.view(ns, c), ref) < tol
     out1 = ops.dot_sc(a, None, p, ns)
     assert relmax(out1.view(ns, c), a.float().view(reps, ns, p, c).sum(dim=(0, 2))) < tol
+
+
+def test_generate_after_training_uses_the_updated_weights():
+    """the bf16 kernel-layout weight banks are rebuilt lazily (only for the model whose parameters changed): sampling
+    right after an optimiser step must see the new generator weights, i.e. equal a bank-less generator with the same
+    state_dict"""
+    import gigagan_pytorch_b200 as g
+    g.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(0)
+    gen = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=64, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    disc = dict(dim_capacity=2, dim_max=16, image_size=64, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(32, 16, 8))
+    gan = g.GigaGAN(generator=gen, discriminator=disc, amp=True, mixed_precision_type="bf16", log_steps_every=10 ** 9,
+                    create_ema_generator_at_init=False).to(dev())
+    reals = [torch.rand(4, 3, 64, 64, generator=torch.Generator().manual_seed(10 + s)).to(dev()) for s in range(4)]
+
+    class Pool:
+        batch_size = 4
+
+        def __iter__(self):
+            return iter(reals)
+
+    gan.set_dataloader(Pool())
+    gan(steps=3)
+    z = rn(7, 2, 16).to(dev())
+    torch.manual_seed(11)
+    a = gan.generate(noise=z)
+    fresh = g.Generator(**gen).to(dev())
+    fresh.load_state_dict(gan.G.state_dict())
+    fresh.eval()
+    torch.manual_seed(11)
+    b = fresh(noise=z)
+    assert relmax(a, b) < 1e-6
+    g.set_compute_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("co", [16, 32, 512])
+def test_conv_bias_lrelu_backward_fused_matches_composed(dtype, tol, co):
+    """first-order backward of conv + bias + LeakyReLU: the fused activation-gradient / bias-gradient kernel against
+    the composed (any-order differentiable) route that create_graph=True selects"""
+    from gigagan_pytorch_b200 import ops
+    x = rn(1, 2, 12, 12, 16).to(dev()).to(dtype)
+    gy = rn(4, 2, 12, 12, co).to(dev()).to(dtype)
+    res = []
+    for cg in (False, True):
+        w = (rn(2, co, 16, 3, 3) * 0.1).to(dev()).requires_grad_()
+        b = rn(3, co).to(dev()).requires_grad_()
+        xx = x.clone().requires_grad_()
+        y = ops.conv2d(xx, w, b, pad=1, act=1)
+        res.append(torch.autograd.grad(y, (xx, w, b), gy, create_graph=cg))
+    for a, b_ in zip(*res):
+        assert relmax(a.detach(), b_.detach()) < tol
