@@ -93,8 +93,8 @@ def real_batch(step, world, rank, batch, size, pin=False):
 # ------------------------------------------------------------------------------------------- reference arm (CPU)
 CPU_THREADS_CAP = 32
 # DRAM traffic of the dominant kernel class per launch, from the ncu launch list of one plain step
-# (profiles/r01_ncu_step_launches.txt: 503 x 22.26 MB conv_fprop_tc + 34 x 45.09 MB conv_thin_tc)
-NCU_CONV_DRAM_BYTES_PER_LAUNCH = 23.7e6
+# (profiles/r01_ncu_step_launches.txt: 503 x 22.23 MB conv_fprop_tc + 36 x 43.18 MB conv_thin_tc)
+NCU_CONV_DRAM_BYTES_PER_LAUNCH = 23.6e6
 
 
 def _oracle_trainer(size):
