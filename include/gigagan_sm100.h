@@ -142,8 +142,9 @@ int gg_incr(int* p, gg_stream_t stream);
 int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream);
-/* Debug only: point the thin-layer convolution kernel (conv_thin_tc.cu) at a device buffer of 16384 uint64; CTA 0 then
- * appends (tag, clock64) pairs per pipeline event (tools/trace_thin.py decodes them).  NULL switches tracing off. */
+/* Debug only: point the thin-layer convolution kernel (conv_thin_tc.cu) at a device buffer of 32*64*8 uint64; CTA 0 then
+ * stores clock64 at slot ((role*64 + row%64)*8 + stage) per pipeline event (tools/trace_thin.py decodes them).
+ * NULL switches tracing off. */
 int gg_debug_thin_trace(void* buf);
 
 /* ---- fused ChannelRMSNorm (gigagan_pytorch.py:224-232  F.normalize(x, dim=1) * sqrt(C) * gamma) over NHWC rows:

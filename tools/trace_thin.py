@@ -12,7 +12,7 @@ b = torch.randn(co, device=dev)
 g = ops.ConvGeom(3, 3, 1, 1, False, act=1)
 for _ in range(3):
     y = ops._conv_fprop_raw(x, w, b, None, g, co)
-buf = torch.zeros(16384, dtype=torch.int64, device=dev)
+buf = torch.zeros(32 * 64 * 8, dtype=torch.int64, device=dev)
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=dev)
 flush.zero_()
 L = _lib.lib()
@@ -22,10 +22,12 @@ torch.cuda.synchronize()
 L.gg_debug_thin_trace(ctypes.c_void_p(0))
 t = buf.cpu().tolist()
 ev = []
-for i in range(0, 16384, 2):
-    if t[i + 1] == 0:
-        break
-    ev.append((t[i] >> 40, (t[i] >> 8) & 0xFFFFFFFF, t[i] & 0xFF, t[i + 1]))
+for role in range(32):
+    for row in range(64):
+        for stage in range(8):
+            v = t[(role * 64 + row) * 8 + stage]
+            if v:
+                ev.append((role, row, stage, v))
 t0 = min(e[3] for e in ev)
 GHZ = 1.9
 by = collections.defaultdict(dict)
@@ -34,7 +36,7 @@ for role, row, stage, clk in ev:
 print(f"{len(ev)} events; roles: 1 = MMA (0 start,1 rows full,2 acc free,3 issued), 2-5 = epilogue (0 wait,1 acc full,2 stored), "
       f"10+ = loader warp (0 wait slot,1 slot free,2 issued,3 landed,4 fenced)")
 rows_m = sorted(r for (role, r) in by if role == 1)
-base_row = rows_m[0]
+base_row = 0
 print("row   loader: free  issued landed fenced |  MMA: start full  accfree issued | epi(w2): wait  full  stored")
 lo = {}
 for (role, c), st in by.items():
