@@ -151,3 +151,121 @@ def test_unet_upsampler():
     torch.testing.assert_close(o, r, **TOL)
     for a, b in zip(os_, rs):
         torch.testing.assert_close(a, b, **TOL)
+
+
+# ------------------------------------------------------------------ text-conditioned path
+def _no_clip(ref, dim_latent=32):
+    """OpenClipAdapter stand-in: with pre-encoded tokens only `.dim_latent` is consulted (the CLIP tower is third-party)."""
+    from gigagan_pytorch.open_clip import OpenClipAdapter
+
+    class NoClip(OpenClipAdapter):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+
+        @property
+        def dim_latent(self):
+            return dim_latent
+
+    return NoClip()
+
+
+TE = dict(dim=24, depth=2, dim_head=8, heads=2)
+G7 = dict(dim_capacity=2, style_network=dict(dim=16, depth=2, dim_text_latent=24), image_size=32, dim_max=16, dim_latent=16,
+          num_skip_layers_excite=2, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2,
+          cross_attn_resolutions=(16, 8), cross_attn_dim_head=8, cross_attn_heads=2, unconditional=False)
+D7 = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, attn_resolutions=(8,), attn_dim_head=8,
+          attn_heads=2, multiscale_input_resolutions=(16, 8), unconditional=False)
+
+
+def _encodings():
+    enc = rn(5, 3, 7, 32)
+    enc[1, 4:] = 0.
+    enc[2, 1:] = 0.
+    return enc
+
+
+def test_text_encoder_and_cross_attention():
+    ref = import_reference()
+    from gigagan_pytorch.gigagan_pytorch import CrossAttentionBlock, TextEncoder
+    torch.manual_seed(0)
+    te = TextEncoder(clip=_no_clip(ref), **TE)
+    enc = _encodings()
+    g_ref, f_ref, m_ref = te(text_encodings=enc)
+    g, f, m = O.text_encoder(dict(te.state_dict()), enc, TE["depth"], TE["heads"], TE["dim_head"])
+    assert torch.equal(m, m_ref)
+    torch.testing.assert_close(g, g_ref, **TOL)
+    torch.testing.assert_close(f, f_ref, **TOL)
+    torch.manual_seed(1)
+    blk = CrossAttentionBlock(16, dim_context=24, dim_head=8, heads=2)
+    x = rn(6, 3, 16, 8, 8)
+    torch.testing.assert_close(O.cross_attention_block(dict(blk.state_dict()), x, f_ref.detach(), m_ref, 2, 8),
+                               blk(x, f_ref.detach(), m_ref), **TOL)
+
+
+def test_text_conditional_generator_and_discriminator():
+    ref = import_reference()
+    from gigagan_pytorch.gigagan_pytorch import TextEncoder
+    enc = _encodings()
+    torch.manual_seed(0)
+    G = ref.Generator(text_encoder=TextEncoder(clip=_no_clip(ref), **TE), **G7)
+    plan = O.generator_plan(32, 2, 16, 16, 2, (16,), 2, 2, 8, unconditional=False, cross_attn_resolutions=(16, 8),
+                            cross_attn_heads=2, cross_attn_dim_head=8)
+    sd = dict(G.state_dict())
+    z = rn(1, 3, 16)
+    torch.manual_seed(2)
+    rgb_ref, rgbs_ref = G(noise=z, text_encodings=enc, return_all_rgbs=True)
+    gt, ft, tm = O.text_encoder(O._sub(sd, "text_encoder."), enc, TE["depth"], TE["heads"], TE["dim_head"])
+    torch.manual_seed(2)
+    rgb, rgbs = O.generator_forward(sd, plan, z, style_depth=2, return_all_rgbs=True, global_text_tokens=gt,
+                                    fine_text_tokens=ft, text_mask=tm)
+    torch.testing.assert_close(rgb, rgb_ref, **TOL)
+    for a, b in zip(rgbs, rgbs_ref):
+        torch.testing.assert_close(a, b, **TOL)
+    torch.manual_seed(1)
+    D = ref.Discriminator(text_encoder=TextEncoder(clip=_no_clip(ref), **TE), **D7)
+    dplan = O.discriminator_plan(32, 2, 16, 3, (8,), (16, 8), 1, (8,), num_skip_layers_excite=2, attn_heads=2, attn_dim_head=8)
+    sd = dict(D.state_dict())
+    img = torch.rand(3, 3, 32, 32, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        lo_ref, ms_ref, _ = D(img, D.real_images_to_rgbs(img), text_encodings=enc, calc_aux_loss=False)
+        emb, _, _ = O.text_encoder(O._sub(sd, "text_encoder."), enc, TE["depth"], TE["heads"], TE["dim_head"])
+        lo, ms, _ = O.discriminator_forward(sd, dplan, img, O.real_images_to_rgbs(img, dplan), True, False, text_embeds=emb)
+    torch.testing.assert_close(lo, lo_ref, **TOL)
+    for a, b in zip(ms, ms_ref):
+        torch.testing.assert_close(a, b, **TOL)
+
+
+# ------------------------------------------------------------------ drop-in layout: same keys, shapes and seeded values
+@pytest.mark.parametrize("which", ["g64", "g256", "d64", "d256", "g_text", "d_text", "unet"])
+def test_dropin_classes_reproduce_reference_state_dict(which):
+    """the product classes (constructed on CPU; no kernels involved) create the reference's parameters in the
+    reference's order: identical state_dict keys, shapes and - with the same manual_seed - identical initial values"""
+    ref = import_reference()
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch.gigagan_pytorch import TextEncoder
+    readme_g = dict(dim_capacity=8, style_network=dict(dim=64, depth=4), image_size=256, dim_max=512, num_skip_layers_excite=4,
+                    unconditional=True)
+    readme_d = dict(dim_capacity=16, dim_max=512, image_size=256, num_skip_layers_excite=4, unconditional=True)
+    mine_te = dict(TE, clip_dim_latent=32)
+    make = {
+        "g64": (lambda: ref.Generator(**GCFG), lambda: g.Generator(**GCFG)),
+        "g256": (lambda: ref.Generator(**readme_g), lambda: g.Generator(**readme_g)),
+        "d64": (lambda: ref.Discriminator(**DCFG), lambda: g.Discriminator(**DCFG)),
+        "d256": (lambda: ref.Discriminator(**readme_d), lambda: g.Discriminator(**readme_d)),
+        "g_text": (lambda: ref.Generator(text_encoder=TextEncoder(clip=_no_clip(ref), **TE), **G7),
+                   lambda: g.Generator(text_encoder=g.TextEncoder(**mine_te), **G7)),
+        "d_text": (lambda: ref.Discriminator(text_encoder=TextEncoder(clip=_no_clip(ref), **TE), **D7),
+                   lambda: g.Discriminator(text_encoder=g.TextEncoder(**mine_te), **D7)),
+        "unet": (lambda: ref.UnetUpsampler(dim=8, image_size=64, input_image_size=16, style_network=dict(dim=64, depth=4),
+                                           unconditional=True),
+                 lambda: g.UnetUpsampler(dim=8, image_size=64, input_image_size=16, style_network=dict(dim=64, depth=4),
+                                         unconditional=True)),
+    }[which]
+    torch.manual_seed(0)
+    a = make[0]().state_dict()
+    torch.manual_seed(0)
+    b = make[1]().state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        assert torch.equal(a[k], b[k]), k
