@@ -156,11 +156,57 @@ class FlatAdamW:
         """SUM all-reduce of the flat gradient; the 1/world scaling is folded into the AdamW kernel."""
         dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
 
+    # ---- checkpoint interchange: the state_dict is the one torch.optim.AdamW produces for the reference's optimiser
+    # (optimizer.py:10-34: group 0 = parameters with ndim >= 2 (weight decay), group 1 = the rest, weight_decay 0;
+    # saved / restored by gigagan_pytorch.py:2039-2107), so checkpoints move between the two trainers in both directions.
+    def _torch_index_order(self):
+        """positions (in self.params) in the order torch numbers them: decayed parameters first, then the others"""
+        wd = [i for i, p in enumerate(self.params) if p.ndim >= 2]
+        no_wd = [i for i, p in enumerate(self.params) if p.ndim < 2]
+        if self.wd > 0:
+            return wd + no_wd, len(wd)
+        return list(range(len(self.params))), len(self.params)
+
     def state_dict(self):
-        return dict(m=self.m, v=self.v, step=self.step_t, lr=self.lr, betas=self.betas, eps=self.eps, wd=self.wd)
+        order, n_wd = self._torch_index_order()
+        offs = list(self._offsets())
+        step = self.step_t.detach().to(torch.float32).reshape(()).cpu()
+        state = {}
+        for k, i in enumerate(order):
+            p, o = self.params[i], offs[i]
+            state[k] = dict(step=step.clone(), exp_avg=self.m[o:o + p.numel()].view(p.shape).detach().clone(),
+                            exp_avg_sq=self.v[o:o + p.numel()].view(p.shape).detach().clone())
+        common = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, amsgrad=False, maximize=False, foreach=None,
+                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
+        if self.wd > 0:
+            groups = [dict(common, weight_decay=self.wd, params=list(range(n_wd))),
+                      dict(common, weight_decay=0, params=list(range(n_wd, len(order))))]
+        else:
+            groups = [dict(common, weight_decay=0, params=list(range(len(order))))]
+        return dict(state=state, param_groups=groups)
 
     def load_state_dict(self, sd):
-        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"])
+        if "m" in sd and "v" in sd:                       # flat format written by earlier versions of this trainer
+            self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"])
+            return
+        order, _ = self._torch_index_order()
+        saved = [i for g in sd["param_groups"] for i in g["params"]]
+        if len(saved) != len(order):
+            raise ValueError(f"optimizer state has {len(saved)} parameters, this model has {len(order)}")
+        offs = list(self._offsets())
+        self.m.zero_(); self.v.zero_()
+        step = 0
+        for k, i in zip(saved, order):
+            st = sd["state"].get(k)
+            if st is None:                                # torch leaves out parameters that never received a gradient
+                continue
+            p, o = self.params[i], offs[i]
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {k}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(p.shape)}")
+            self.m[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1))
+            self.v[o:o + p.numel()].copy_(st["exp_avg_sq"].reshape(-1))
+            step = max(step, int(float(st["step"])))
+        self.step_t.fill_(step)
 
 
 def get_optimizer(module_or_params, lr=1e-4, wd=1e-2, betas=(0.9, 0.99), eps=1e-8, **_):
@@ -328,8 +374,11 @@ class GigaGAN(nn.Module):
         self.D.load_state_dict(pkg["D"], strict=strict)
         self._ensure_optimizers()
         for opt, key in ((self.G_opt, "G_opt"), (self.D_opt, "D_opt")):
-            if key in pkg and isinstance(pkg[key], dict) and "m" in pkg[key]:
-                opt.load_state_dict(pkg[key])
+            if key in pkg and isinstance(pkg[key], dict) and ("m" in pkg[key] or "param_groups" in pkg[key]):
+                try:
+                    opt.load_state_dict(pkg[key])
+                except ValueError as e:                  # same policy as the reference (:2103-2105): reset, keep the weights
+                    self.print(f"unable to load optimizer state ({e}) - it will be reset")
         if "steps" in pkg:
             self._host_steps = int(pkg["steps"])
             self.steps.fill_(self._host_steps)

@@ -1,2 +1,1 @@
-from . import numerize as _m  # noqa: F401
-from .numerize import numerize  # noqa: F401
+from . import numerize  # noqa: F401  (the reference does `from numerize import numerize; numerize.numerize(x)`)

@@ -78,3 +78,89 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_optimizer_state_dict_interchanges_with_the_reference_optimizer():
+    """FlatAdamW.state_dict()/load_state_dict() speak torch.optim.AdamW's format as the reference builds it
+    (optimizer.py:10-34: decayed parameters first, then the rest) - checkpoints move both ways (gp.py:2039-2107)"""
+    import pytest
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import import_reference
+    ref = import_reference()
+    from gigagan_pytorch.optimizer import get_optimizer as ref_get_optimizer
+    from gigagan_pytorch_b200.trainer import FlatAdamW
+    import gigagan_pytorch_b200 as g
+    cfg = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    torch.manual_seed(0)
+    Gr = ref.Generator(**cfg)
+    torch.manual_seed(0)
+    Gm = g.Generator(**cfg)
+    opt_r = ref_get_optimizer(Gr.parameters(), lr=2e-4, betas=(0.5, 0.9), weight_decay=0.)   # as gp.py:1982 calls it
+    for step in range(3):
+        for k, p in enumerate(Gr.parameters()):
+            p.grad = torch.randn(p.shape, generator=torch.Generator().manual_seed(100 * step + k))
+        opt_r.step()
+    opt_m = FlatAdamW(Gm, lr=2e-4, betas=(0.5, 0.9))
+    opt_m.load_state_dict(opt_r.state_dict())                       # reference -> this trainer
+    assert int(opt_m.step_t) == 3
+    off = 0
+    by_param = {id(p): st for grp in opt_r.param_groups for p in grp["params"] for st in [opt_r.state[p]]}
+    for pr, pm in zip(Gr.parameters(), opt_m.params):
+        st = by_param[id(pr)]
+        n = pm.numel()
+        assert torch.equal(opt_m.m[off:off + n].view(pm.shape), st["exp_avg"])
+        assert torch.equal(opt_m.v[off:off + n].view(pm.shape), st["exp_avg_sq"])
+        off += n
+    opt_r2 = ref_get_optimizer(Gr.parameters(), lr=2e-4, betas=(0.5, 0.9), weight_decay=0.)
+    opt_r2.load_state_dict(opt_m.state_dict())                      # this trainer -> reference
+    for pr in Gr.parameters():
+        a, b = opt_r.state[pr], opt_r2.state[pr]
+        assert torch.equal(a["exp_avg"], b["exp_avg"]) and torch.equal(a["exp_avg_sq"], b["exp_avg_sq"])
+        assert float(a["step"]) == float(b["step"]) == 3.0
+    assert [grp["weight_decay"] for grp in opt_r2.param_groups] == [grp["weight_decay"] for grp in opt_r.param_groups]
+    opt_r2.step()                                                   # the restored reference optimiser is usable
+
+
+def test_checkpoints_interchange_with_the_reference_trainer(tmp_path):
+    """GigaGAN.save() here -> reference GigaGAN.load() and back (gp.py:2033-2107): same dictionary schema, weights
+    bit-identical, optimizer state accepted by torch.optim.AdamW as the reference configures it"""
+    import pytest
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import import_reference
+    ref = import_reference()
+    import gigagan_pytorch_b200 as g
+    gen = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    disc = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8))
+    g.set_compute_dtype(torch.float32)
+    torch.manual_seed(0)
+    mine = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False)
+    mine._ensure_optimizers()
+    mine.G_opt.m.normal_(generator=torch.Generator().manual_seed(1))          # a non-trivial optimizer state
+    mine.G_opt.v.uniform_(generator=torch.Generator().manual_seed(2))
+    mine.G_opt.step_t.fill_(7)
+    p1 = str(tmp_path / "mine.pt")
+    mine.save(p1)
+    pkg = torch.load(p1, weights_only=False)
+    assert {"G", "D", "G_opt", "D_opt", "steps", "version"} <= set(pkg)
+    torch.manual_seed(1)
+    theirs = ref.GigaGAN(generator=dict(gen), discriminator=dict(disc), amp=False, create_ema_generator_at_init=False)
+    theirs.load(p1)
+    for a, b in ((mine.G, theirs.G), (mine.D, theirs.D)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+    st = theirs.G_opt.state_dict()["state"]
+    assert len(st) == len(mine.G_opt.params) and all(float(v["step"]) == 7.0 for v in st.values())
+    p2 = str(tmp_path / "theirs.pt")
+    theirs.save(p2)
+    torch.manual_seed(2)
+    back = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False)
+    back.load(p2)
+    assert all(torch.equal(a, b) for a, b in zip(mine.G.state_dict().values(), back.G.state_dict().values()))
+    assert torch.equal(back.G_opt.m, mine.G_opt.m) and torch.equal(back.G_opt.v, mine.G_opt.v) and int(back.G_opt.step_t) == 7
