@@ -338,12 +338,38 @@ class GigaGAN(nn.Module):
         self._ema_step += 1
         if step % every != 0:
             return
-        if step <= after:
+        flat = self._ema_flat_buffer()
+        if flat is None:                                 # optimiser not built yet: per-parameter path
             for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
-                pe.copy_(p)
+                pe.copy_(p if step <= after else ops.axpby(decay, pe, 1.0 - decay, p))
             return
-        for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
-            pe.copy_(ops.axpby(decay, pe, 1.0 - decay, p))
+        src = self.G_opt.flat
+        if step <= after:
+            flat.copy_(src)                              # ema_pytorch copies the online weights until update_after_step
+            return
+        # one launch over the whole generator: ema = decay * ema + (1 - decay) * online   (ref :2184, :2602-2603)
+        call("gg_pw_axpby", float(decay), _p(flat), float(1.0 - decay), _p(src), _p(flat), flat.numel(), 0, _st())
+
+    def _ema_flat_buffer(self):
+        """EMA parameters as views of ONE fp32 buffer laid out like the generator's flat master buffer (built lazily,
+        once the optimiser exists); None while that is not possible."""
+        if getattr(self, "_ema_flat", None) is not None:
+            return self._ema_flat
+        if getattr(self, "G_opt", None) is None:
+            return None
+        eparams = [p for p in self.G_ema.parameters()]
+        gparams = self.G_opt.params
+        if len(eparams) != len(gparams) or any(a.shape != b.shape for a, b in zip(eparams, gparams)):
+            return None
+        flat = torch.empty_like(self.G_opt.flat)
+        off = 0
+        for pe in eparams:
+            n = pe.numel()
+            flat[off:off + n].copy_(pe.data.reshape(-1))
+            pe.data = flat[off:off + n].view(pe.shape)
+            off += n
+        self._ema_flat = flat
+        return flat
 
     def set_dataloader(self, dl):
         assert not exists(self.train_dl), "training dataloader has already been set"

@@ -734,3 +734,26 @@ def test_conv_bias_lrelu_backward_fused_matches_composed(dtype, tol, co):
         res.append(torch.autograd.grad(y, (xx, w, b), gy, create_graph=cg))
     for a, b_ in zip(*res):
         assert relmax(a.detach(), b_.detach()) < tol
+
+
+def test_flat_ema_update_matches_lerp():
+    """EMA generator kept in one flat buffer: copy until update_after_step, then one axpby launch == per-parameter lerp"""
+    import gigagan_pytorch_b200 as g
+    g.set_compute_dtype(torch.float32)
+    torch.manual_seed(0)
+    gen = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    disc = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8))
+    gan = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False).to(dev())
+    gan._ensure_optimizers()
+    gan.create_ema_generator(update_every=1, update_after_step=0, decay=0.9)
+    gan._ema_update()                                              # step 0 <= update_after_step: plain copy
+    for pe, p in zip(gan.G_ema.parameters(), gan.G.parameters()):
+        assert torch.equal(pe, p)
+    before = [pe.detach().clone() for pe in gan.G_ema.parameters()]
+    gan.G_opt.flat.add_(torch.randn_like(gan.G_opt.flat) * 0.1)    # "an optimiser step"
+    gan._ema_update()
+    for b, pe, p in zip(before, gan.G_ema.parameters(), gan.G.parameters()):
+        assert relmax(pe, torch.lerp(b, p.detach(), 0.1)) < 1e-6
+    assert gan._ema_flat is not None and gan._ema_flat.numel() == gan.G_opt.flat.numel()
