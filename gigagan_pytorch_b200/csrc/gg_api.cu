@@ -187,6 +187,7 @@ int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const vo
                    float s, int dtype, gg_stream_t stream) {
   return ggi_rmsnorm_bwd(x, gamma, inv, gy, gx, dgamma, (long)R, C, s, dtype, ST);
 }
+int gg_debug_mma_chain(int N, int nacc, int iters, void* out, gg_stream_t stream) { return ggi_debug_mma_chain(N, nacc, iters, (unsigned long long*)out, ST); }
 int gg_debug_thin_trace(void* buf) { return ggi_debug_thin_trace((unsigned long long*)buf); }
 int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int dtype, gg_stream_t stream) {
   return ggi_lrelu_bwd_bias(y, gy, out, dbias, (long)R, C, dtype, ST);

@@ -47,6 +47,7 @@ int ggi_rmsnorm_fwd(const void* x, const float* gamma, void* y, float* inv, long
 int ggi_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const void* gy, void* gx, float* dgamma, long R, int C,
                     float s, int dtype, cudaStream_t st);
 int ggi_debug_thin_trace(unsigned long long* buf);
+int ggi_debug_mma_chain(int N, int nacc, int iters, unsigned long long* out, cudaStream_t st);
 int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int dtype, cudaStream_t st);
 int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, cudaStream_t st);
 int ggi_tc_conv_thin(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W, int Cin,

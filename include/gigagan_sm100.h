@@ -142,6 +142,10 @@ int gg_incr(int* p, gg_stream_t stream);
 int gg_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, gg_stream_t stream);
 int gg_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, gg_stream_t stream);
+/* Debug only (tools/bench_mma_chain.py): one warp issues `iters` tcgen05.mma (M=128, N, K=16, zero operands) that cycle
+ * over `nacc` TMEM accumulators; out[0] = SM cycles to issue them, out[1] = cycles until the last one completed. */
+int gg_debug_mma_chain(int N, int nacc, int iters, void* out, gg_stream_t stream);
+
 /* Debug only: point the thin-layer convolution kernel (conv_thin_tc.cu) at a device buffer of 32*64*8 uint64; CTA 0 then
  * stores clock64 at slot ((role*64 + row%64)*8 + stage) per pipeline event (tools/trace_thin.py decodes them).
  * NULL switches tracing off. */
