@@ -199,4 +199,11 @@ int gg_weight_prep_multi(const float* master, const void* entries, const void* c
                          int dtype, gg_stream_t stream) {
   return ggi_weight_prep_multi(master, entries, chunks, nchunks, fwd, bwd, dtype, ST);
 }
+int gg_gan_loss_fwd(const void* const* h_x, const int64_t* h_meta, int k, int mode, float w_ms, float* out, gg_stream_t stream) {
+  return ggi_gan_loss_fwd(h_x, (const long*)h_meta, k, mode, w_ms, out, ST);
+}
+int gg_gan_loss_bwd(const void* const* h_x, void* const* h_dx, const int64_t* h_meta, int k, int mode, float w_ms,
+                    const float* gout, gg_stream_t stream) {
+  return ggi_gan_loss_bwd(h_x, h_dx, (const long*)h_meta, k, mode, w_ms, gout, ST);
+}
 }

@@ -75,3 +75,6 @@ int ggi_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_
 int ggi_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
 int ggi_maxpool2_bwd(const void* x, const void* gy, void* gx, int N, int H, int W, int C, int dtype, cudaStream_t st);
 int ggi_softmax_tokens(const void* x, void* y, int B, int n, int C, int dtype, cudaStream_t st);
+int ggi_gan_loss_fwd(const void* const* x, const long* meta, int k, int mode, float w_ms, float* out, cudaStream_t st);
+int ggi_gan_loss_bwd(const void* const* x, void* const* dx, const long* meta, int k, int mode, float w_ms, const float* gout,
+                     cudaStream_t st);

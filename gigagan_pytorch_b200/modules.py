@@ -692,10 +692,13 @@ class Discriminator(nn.Module):
         return text_embeds
 
     def forward_nhwc(self, images, rgbs: List[torch.Tensor], return_multiscale_outputs=True, calc_aux_loss=True,
-                     fused_attention=None, text_embeds=None):
-        """images (B,S,S,C) NHWC compute dtype; rgbs: NHWC maps.  -> (logits (s,B) fp32, [ms logits NHWC], [aux])."""
+                     fused_attention=None, text_embeds=None, aux_batch=None):
+        """images (B,S,S,C) NHWC compute dtype; rgbs: NHWC maps.  -> (logits (s,B) fp32, [ms logits NHWC], [aux]).
+        ``aux_batch``: the auxiliary reconstruction (ref :1812-1827) only sees the first aux_batch images (the trainer
+        passes real and fake images as one batch, real rows first)."""
         x = images
         batch = x.shape[0]
+        aux_batch = batch if aux_batch is None else aux_batch
         assert x.shape[1] == x.shape[2] == self.image_size
         by_res = {t.shape[2]: t for t in rgbs} if rgbs is not None else {}
         missing = set(self.multiscale_input_resolutions) - set(by_res.keys())
@@ -738,7 +741,7 @@ class Discriminator(nn.Module):
             else:
                 x = ops.axpby(self.residual_scale, x, self.residual_scale, residual)
             if exists(decoder) and calc_aux_loss:                 # ref :1812-1827 (post-downsample x, first B rows)
-                aux_losses.append(decoder.forward_nhwc(x[:batch], images))   # images keep their zero pad channels
+                aux_losses.append(decoder.forward_nhwc(x[:aux_batch], images[:aux_batch]))   # zero pad channels kept
         x = ops.conv2d(x, self.to_logits[0].weight, self.to_logits[0].bias, pad=1)
         lw = self.to_logits[2].weight                                                   # (1, c*h*w) in (c h w) order
         c = x.shape[-1]

@@ -132,6 +132,11 @@ def register_weight_bank(bank):
     _BANKS.append(bank)
 
 
+def unregister_weight_bank(bank):
+    if bank in _BANKS:
+        _BANKS.remove(bank)
+
+
 def _bank_lookup(weight, cin, dtype):
     for b in _BANKS:
         r = b.lookup(weight, cin, dtype)
@@ -1049,6 +1054,51 @@ class FusedAttnFn(Function):
 def fused_attention(q, k, v, null_kv, heads, scale, l2=False):
     shared = k is q
     return FusedAttnFn.apply(q, k, v, null_kv, heads, scale, l2, shared)
+
+
+# ============================================================================= GAN objective (first-order)
+class GanLossFn(Function):
+    """Hinge objective over all logit tensors of one discriminator pass in ONE launch (ref gigagan_pytorch.py:159-163
+    and the weighted sums at :2327-2347 / :2538-2551).  tensors[0] = main logits, the rest = multiscale logits; each is
+    viewed as rows of ``rows[j]`` elements whose first ``splits[j]`` are real logits and the rest fake (mode 0), or
+    averaged as a whole (mode 1, generator).  -> (total = L_0 + w_ms * sum_j L_j, L_0, sum_{j>=1} L_j); only ``total``
+    is differentiable (the parts are logged).  First-order only: the loss is outside the gradient penalty's graph."""
+
+    @staticmethod
+    def forward(ctx, mode, w_ms, rows, splits, *tensors):
+        import ctypes
+        k = len(tensors)
+        xs = [_c(t) for t in tensors]
+        meta = (ctypes.c_int64 * (4 * k))()
+        for j, t in enumerate(xs):
+            meta[4 * j:4 * j + 4] = [t.numel(), rows[j], splits[j], _dt(t)]
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in xs])
+        out = torch.empty(3, dtype=torch.float32, device=xs[0].device)
+        call("gg_gan_loss_fwd", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(meta, ctypes.c_void_p), k, mode,
+             float(w_ms), _p(out), _st())
+        ctx.cfg = (mode, float(w_ms), k, meta)
+        ctx.save_for_backward(*xs)
+        total, l0, lms = out[2], out[0], out[1]
+        ctx.mark_non_differentiable(l0, lms)
+        return total, l0, lms
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g, _g0, _g1):
+        import ctypes
+        mode, w_ms, k, meta = ctx.cfg
+        xs = ctx.saved_tensors
+        dxs = [torch.empty_like(t) for t in xs]
+        ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in xs])
+        dptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in dxs])
+        g = _c(g.float().reshape(1))
+        call("gg_gan_loss_bwd", ctypes.cast(ptrs, ctypes.c_void_p), ctypes.cast(dptrs, ctypes.c_void_p),
+             ctypes.cast(meta, ctypes.c_void_p), k, mode, w_ms, _p(g), _st())
+        return (None, None, None, None, *dxs)
+
+
+def gan_loss(mode, w_ms, tensors, rows, splits):
+    return GanLossFn.apply(mode, w_ms, tuple(rows), tuple(splits), *tensors)
 
 
 # ============================================================================= UnetUpsampler extras

@@ -96,6 +96,25 @@ def gradient_penalty(images, outputs, grad_output_weights=None, weight=10, cente
     return ops.axpby(float(weight) / b, ops.sum_all(t))
 
 
+def gradient_penalty_pair(images, outputs, grad_output_weights, weight=10):
+    """Sum of the reference's two penalties (ref :2363-2377) when the real and the fake batch went through D as ONE
+    batch: samples are independent, so d(sum of all outputs)/d(images_k) only sees the outputs of images_k's rows and a
+    single autograd.grad call yields both input gradients.  images: list of leaf tensors; -> weight * sum_k mean_b |g_k|^2."""
+    gos = [torch.full_like(o, float(w)) for o, w in zip(outputs, grad_output_weights)]
+    with ops.skip_param_grads():
+        grads = torch.autograd.grad(outputs=list(outputs), inputs=list(images), grad_outputs=gos, create_graph=True,
+                                    retain_graph=True)
+    total = None
+    for g in grads:
+        b = g.shape[0]
+        per = g.numel() // b
+        c = 64 if per % 64 == 0 else (g.shape[-1] if per % g.shape[-1] == 0 else 1)
+        g2 = g.reshape(-1, c)
+        t = ops.axpby(float(weight) / b, ops.sum_all(ops.dot_sc(g2, g2, per // c, b)))
+        total = t if total is None else ops.add(total, t)
+    return total
+
+
 # ----------------------------------------------------------------------------- flat parameters + fused AdamW
 class FlatAdamW:
     """All parameters of a module live in one fp32 buffer (and their .grad in another); AdamW is one kernel launch
@@ -185,6 +204,16 @@ class FlatAdamW:
             groups = [dict(common, weight_decay=0, params=list(range(len(order))))]
         return dict(state=state, param_groups=groups)
 
+    @staticmethod
+    def fresh_state_dict(module, lr, betas, eps=1e-8, wd=1e-2):
+        """torch.optim.AdamW.state_dict() of a never-stepped optimiser over ``module`` (the reference's two groups)"""
+        params = [p for p in module.parameters() if p.requires_grad]
+        n_wd = sum(1 for p in params if p.ndim >= 2)
+        common = dict(lr=lr, betas=tuple(betas), eps=eps, amsgrad=False, maximize=False, foreach=None,
+                      capturable=False, differentiable=False, fused=None, decoupled_weight_decay=True)
+        return dict(state={}, param_groups=[dict(common, weight_decay=wd, params=list(range(n_wd))),
+                                            dict(common, weight_decay=0, params=list(range(n_wd, len(params))))])
+
     def load_state_dict(self, sd):
         if "m" in sd and "v" in sd:                       # flat format written by earlier versions of this trainer
             self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_t.copy_(sd["step"])
@@ -215,6 +244,15 @@ def get_optimizer(module_or_params, lr=1e-4, wd=1e-2, betas=(0.9, 0.99), eps=1e-
 
 
 # ----------------------------------------------------------------------------- trainer
+def ema_current_decay(step_after_increment, update_after_step, beta, inv_gamma=1.0, power=2.0 / 3.0, min_value=0.0):
+    """ema_pytorch's warm-up of the decay (EMA.get_current_decay, called after the step counter was incremented):
+    epoch = step - update_after_step - 1;  0 while epoch <= 0, else clamp(1 - (1 + epoch/inv_gamma)^-power, min, beta)."""
+    epoch = max(step_after_increment - update_after_step - 1, 0)
+    if epoch <= 0:
+        return 0.0
+    return min(max(1.0 - (1.0 + epoch / inv_gamma) ** -power, min_value), beta)
+
+
 class GigaGAN(nn.Module):
     def __init__(self, *, generator: BaseGenerator | Dict, discriminator: Discriminator | Dict,
                  vision_aided_discriminator=None, diff_augment=None, learning_rate=2e-4, betas=(0.5, 0.9),
@@ -251,8 +289,15 @@ class GigaGAN(nn.Module):
         self.diff_augment = None
         assert generator.unconditional == discriminator.unconditional
         self.unconditional = generator.unconditional
+        # the CLIP-based auxiliary losses need the OpenCLIP tower (third-party weights, not available offline) and are
+        # broken under DDP in the reference: text-conditional training runs with both switched off
+        if not self.unconditional:
+            assert matching_awareness_loss_weight == 0. and generator_contrastive_loss_weight == 0., \
+                ("text-conditional training here runs on pre-encoded text_encodings: set matching_awareness_loss_weight=0 "
+                 "and generator_contrastive_loss_weight=0 (both need the OpenCLIP tower)")
         self.learning_rate, self.betas = learning_rate, betas
         self.G_opt = self.D_opt = None          # built lazily once the parameters are on the GPU
+        self._pending_opt_state = {}            # optimiser state loaded (or carried over a .to()) before they exist
         self.has_ema_generator = False
         self._want_ema = create_ema_generator_at_init
         self.discr_aux_recon_loss_weight = discr_aux_recon_loss_weight
@@ -269,9 +314,11 @@ class GigaGAN(nn.Module):
         self.early_save_and_sample_every = early_save_and_sample_every
         self.num_samples = num_samples
         self.train_dl = None
+        self.sample_upsampler_dl_iter = cycle(sample_upsampler_dl) if exists(sample_upsampler_dl) else None
         self.use_cuda_graphs = False            # capture fwd+bwd of each step variant once, then replay
+        self.merge_real_fake = True             # D sees real and fake as ONE batch (identical maths, half the launches)
         self._graphs, self._graph_pool, self.graph_kernel_launches = {}, None, 0
-        self._real_buf = None
+        self._real_buf = self._text_buf = None
         self.results_folder, self.model_folder = Path(results_folder), Path(model_folder)
         self.print(f"Generator: {generator.total_params:,}  Discriminator: {discriminator.total_params:,}")
 
@@ -304,6 +351,21 @@ class GigaGAN(nn.Module):
     def unwrapped_D(self):
         return self.D
 
+    def _apply(self, fn, *a, **k):
+        """.to()/.cuda()/.float() replace every p.data, which would silently detach the parameters from the flat
+        AdamW buffers, the kernel-layout weight banks and the flat EMA buffer: tear those down first (keeping the
+        optimiser state) and let the next step rebuild them on the new device."""
+        if self.G_opt is not None:
+            self._pending_opt_state = dict(G_opt=self.G_opt.state_dict(), D_opt=self.D_opt.state_dict())
+            for bank in getattr(self, "_banks", []):
+                ops.unregister_weight_bank(bank)
+            self._banks = []
+            self.G_opt = self.D_opt = None
+        self._ema_flat = None
+        self._graphs.clear()
+        ops.clear_weight_cache()
+        return super()._apply(fn, *a, **k)
+
     def _ensure_optimizers(self):
         if self.G_opt is None:
             if self.is_distributed:          # identical initial weights on every rank, like DDP's broadcast
@@ -314,22 +376,45 @@ class GigaGAN(nn.Module):
             self.G_opt = FlatAdamW(self.G, lr=self.learning_rate, betas=self.betas)
             self.D_opt = FlatAdamW(self.D, lr=self.learning_rate, betas=self.betas)
             self._banks = []
-            if compute_dtype() == torch.bfloat16:
+            if compute_dtype() == torch.bfloat16 and self.device.type == "cuda":
                 for opt, mod in ((self.G_opt, self.G), (self.D_opt, self.D)):
                     bank = ops.WeightBank(opt.flat, opt.params, torch.bfloat16, img_cpad)
                     ops.register_weight_bank(bank)
                     self._banks.append(bank)
                     opt.bank = bank                  # the optimiser marks it stale after every parameter update
                     mod.register_load_state_dict_post_hook(lambda m, keys, bank=bank: setattr(bank, "dirty", True))
+            pend, self._pending_opt_state = self._pending_opt_state, {}
+            for opt, key in ((self.G_opt, "G_opt"), (self.D_opt, "D_opt")):
+                if key in pend:
+                    self._load_opt_state(opt, pend[key])
 
+    def _load_opt_state(self, opt, sd):
+        if not (isinstance(sd, dict) and ("m" in sd or "param_groups" in sd)):
+            return
+        try:
+            opt.load_state_dict(sd)
+        except Exception as e:                   # same policy as the reference (:2089-2108): reset, keep the weights
+            self.print(f"unable to load optimizer state ({e}) - it will be reset")
+
+    # ---- EMA generator (ema_pytorch.EMA semantics, ref :2172-2184, :2602-2603)
     def create_ema_generator(self, update_every=10, update_after_step=100, decay=0.995):
         if not self.is_main:
             return
-        assert not self.has_ema_generator
-        self.G_ema = copy.deepcopy(self.G).requires_grad_(False)
+        assert not self.has_ema_generator, "EMA generator has already been created"
+        # never deepcopy parameters that are views of the optimiser's flat buffer (it would clone the whole storage)
+        self.G_ema = copy.deepcopy(self.G) if self.G_opt is None else self._clone_generator()
+        self.G_ema.requires_grad_(False)
         self._ema_cfg = (update_every, update_after_step, decay)
         self._ema_step = 0
+        self._ema_initted = False
+        self._ema_flat = None
         self.has_ema_generator = True
+
+    def _clone_generator(self):
+        memo = {}
+        for p in self.G.parameters():            # each parameter becomes its own dense tensor (not the flat storage)
+            memo[id(p)] = nn.Parameter(p.detach().clone(), requires_grad=p.requires_grad)
+        return copy.deepcopy(self.G, memo)
 
     @torch.no_grad()
     def _ema_update(self):
@@ -338,24 +423,29 @@ class GigaGAN(nn.Module):
         self._ema_step += 1
         if step % every != 0:
             return
+        copy_only = step <= after or not self._ema_initted
+        self._ema_initted = True
+        d = 0.0 if copy_only else ema_current_decay(self._ema_step, after, decay)
+        for be, bo in zip(self.G_ema.buffers(), self.G.buffers()):      # ema_pytorch copies buffers as they are
+            be.copy_(bo)
         flat = self._ema_flat_buffer()
         if flat is None:                                 # optimiser not built yet: per-parameter path
             for pe, p in zip(self.G_ema.parameters(), self.G.parameters()):
-                pe.copy_(p if step <= after else ops.axpby(decay, pe, 1.0 - decay, p))
+                pe.copy_(p) if d == 0.0 else pe.lerp_(p.detach(), 1.0 - d)
             return
         src = self.G_opt.flat
-        if step <= after:
+        if d == 0.0:
             flat.copy_(src)                              # ema_pytorch copies the online weights until update_after_step
             return
-        # one launch over the whole generator: ema = decay * ema + (1 - decay) * online   (ref :2184, :2602-2603)
-        call("gg_pw_axpby", float(decay), _p(flat), float(1.0 - decay), _p(src), _p(flat), flat.numel(), 0, _st())
+        # one launch over the whole generator: ema = d * ema + (1 - d) * online
+        call("gg_pw_axpby", float(d), _p(flat), float(1.0 - d), _p(src), _p(flat), flat.numel(), 0, _st())
 
     def _ema_flat_buffer(self):
         """EMA parameters as views of ONE fp32 buffer laid out like the generator's flat master buffer (built lazily,
-        once the optimiser exists); None while that is not possible."""
+        once the optimiser exists and lives on the GPU); None while that is not possible."""
         if getattr(self, "_ema_flat", None) is not None:
             return self._ema_flat
-        if getattr(self, "G_opt", None) is None:
+        if self.G_opt is None or self.G_opt.flat.device.type != "cuda":
             return None
         eparams = [p for p in self.G_ema.parameters()]
         gparams = self.G_opt.params
@@ -371,6 +461,23 @@ class GigaGAN(nn.Module):
         self._ema_flat = flat
         return flat
 
+    def _ema_state_dict(self):
+        """ema_pytorch.EMA.state_dict() schema: 'ema_model.<generator key>', 'initted', 'step' (what the reference's
+        G_ema.load_state_dict expects, ref :2081-2082)."""
+        sd = {"initted": torch.tensor(bool(self._ema_initted)), "step": torch.tensor(int(self._ema_step))}
+        for k, v in self.G_ema.state_dict().items():
+            sd["ema_model." + k] = v.detach().clone()
+        return sd
+
+    def _load_ema_state_dict(self, sd):
+        own = {k[len("ema_model."):]: v for k, v in sd.items() if k.startswith("ema_model.")}
+        if not own:                                       # bare generator state_dict (earlier versions of this trainer)
+            own = {k: v for k, v in sd.items() if k not in ("initted", "step") and not k.startswith("online_model.")}
+        self.G_ema.load_state_dict(own, strict=False)
+        if "step" in sd:
+            self._ema_step = int(sd["step"])
+        self._ema_initted = bool(sd["initted"]) if "initted" in sd else self._ema_step > 0
+
     def set_dataloader(self, dl):
         assert not exists(self.train_dl), "training dataloader has already been set"
         self.train_dl = dl
@@ -383,62 +490,163 @@ class GigaGAN(nn.Module):
         self._begin_work(self._stale_banks())       # kernel-layout weights follow the latest optimiser step
         return model(*args, **kwargs)
 
+    # ---- checkpoints (ref :2033-2108: same dictionary schema; optimiser state in torch.optim.AdamW's format)
     def save(self, path, overwrite=True):
         path = Path(path)
         path.parents[0].mkdir(exist_ok=True, parents=True)
         assert overwrite or not path.exists()
-        self._ensure_optimizers()
-        pkg = dict(G=self.G.state_dict(), D=self.D.state_dict(), G_opt=self.G_opt.state_dict(),
-                   D_opt=self.D_opt.state_dict(), steps=self._host_steps, version=__version__)
+        if self.G_opt is not None:
+            g_opt, d_opt = self.G_opt.state_dict(), self.D_opt.state_dict()
+        else:                          # not trained yet on this device: what was loaded, else a fresh optimiser's state
+            pend = self._pending_opt_state
+            g_opt = pend.get("G_opt") or FlatAdamW.fresh_state_dict(self.G, self.learning_rate, self.betas)
+            d_opt = pend.get("D_opt") or FlatAdamW.fresh_state_dict(self.D, self.learning_rate, self.betas)
+        pkg = dict(G=self.G.state_dict(), D=self.D.state_dict(), G_opt=g_opt, D_opt=d_opt, steps=self._host_steps,
+                   version=__version__)
         if self.has_ema_generator:
-            pkg["G_ema"] = self.G_ema.state_dict()
+            pkg["G_ema"] = self._ema_state_dict()
         torch.save(pkg, str(path))
 
     def load(self, path, strict=False):
+        path = Path(path)
+        assert path.exists()
+        # checkpoints carry optimiser dictionaries (python containers), hence weights_only=False: load trusted files only
         pkg = torch.load(str(path), map_location=self.device, weights_only=False)
         self.G.load_state_dict(pkg["G"], strict=strict)
         self.D.load_state_dict(pkg["D"], strict=strict)
-        self._ensure_optimizers()
-        for opt, key in ((self.G_opt, "G_opt"), (self.D_opt, "D_opt")):
-            if key in pkg and isinstance(pkg[key], dict) and ("m" in pkg[key] or "param_groups" in pkg[key]):
-                try:
-                    opt.load_state_dict(pkg[key])
-                except ValueError as e:                  # same policy as the reference (:2103-2105): reset, keep the weights
-                    self.print(f"unable to load optimizer state ({e}) - it will be reset")
+        if "G_ema" in pkg and self.is_main:
+            if not self.has_ema_generator:
+                self.create_ema_generator()
+            self._load_ema_state_dict(pkg["G_ema"])
         if "steps" in pkg:
             self._host_steps = int(pkg["steps"])
             self.steps.fill_(self._host_steps)
+        for opt, key in ((self.G_opt, "G_opt"), (self.D_opt, "D_opt")):
+            if key not in pkg:
+                continue
+            if opt is None:
+                self._pending_opt_state[key] = pkg[key]      # applied when the optimisers are built (first step)
+            else:
+                self._load_opt_state(opt, pkg[key])
+
+    # ---- sampling (ref :2612-2662): rank 0 writes sample PNGs and a checkpoint on the reference's schedule
+    def _text_kwargs(self, text):
+        return {} if text is None else dict(text_encodings=text)
+
+    def generate_kwargs(self, dl_iter, batch_size):
+        """ref :2186-2222.  Text conditioning enters as pre-encoded CLIP token encodings (b, n, clip_dim): datasets for
+        conditional training yield (images, text_encodings)."""
+        maybe_text = {}
+        real = None
+        if self.train_upsampler or not self.unconditional:
+            assert exists(dl_iter)
+            real, text = self._next_batch(dl_iter)
+            if not self.unconditional:
+                assert exists(text), ("dataset should return a tuple (images, text_encodings) for text conditioned "
+                                      "training")
+                maybe_text["text_encodings"] = text[:batch_size]
+        if self.train_upsampler:
+            size = self.G.input_image_size
+            f = real.shape[-1] // size
+            G_kwargs = dict(lowres_image=real[:, :, ::f, ::f].contiguous())       # F.interpolate default = nearest
+        else:
+            assert exists(batch_size)
+            G_kwargs = dict(batch_size=batch_size)
+        G_kwargs.update(noise=torch.randn(batch_size, self.G.style_network.dim, device=self.device))
+        return G_kwargs, maybe_text
+
+    def sample(self, model, dl_iter, batch_size):
+        G_kwargs, maybe_text = self.generate_kwargs(dl_iter, batch_size)
+        out = model(**G_kwargs, **maybe_text)
+        if not self.train_upsampler:
+            return out
+        size = out.shape[-1]
+        low = G_kwargs["lowres_image"]
+        f = size // low.shape[-1]
+        low = low.repeat_interleave(f, dim=-2).repeat_interleave(f, dim=-1)        # nearest upsampling
+        return torch.cat([low[: out.shape[0]], out])
+
+    @torch.inference_mode()
+    def save_sample(self, batch_size, dl_iter=None):
+        from torchvision import utils as tv_utils
+        milestone = self._host_steps // self.save_and_sample_every
+        nrow_mult = 2 if self.train_upsampler else 1
+        groups, rem = divmod(self.num_samples, batch_size)
+        batches = [batch_size] * groups + ([rem] if rem > 0 else [])
+        if self.train_upsampler and exists(self.sample_upsampler_dl_iter):
+            dl_iter = self.sample_upsampler_dl_iter
+        assert exists(dl_iter) or not (self.train_upsampler or not self.unconditional)
+        self._begin_work(self._stale_banks())
+        models = [(self.G, f"sample-{milestone}.png")]
+        if self.has_ema_generator:
+            models.append((self.G_ema, f"ema-sample-{milestone}.png"))
+        self.results_folder.mkdir(exist_ok=True, parents=True)
+        for model, filename in models:
+            was_training = model.training
+            model.eval()
+            imgs = torch.cat([self.sample(model, dl_iter, n) for n in batches], dim=0).clamp_(0., 1.)
+            tv_utils.save_image(imgs.float().cpu(), str(self.results_folder / filename),
+                                nrow=int(math.sqrt(self.num_samples)) * nrow_mult)
+            model.train(was_training)
+        self.save(str(self.model_folder / f"model-{milestone}.ckpt"))
 
     # ---- one micro-batch of each objective (device tensors in, 0-dim loss tensors out)
-    def _d_objective(self, real, noise, apply_gradient_penalty, calc_multiscale_loss):
-        D, G, dt = self.D, self.G, compute_dtype()
+    def _d_objective(self, real, noise, apply_gradient_penalty, calc_multiscale_loss, text=None):
+        D, dt = self.D, compute_dtype()
         gp_on = apply_gradient_penalty
+        B = real.shape[0]
         real = real.float()
         if gp_on:
             real.requires_grad_()
         real_n = ops.to_nhwc(real, img_cpad(D.channels), dt)
         real_rgbs = D.real_images_to_rgbs_nhwc(real_n)
         with torch.no_grad():
-            fake, rgbs = self._generate(noise, real_n.detach())
+            fake, rgbs = self._generate(noise, real_n.detach(), text)
         fake = fake.detach().requires_grad_(gp_on)
-        rgbs = [t.detach().requires_grad_(gp_on) for t in rgbs]
+        rgbs = [t.detach() for t in rgbs]
         fused = False if gp_on else None      # gradient penalty needs the any-order-differentiable attention
-        fl, fm, _ = D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False, fused_attention=fused)
-        rl, rm, aux = D.forward_nhwc(real_n, real_rgbs, calc_multiscale_loss, True, fused_attention=fused)
-        div = discriminator_hinge_loss(rl, fl)
-        total = div
+        te = None if text is None else D.encode_text(text_encodings=text)
         zero = torch.zeros((), device=real.device)
-        ms = zero
-        if self.multiscale_divergence_loss_weight > 0. and len(fm) > 0:
-            ms = None
-            for a, b in zip(fm, rm):
-                t = discriminator_hinge_loss(b, a)
-                ms = t if ms is None else ops.add(ms, t)
-            total = ops.axpby(1.0, total, self.multiscale_divergence_loss_weight, ms)
-        gp = zero
+        w_ms = self.multiscale_divergence_loss_weight
+        hinge = None
+        calc_aux = self.discr_aux_recon_loss_weight > 0.
+        if self.merge_real_fake:
+            # real rows first: the aux decoder reads x[:B] / images[:B] (ref :1812-1827 sees the real pass only)
+            fr = {t.shape[2]: t for t in rgbs}
+            images = torch.cat((real_n, fake), dim=0)
+            both = [torch.cat((r, fr[r.shape[2]]), dim=0) for r in real_rgbs]
+            te2 = None if te is None else torch.cat((te, te), dim=0)
+            logits, ms_out, aux = D.forward_nhwc(images, both, calc_multiscale_loss, calc_aux, fused_attention=fused,
+                                                 text_embeds=te2, aux_batch=B)
+            # hinge + multiscale hinge of the whole pass in one launch: rows '(2 b) ...' = B real then B fake logits
+            use_ms = w_ms > 0. and len(ms_out) > 0
+            ts = [logits] + (list(ms_out) if use_ms else [])
+            rows = [2 * B] + [2 * B * m.shape[1] * m.shape[2] for m in ts[1:]]
+            hinge, div, ms = ops.gan_loss(0, w_ms, ts, rows, [r // 2 for r in rows])
+            if not use_ms:
+                ms = zero
+            gp = zero
+            if gp_on:
+                gp = gradient_penalty_pair([real, fake], [logits, *ms_out], [1.] + [w_ms] * len(ms_out))
+        else:
+            fl, fm, _ = D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False, fused_attention=fused, text_embeds=te)
+            rl, rm, aux = D.forward_nhwc(real_n, real_rgbs, calc_multiscale_loss, calc_aux, fused_attention=fused,
+                                         text_embeds=te)
+            div, ms = discriminator_hinge_loss(rl, fl), zero
+            if w_ms > 0. and len(fm) > 0:
+                ms = None
+                for a, b in zip(fm, rm):
+                    t = discriminator_hinge_loss(b, a)
+                    ms = t if ms is None else ops.add(ms, t)
+            gp = zero
+            if gp_on:
+                w = [1.] + [w_ms] * len(rm)
+                gp = ops.add(gradient_penalty(real, [rl, *rm], w), gradient_penalty(fake, [fl, *fm], w))
+        if hinge is None:
+            total = div if ms is zero else ops.axpby(1.0, div, w_ms, ms)
+        else:
+            total = hinge
         if gp_on:
-            w = [1.] + [self.multiscale_divergence_loss_weight] * len(rm)
-            gp = ops.add(gradient_penalty(real, [rl, *rm], w), gradient_penalty(fake, [fl, *fm], w))
             total = ops.add(total, gp)
         aux_loss = zero
         if self.discr_aux_recon_loss_weight > 0. and len(aux) > 0:
@@ -448,29 +656,34 @@ class GigaGAN(nn.Module):
             total = ops.axpby(1.0, total, self.discr_aux_recon_loss_weight, aux_loss)
         return total, (div, ms, gp, aux_loss)
 
-    def _generate(self, noise, real_n=None):
+    def _generate(self, noise, real_n=None, text=None):
         """G forward in NHWC.  The upsampler sees the real batch resized (nearest, like F.interpolate's default at
-        ref gigagan_pytorch.py:2210) to its input size."""
-        if not self.train_upsampler:
+        ref gigagan_pytorch.py:2210) to its input size; the text-conditional generator gets the pre-encoded tokens."""
+        if self.train_upsampler:
+            f = real_n.shape[1] // self.G.input_image_size
+            lowres = real_n[:, ::f, ::f, :].contiguous()
+            return self.G.forward_nhwc(lowres, noise=noise)
+        if text is None:
             return self.G.forward_nhwc(noise=noise)
-        f = real_n.shape[1] // self.G.input_image_size
-        lowres = real_n[:, ::f, ::f, :].contiguous()
-        return self.G.forward_nhwc(lowres, noise=noise)
+        g, f, tm = self.G.encode_text(text_encodings=text)
+        return self.G.forward_nhwc(noise=noise, global_text_tokens=g, fine_text_tokens=f, text_mask=tm)
 
-    def _g_objective(self, noise, calc_multiscale_loss):
+    def _g_objective(self, noise, calc_multiscale_loss, text=None):
         real_n = None
         if self.train_upsampler:
             real_n = ops.to_nhwc(self._real_buf.detach(), img_cpad(self.D.channels), compute_dtype())
-        fake, rgbs = self._generate(noise, real_n)
-        logits, ms, _ = self.D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False)
-        div = generator_hinge_loss(logits)
-        total, msd = div, torch.zeros((), device=noise.device)
-        if self.multiscale_divergence_loss_weight > 0. and len(ms) > 0:
-            msd = None
-            for m in ms:
-                t = generator_hinge_loss(m)
-                msd = t if msd is None else ops.add(msd, t)
-            total = ops.axpby(1.0, total, self.multiscale_divergence_loss_weight, msd)
+        fake, rgbs = self._generate(noise, real_n, text)
+        te = None
+        if text is not None:
+            with torch.no_grad():                      # D (and its text encoder) only passes gradients here (Q12)
+                te = self.D.encode_text(text_encodings=text)
+        logits, ms, _ = self.D.forward_nhwc(fake, rgbs, calc_multiscale_loss, False, text_embeds=te)
+        w_ms = self.multiscale_divergence_loss_weight
+        use_ms = w_ms > 0. and len(ms) > 0
+        ts = [logits] + (list(ms) if use_ms else [])
+        total, div, msd = ops.gan_loss(1, w_ms, ts, [t.numel() for t in ts], [0] * len(ts))
+        if not use_ms:
+            msd = torch.zeros((), device=noise.device)
         return total, (div, msd)
 
     # ---- CUDA graphs: the first occurrence of a step variant runs eagerly (warm-up), the second is captured,
@@ -527,15 +740,50 @@ class GigaGAN(nn.Module):
                 sel = dec.draw_patch_selection(real.shape[0])
                 if dec.static_onehot is None or dec.static_onehot.shape != sel.shape:
                     dec.static_onehot = torch.empty(sel.shape, dtype=torch.float32, device=self.device)
-                    self._pinned_sel = torch.empty(sel.shape, dtype=torch.float32).pin_memory()
-                self._pinned_sel.copy_(sel)
-                dec.static_onehot.copy_(self._pinned_sel, non_blocking=True)
+                    dec._pinned_sel = torch.empty(sel.shape, dtype=torch.float32).pin_memory()
+                    dec._pinned_evt = None
+                    self._graphs.clear()
+                if dec._pinned_evt is not None:   # the previous step's H2D copy may still be queued (no host sync per step)
+                    dec._pinned_evt.synchronize()
+                dec._pinned_sel.copy_(sel)
+                dec.static_onehot.copy_(dec._pinned_sel, non_blocking=True)
+                dec._pinned_evt = torch.cuda.Event()
+                dec._pinned_evt.record()
+
+    def _stage_text(self, text):
+        """static buffer for the step's text encodings (CUDA-graph input); None when unconditional"""
+        if text is None:
+            return None
+        if self._text_buf is None or self._text_buf.shape != text.shape:
+            self._text_buf = torch.empty(text.shape, dtype=torch.float32, device=self.device)
+            self._graphs.clear()
+        self._text_buf.copy_(text, non_blocking=True)
+        return self._text_buf
+
+    def _next_batch(self, dl_iter):
+        """-> (images on device, text_encodings on device | None).  Conditional datasets yield (images, text_encodings)."""
+        batch = next(dl_iter)
+        text = None
+        if isinstance(batch, (tuple, list)):
+            if len(batch) > 1 and not self.unconditional:
+                text = batch[1]
+                assert torch.is_tensor(text), ("raw caption strings need the OpenCLIP tower (not available offline): "
+                                               "yield pre-encoded text_encodings (b, n, clip_dim) tensors instead")
+                text = text.to(self.device, non_blocking=True).float()
+            batch = batch[0]
+        return batch.to(self.device, non_blocking=True), text
 
     def _next_images(self, dl_iter):
-        batch = next(dl_iter)
-        if isinstance(batch, (tuple, list)):
-            batch = batch[0]
-        return batch.to(self.device, non_blocking=True)
+        return self._next_batch(dl_iter)[0]
+
+    def _step_text(self, dl_iter, batch_size):
+        """the reference draws the step's captions from ONE MORE batch of the loader (generate_kwargs, ref :2196-2204)
+        and uses them for the generator and for both discriminator passes"""
+        if self.unconditional:
+            return None
+        _, text = self._next_batch(dl_iter)
+        assert exists(text), "dataset should return a tuple (images, text_encodings) for text conditioned training"
+        return text[:batch_size]
 
     def train_discriminator_step(self, dl_iter: Iterable, grad_accum_every=1, apply_gradient_penalty=False,
                                  calc_multiscale_loss=True):
@@ -544,7 +792,9 @@ class GigaGAN(nn.Module):
         d_params = self.D_opt.params
         acc = None
         if grad_accum_every == 1:
-            self._stage_real(self._next_images(dl_iter))
+            real = self._next_images(dl_iter)
+            self._stage_real(real)
+            text = self._stage_text(self._step_text(dl_iter, real.shape[0]))
             stale = self._stale_banks()
 
             def work():
@@ -552,7 +802,7 @@ class GigaGAN(nn.Module):
                 self.D_opt.zero_grad()
                 real = self._real_buf.detach()
                 noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)      # ref :2220
-                total, parts = self._d_objective(real, noise, apply_gradient_penalty, calc_multiscale_loss)
+                total, parts = self._d_objective(real, noise, apply_gradient_penalty, calc_multiscale_loss, text)
                 total.backward(inputs=d_params)
                 return [p.detach() for p in parts]
 
@@ -563,9 +813,10 @@ class GigaGAN(nn.Module):
             for _ in range(grad_accum_every):
                 real = self._next_images(dl_iter)
                 self._stage_real(real)
+                text = self._stage_text(self._step_text(dl_iter, real.shape[0]))
                 noise = torch.randn(real.shape[0], self.G.style_network.dim, device=self.device)
                 total, parts = self._d_objective(self._real_buf.detach(), noise, apply_gradient_penalty,
-                                                 calc_multiscale_loss)
+                                                 calc_multiscale_loss, text)
                 ops.axpby(1.0 / grad_accum_every, total).backward(inputs=d_params)
                 parts = [p.detach() / grad_accum_every for p in parts]
                 acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
@@ -579,22 +830,32 @@ class GigaGAN(nn.Module):
                              calc_multiscale_loss=True):
         self._ensure_optimizers()
         self.G.train(); self.D.train()
-        d_params = list(self.D.parameters())
         g_params = self.G_opt.params
-        for p in d_params:                   # Q12: D's weight gradients are discarded by the reference; skip them
+        frozen = [p for p in self.D.parameters() if p.requires_grad]
+        for p in frozen:                     # Q12: D's weight gradients are discarded by the reference; skip them
             p.requires_grad_(False)
         acc = None
         try:
-            if self.train_upsampler:                       # ref generate_kwargs (:2196): a fresh real batch per G step
-                self._stage_real(self._next_images(dl_iter))
+            def stage():
+                text = None
+                if self.train_upsampler or not self.unconditional:       # ref generate_kwargs (:2196): a fresh batch
+                    real, text = self._next_batch(dl_iter)
+                    if self.train_upsampler:
+                        self._stage_real(real)
+                    if not self.unconditional:
+                        assert exists(text), "dataset should return (images, text_encodings) for text conditioned training"
+                        text = text[:batch_size]
+                return self._stage_text(text)
+
             if grad_accum_every == 1:
+                text = stage()
                 stale = self._stale_banks()
 
                 def work():
                     self._begin_work(stale)
                     self.G_opt.zero_grad()
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
-                    total, parts = self._g_objective(noise, calc_multiscale_loss)
+                    total, parts = self._g_objective(noise, calc_multiscale_loss, text)
                     total.backward(inputs=g_params)
                     return [p.detach() for p in parts]
 
@@ -603,13 +864,14 @@ class GigaGAN(nn.Module):
                 self._begin_work(self._stale_banks())
                 self.G_opt.zero_grad()
                 for _ in range(grad_accum_every):
+                    text = stage()
                     noise = torch.randn(batch_size, self.G.style_network.dim, device=self.device)
-                    total, parts = self._g_objective(noise, calc_multiscale_loss)
+                    total, parts = self._g_objective(noise, calc_multiscale_loss, text)
                     ops.axpby(1.0 / grad_accum_every, total).backward(inputs=g_params)
                     parts = [p.detach() / grad_accum_every for p in parts]
                     acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
         finally:
-            for p in d_params:
+            for p in frozen:                 # only the flags that were set before
                 p.requires_grad_(True)
         if self.is_distributed:
             self.G_opt.all_reduce_grads()
@@ -642,6 +904,12 @@ class GigaGAN(nn.Module):
                 losses = (("G", g.divergence), ("MSG", last_msg), ("VG", 0.), ("D", d.divergence), ("MSD", last_msd),
                           ("VD", 0.), ("GP", last_gp), ("SSL", d.aux_reconstruction), ("CL", 0.), ("MAL", 0.))
                 self.print(" | ".join(f"{n}: {float(v):.2f}" for n, v in losses))
+            # ref :2745: sample PNGs + checkpoint at step 1, every save_and_sample_every steps and, early in training,
+            # every early_save_and_sample_every steps (0 / None switches a schedule off)
+            every, early = self.save_and_sample_every, self.early_save_and_sample_every
+            if self.is_main and every and (step == 1 or step % every == 0 or
+                                           (early and step <= self.early_save_thres_steps and step % early == 0)):
+                self.save_sample(batch_size, dl_iter)
             self._host_steps += 1
             self.steps += 1
         self.print(f"complete {steps} training steps")

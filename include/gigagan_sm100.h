@@ -177,6 +177,17 @@ int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, g
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream);
 
+/* ---- GAN hinge objective over all logit tensors of a pass in ONE launch (replaces discriminator_hinge_loss /
+ * generator_hinge_loss gigagan_pytorch.py:159-163 and their weighted sums :2327-2347, :2538-2551).
+ * h_x: host array of k <= 8 device pointers; h_meta: host int64 [k][4] = {elements, row length, split, dtype}: every
+ * row holds `split` real logits followed by fake logits (the trainer stacks real and fake images in one batch).
+ * mode 0 (discriminator): L_j = mean_real relu(1 + x) + mean_fake relu(1 - x);  mode 1 (generator): L_j = mean(x).
+ * out[0] = L_0, out[1] = sum_{j>=1} L_j, out[2] = L_0 + w_ms * out[1].  bwd writes dL/dx_j for out[2] scaled by the
+ * device scalar gout. */
+int gg_gan_loss_fwd(const void* const* h_x, const int64_t* h_meta, int k, int mode, float w_ms, float* out, gg_stream_t stream);
+int gg_gan_loss_bwd(const void* const* h_x, void* const* h_dx, const int64_t* h_meta, int k, int mode, float w_ms,
+                    const float* gout, gg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

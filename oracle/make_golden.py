@@ -151,9 +151,97 @@ def main():
                     ggrads={k: p.grad.clone() for k, p in G7.named_parameters() if p.grad is not None},
                     dgrads={k: p.grad.clone() for k, p in D7.named_parameters() if p.grad is not None}),
                os.path.join(OUT, "ka7_text_conditional.pt"))
+    make_aux_decoder()
+    make_text_step()
     for f_ in sorted(os.listdir(OUT)):
         print(f_, os.path.getsize(os.path.join(OUT, f_)))
 
 
+def make_aux_decoder():
+    """KA5b: the auxiliary reconstruction decoder (SimpleDecoder, ref :1290-1317 via :1812-1827), calc_aux_loss=True.
+    eval mode (no dropout) so that the only randomness is the CPU randn patch permutation (:1310), drawn right after
+    manual_seed(patch_seed)."""
+    dcfg = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8),
+                aux_recon_resolutions=(8,))
+    torch.manual_seed(0)
+    D = ref.Discriminator(**dcfg)
+    D.eval()
+    img = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    torch.manual_seed(7)
+    logits, ms, aux = D(img, D.real_images_to_rgbs(img), calc_aux_loss=True)
+    assert len(aux) == 1
+    aux[0].backward()
+    torch.save(dict(cfg=dcfg, sd=sd_of(D), img=img, patch_seed=7, aux=[a.detach() for a in aux],
+                    grads={k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}),
+               os.path.join(OUT, "ka5b_aux_decoder.pt"))
+
+
+def make_text_step():
+    """KA9: one text-conditional discriminator step objective (with gradient penalty) and one generator step objective
+    built from the reference's Generator / Discriminator exactly as its trainer does (ref :2263-2417, :2518-2551), on
+    pre-encoded text_encodings (the OpenCLIP tower is outside the path).  Auxiliary losses off."""
+    from gigagan_pytorch.gigagan_pytorch import TextEncoder as RefTextEncoder, generator_hinge_loss
+    from gigagan_pytorch.open_clip import OpenClipAdapter
+
+    class _NoClip(OpenClipAdapter):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+
+        @property
+        def dim_latent(self):
+            return 32
+
+    tecfg = dict(dim=24, depth=1, dim_head=8, heads=2)
+    gcfg = dict(dim_capacity=2, style_network=dict(dim=16, depth=2, dim_text_latent=24), image_size=32, dim_max=16,
+                dim_latent=16, num_skip_layers_excite=2, self_attn_resolutions=(16,), self_attn_dim_head=8,
+                self_attn_heads=2, cross_attn_resolutions=(16, 8), cross_attn_dim_head=8, cross_attn_heads=2,
+                unconditional=False)
+    dcfg = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, attn_resolutions=(8,),
+                attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8), unconditional=False)
+    torch.manual_seed(0)
+    G = ref.Generator(text_encoder=RefTextEncoder(clip=_NoClip(), **tecfg), **gcfg)
+    torch.manual_seed(1)
+    D = ref.Discriminator(text_encoder=RefTextEncoder(clip=_NoClip(), **tecfg), **dcfg)
+    enc = rn(5, 2, 6, 32)
+    enc[1, 4:] = 0.
+    z = rn(1, 2, 16)
+    real = torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(4)).requires_grad_()
+    G.train(); D.train()
+    with torch.no_grad():
+        torch.manual_seed(2)
+        fake, rgbs = G(noise=z, text_encodings=enc, return_all_rgbs=True)
+    fake = fake.detach().requires_grad_()
+    rgbs = [t.detach().requires_grad_() for t in rgbs]
+    fl, fm, _ = D(fake, rgbs, text_encodings=enc, calc_aux_loss=False)
+    rl, rm, _ = D(real, D.real_images_to_rgbs(real), text_encodings=enc, calc_aux_loss=False)
+    div = discriminator_hinge_loss(rl, fl)
+    msl = sum(discriminator_hinge_loss(b, a) for a, b in zip(fm, rm))
+    w = [1.0] + [0.1] * len(rm)
+    gp = gradient_penalty(real, [rl, *rm], w) + gradient_penalty(fake, [fl, *fm], w)
+    total = div + gp + 0.1 * msl
+    total.backward()
+    dgrads = {k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}
+    dloss = dict(total=total.detach(), divergence=div.detach(), multiscale=msl.detach(), gradient_penalty=gp.detach())
+    D.zero_grad()
+    torch.manual_seed(2)
+    fake, rgbs = G(noise=z, text_encodings=enc, return_all_rgbs=True)
+    logits, ms, _ = D(fake, rgbs, text_encodings=enc, calc_aux_loss=False)
+    gdiv = generator_hinge_loss(logits)
+    gms = sum(generator_hinge_loss(m_) for m_ in ms)
+    gtotal = gdiv + 0.1 * gms
+    gtotal.backward()
+    ggrads = {k: p.grad.clone() for k, p in G.named_parameters() if p.grad is not None}
+    torch.save(dict(te_cfg=dict(clip_dim_latent=32, **tecfg), gcfg=gcfg, dcfg=dcfg, gsd=sd_of(G), dsd=sd_of(D), enc=enc,
+                    z=z, real=real.detach(), dloss=dloss, dgrads=dgrads,
+                    gloss=dict(total=gtotal.detach(), divergence=gdiv.detach(), multiscale=gms.detach()), ggrads=ggrads),
+               os.path.join(OUT, "ka9_text_step.pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "aux":
+        make_aux_decoder()
+    elif len(sys.argv) > 1 and sys.argv[1] == "text_step":
+        make_text_step()
+    else:
+        main()

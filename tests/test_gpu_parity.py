@@ -543,13 +543,16 @@ def test_trainer_steps_run_and_cuda_graph_replay_matches_eager(upsampler, amp):
                 return iter(reals)
 
         gan.set_dataloader(Pool())
-        torch.manual_seed(5)
+        flat = lambda: torch.cat([p.detach().flatten().float() for p in list(gan.G.parameters()) + list(gan.D.parameters())])
+        p0 = flat().clone()
+        torch.manual_seed(5)       # same device and host RNG streams for both runs (captured randn replays the eager stream)
         gan(steps=5)               # step 4 carries the gradient penalty; graphs: steps 1-2 eager, then capture/replay
         torch.cuda.synchronize()
-        res.append(torch.cat([p.detach().flatten().float() for p in list(gan.G.parameters()) + list(gan.D.parameters())]))
-        assert torch.isfinite(res[-1]).all()
-    # identical RNG streams are not guaranteed between eager and captured randn; require the same scale of update
-    assert (res[0] - res[1]).abs().max().item() < 0.05
+        res.append(flat() - p0)
+        assert torch.isfinite(res[-1]).all() and res[-1].abs().max().item() > 1e-4       # the parameters did move
+    # the parameter UPDATES of the eager and the graph-replayed run agree (not merely the parameters, which barely move)
+    rel = (res[0] - res[1]).abs().max().item() / res[0].abs().max().item()
+    assert rel < (1e-2 if not amp else 5e-2), rel
 
 
 # ------------------------------------------------------------------ text-conditioned path
@@ -746,14 +749,90 @@ def test_flat_ema_update_matches_lerp():
     disc = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
                 attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8))
     gan = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False).to(dev())
+    from gigagan_pytorch_b200.trainer import ema_current_decay
     gan._ensure_optimizers()
     gan.create_ema_generator(update_every=1, update_after_step=0, decay=0.9)
     gan._ema_update()                                              # step 0 <= update_after_step: plain copy
     for pe, p in zip(gan.G_ema.parameters(), gan.G.parameters()):
         assert torch.equal(pe, p)
-    before = [pe.detach().clone() for pe in gan.G_ema.parameters()]
-    gan.G_opt.flat.add_(torch.randn_like(gan.G_opt.flat) * 0.1)    # "an optimiser step"
-    gan._ema_update()
-    for b, pe, p in zip(before, gan.G_ema.parameters(), gan.G.parameters()):
-        assert relmax(pe, torch.lerp(b, p.detach(), 0.1)) < 1e-6
+    for k in range(1, 4):                                          # ema_pytorch warms the decay up: 0.37, 0.52, 0.60 ... -> 0.9
+        before = [pe.detach().clone() for pe in gan.G_ema.parameters()]
+        gan.G_opt.flat.add_(torch.randn_like(gan.G_opt.flat) * 0.1)    # "an optimiser step"
+        gan._ema_update()
+        d = ema_current_decay(k + 1, 0, 0.9)
+        assert abs(d - min(0.9, 1 - (1 + k) ** (-2 / 3))) < 1e-12
+        for b, pe, p in zip(before, gan.G_ema.parameters(), gan.G.parameters()):
+            assert relmax(pe, torch.lerp(b, p.detach(), 1.0 - d)) < 1e-6
     assert gan._ema_flat is not None and gan._ema_flat.numel() == gan.G_opt.flat.numel()
+
+
+@pytest.mark.parametrize("merge", [True, False])
+def test_ka9_text_conditional_trainer_step(merge):
+    """One text-conditional D step objective (hinge + multiscale + gradient penalty) and one G step objective through the
+    TRAINER (GigaGAN._d_objective / _g_objective with pre-encoded text_encodings, ref :2263-2417 / :2518-2551) against
+    the same quantities built from the reference's modules (fixture ka9)."""
+    import gigagan_pytorch_b200 as g
+    fx = load("ka9_text_step.pt")
+    g.set_compute_dtype(torch.float32)
+    G = g.Generator(text_encoder=g.TextEncoder(**fx["te_cfg"]), **fx["gcfg"])
+    D = g.Discriminator(text_encoder=g.TextEncoder(**fx["te_cfg"]), **fx["dcfg"])
+    G.load_state_dict(fx["gsd"]); D.load_state_dict(fx["dsd"])
+    gan = g.GigaGAN(generator=G, discriminator=D, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False,
+                    discr_aux_recon_loss_weight=0., matching_awareness_loss_weight=0.,
+                    generator_contrastive_loss_weight=0.).to(dev())
+    gan.merge_real_fake = merge
+    gan.G.train(); gan.D.train()
+    enc, z, real = fx["enc"].to(dev()), fx["z"].to(dev()), fx["real"].to(dev())
+    total, (div, ms, gp, _) = gan._d_objective(real, z, True, True, text=enc)
+    total.backward(inputs=list(gan.D.parameters()))
+    tol = 2e-4
+    for k, v in (("total", total), ("divergence", div), ("multiscale", ms), ("gradient_penalty", gp)):
+        assert relmax(v.detach(), fx["dloss"][k].to(dev())) < tol * 5, (k, v.item(), fx["dloss"][k].item())
+    named = dict(gan.D.named_parameters())
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["dgrads"].items())
+    assert worst[0] < tol * 10, worst
+    for p in gan.D.parameters():
+        p.grad = None
+        p.requires_grad_(False)
+    total, (gdiv, gms) = gan._g_objective(z, True, enc)
+    total.backward(inputs=list(gan.G.parameters()))
+    for k, v in (("total", total), ("divergence", gdiv), ("multiscale", gms)):
+        assert relmax(v.detach(), fx["gloss"][k].to(dev())) < tol * 5, (k, v.item(), fx["gloss"][k].item())
+    named = dict(gan.G.named_parameters())
+    # Noise.weight gradients depend on the per-layer noise images (device RNG here, CPU RNG in the fixture): not compared
+    skip = lambda k, v: v.ndim == 3 and v.shape[1:] == (1, 1) and ".1." in k
+    worst = max((relmax(named[k].grad, v.to(dev())), k) for k, v in fx["ggrads"].items() if not skip(k, v))
+    assert worst[0] < tol * 10, worst
+
+
+def test_text_conditional_trainer_runs_with_graphs():
+    """GigaGAN(steps=...) on a conditional dataset yielding (images, text_encodings): eager warm-up, capture, replay"""
+    import gigagan_pytorch_b200 as g
+    fx = load("ka9_text_step.pt")
+    g.set_compute_dtype(torch.float32)
+    torch.manual_seed(0)
+    gan = g.GigaGAN(generator=dict(fx["gcfg"], text_encoder=dict(fx["te_cfg"])),
+                    discriminator=dict(fx["dcfg"], text_encoder=dict(fx["te_cfg"])), amp=True, mixed_precision_type="bf16",
+                    log_steps_every=10 ** 9, create_ema_generator_at_init=True, matching_awareness_loss_weight=0.,
+                    generator_contrastive_loss_weight=0., save_and_sample_every=0).to(dev())
+    gan.use_cuda_graphs = True
+    items = []
+    for s in range(4):
+        enc = torch.randn(4, 6, 32, generator=torch.Generator().manual_seed(s))
+        enc[1, 3:] = 0.
+        items.append((torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(10 + s)), enc))
+
+    class Pool:
+        batch_size = 4
+
+        def __iter__(self):
+            return iter(items)
+
+    gan.set_dataloader(Pool())
+    p0 = torch.cat([p.detach().flatten().float().clone() for p in gan.G.parameters()])
+    gan(steps=6)
+    torch.cuda.synchronize()
+    p1 = torch.cat([p.detach().flatten().float() for p in gan.G.parameters()])
+    assert torch.isfinite(p1).all() and (p1 - p0).abs().max().item() > 1e-5
+    out = gan.generate(batch_size=2, text_encodings=items[0][1][:2].to(dev()))
+    assert out.shape == (2, 3, 32, 32) and torch.isfinite(out).all()

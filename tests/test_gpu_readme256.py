@@ -1,0 +1,287 @@
+"""GPU parity AT THE BENCHMARKED CONFIGURATION (README unconditional 256, the models bench.py times) against the fixture
+oracle/make_golden_readme256.py wrote from the unmodified reference, plus direct torch/cuDNN-free checks of the wide
+tcgen05 paths that dominate the step (512-channel layers, dual-M tiles, the discriminator's res-32 L2 attention).
+
+Tolerances.  fp32 (FFMA kernels): 2e-4 of each tensor's max for outputs and losses, 2e-3 for gradient samples / norms
+(two 65k-pixel reductions and a double backward in different summation orders).  bf16 (the benchmarked tcgen05 path):
+the reference's OWN bf16-autocast run deviates from its fp32 run by far more than north_star's 1e-2 at this
+configuration (rgb 3.2e-2, gradients up to O(1) where they cancel), so the bound is tied to it:
+    |ours_bf16 - ref_fp32|  <=  max(K_BF16 * |ref_bf16 - ref_fp32|, 1e-2)        per tensor, K_BF16 = 2.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K_BF16 = 2.0
+FLOOR = 1e-2
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    import gigagan_pytorch_b200 as g
+    g.set_compute_dtype(torch.float32)
+    yield
+    g.set_compute_dtype(torch.float32)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def relmax(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item() / (b.float().abs().max().item() + 1e-30)
+
+
+def rn(k, *s):
+    return torch.randn(*s, generator=torch.Generator().manual_seed(k))
+
+
+def sample_idx(n, ns=512):
+    return torch.linspace(0, n - 1, min(ns, n)).long()
+
+
+_FX = {}
+
+
+def fixture():
+    if "fx" not in _FX:
+        _FX["fx"] = torch.load(os.path.join(ROOT, "tests", "golden", "ka8_readme256.pt"), weights_only=False)
+    return _FX["fx"]
+
+
+def build_models(dtype):
+    """seeded construction exactly as the fixture script did it; the checksums pin that the weights are the reference's"""
+    import gigagan_pytorch_b200 as g
+    fx = fixture()
+    g.set_compute_dtype(dtype)
+    torch.manual_seed(fx["seeds"]["G"])
+    G = g.Generator(**fx["gcfg"])
+    torch.manual_seed(fx["seeds"]["D"])
+    D = g.Discriminator(**fx["dcfg"])
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(fx["seeds"]["noise_weights"])
+        for n, p in G.named_parameters():
+            if n.endswith(".1.1.weight") or n.endswith(".1.4.weight"):
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1)
+    for name, m in (("G", G), ("D", D)):
+        for k, v in m.state_dict().items():
+            ref = fx["checksums"][name][k]
+            assert abs(v.double().abs().sum().item() - ref) <= 1e-9 * max(1.0, abs(ref)), (name, k)
+    return G.to(dev()), D.to(dev())
+
+
+def check(name, ours, ref, dtype, dev_ref, tol32, report):
+    err = relmax(ours, ref)
+    bound = tol32 if dtype == torch.float32 else max(K_BF16 * dev_ref, FLOOR)
+    report.append((err / bound, name, err, bound))
+
+
+def check_grads(named, fxg, devg, dtype, report, skip=lambda k: False):
+    for k, ref in fxg.items():
+        if skip(k):
+            continue
+        g = named[k].grad.detach().float().flatten()
+        smp = g[sample_idx(g.numel()).to(g.device)]
+        if dtype == torch.float32:
+            b_s = b_n = 2e-3
+        else:
+            b_s = max(K_BF16 * devg[k]["sample_rel"], FLOOR)
+            b_n = max(K_BF16 * devg[k]["norm_rel"], FLOOR)
+        e_s = relmax(smp, ref["sample"])
+        e_n = abs(g.norm().item() - ref["norm"]) / max(ref["norm"], 1e-30)
+        report.append((e_s / b_s, "grad sample " + k, e_s, b_s))
+        report.append((e_n / b_n, "grad norm " + k, e_n, b_n))
+
+
+def finish(report, what):
+    report.sort(reverse=True)
+    print(f"\n[{what}] worst error/bound ratios:")
+    for r in report[:8]:
+        print(f"   {r[0]:.3f}  {r[1]}: err {r[2]:.3e} bound {r[3]:.3e}")
+    bad = [r for r in report if not r[0] <= 1.0]
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ka8_generator_readme256(dtype):
+    from gigagan_pytorch_b200 import ops
+    fx = fixture()
+    G, _ = build_models(dtype)
+    torch.manual_seed(fx["seeds"]["layer_noise"])       # the reference drew its layer noises from the CPU generator
+    noises = [torch.randn(2, 1, r, r).to(dev()) for r in (4, 8, 16, 32, 64, 128, 256) for _ in range(2)]
+    rgb, rgbs = G.forward_nhwc(noise=rn(fx["seeds"]["z"], 2, 64).to(dev()), layer_noises=noises)
+    out = ops.to_nchw(rgb, 3)
+    rep = []
+    dv = fx["g_bf16_dev"]
+    check("rgb", out, fx["g"]["rgb"], dtype, dv["rgb"], 2e-4, rep)
+    small = [t for t in rgbs if t.shape[2] <= 64]
+    for i, (a, b) in enumerate(zip(small, fx["g"]["rgbs"])):
+        check(f"rgbs[{b.shape[-1]}]", ops.to_nchw(a, 3), b, dtype, dv["rgbs"][i], 2e-4, rep)
+    loss = (out ** 2).mean()
+    check("loss", loss.detach(), fx["g"]["loss"], dtype, dv["loss"], 2e-4, rep)
+    loss.backward()
+    check_grads(dict(G.named_parameters()), fx["g"]["grads"], dv["grads"], dtype, rep)
+    finish(rep, f"G README-256 {dtype}")
+
+
+@pytest.mark.parametrize("merged", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ka8_discriminator_step_readme256(dtype, merged):
+    """the discriminator step's objective (hinge + multiscale hinge + gradient penalty on real and fake) and every D
+    parameter gradient at README-256; merged=True goes through the trainer's own _d_objective (real and fake as one
+    batch, fused hinge kernel, kernel-layout weight banks and the weight-gradient sink in bf16) - the path bench.py times"""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    from gigagan_pytorch_b200.modules import img_cpad
+    from gigagan_pytorch_b200.trainer import discriminator_hinge_loss, gradient_penalty
+    fx = fixture()
+    G, D = build_models(dtype)
+    D.train()
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(fx["seeds"]["img"])).to(dev())
+    fake = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(fx["seeds"]["fake"])) * 2 - 1).to(dev())
+    rep = []
+    dv, ref = fx["d_bf16_dev"], fx["d"]
+    cp = img_cpad(3)
+    if merged:
+        gan = g.GigaGAN(generator=G, discriminator=D, amp=(dtype == torch.bfloat16), mixed_precision_type="bf16",
+                        log_steps_every=10 ** 9, create_ema_generator_at_init=False, discr_aux_recon_loss_weight=0.).to(dev())
+        gan._ensure_optimizers()
+        fake_n = ops.to_nhwc(fake, cp, dtype)
+        gan._generate = lambda noise, real_n=None, text=None: (fake_n, D.real_images_to_rgbs_nhwc(fake_n))
+        gan._begin_work(gan._stale_banks())
+        gan.D_opt.zero_grad()
+        total, (div, msl, gp, _) = gan._d_objective(img, None, True, True)
+        total.backward(inputs=gan.D_opt.params)
+    else:
+        r = img.clone().requires_grad_()
+        f = fake.clone().requires_grad_()
+        fn, rn_ = ops.to_nhwc(f, cp, dtype), ops.to_nhwc(r, cp, dtype)
+        frgbs = [t.detach() for t in D.real_images_to_rgbs_nhwc(fn)]
+        fl, fm, _ = D.forward_nhwc(fn, frgbs, True, False, fused_attention=False)
+        rl, rm, _ = D.forward_nhwc(rn_, D.real_images_to_rgbs_nhwc(rn_), True, False, fused_attention=False)
+        check("real_logits", rl.t() if rl.shape != ref["real_logits"].shape else rl, ref["real_logits"], dtype,
+              dv["real_logits"], 2e-4, rep)
+        check("fake_logits", fl, ref["fake_logits"], dtype, dv["fake_logits"], 2e-4, rep)
+        for i, (a, b) in enumerate(zip(rm, ref["real_ms"])):
+            check(f"real_ms[{i}]", ops.to_nchw(a, 1), b, dtype, dv["real_ms"][i], 2e-4, rep)
+        for i, (a, b) in enumerate(zip(fm, ref["fake_ms"])):
+            check(f"fake_ms[{i}]", ops.to_nchw(a, 1), b, dtype, dv["fake_ms"][i], 2e-4, rep)
+        div = discriminator_hinge_loss(rl, fl)
+        msl = sum(discriminator_hinge_loss(b, a) for a, b in zip(fm, rm))
+        w = [1.0] + [0.1] * len(rm)
+        gp = gradient_penalty(r, [rl, *rm], w) + gradient_penalty(f, [fl, *fm], w)
+        total = div + gp + 0.1 * msl
+        total.backward()
+    for k, v in (("total", total), ("divergence", div), ("multiscale", msl), ("gradient_penalty", gp)):
+        check("loss." + k, v.detach(), ref["loss"][k], dtype, dv["loss"][k], 2e-4 if k != "gradient_penalty" else 1e-3, rep)
+    check_grads(dict(D.named_parameters()), ref["grads"], dv["grads"], dtype, rep)
+    finish(rep, f"D step README-256 {dtype} merged={merged}")
+
+
+# ------------------------------------------------------------------ wide tcgen05 paths against torch directly
+def _conv_ref(x, w, b, stride, pad):
+    """fp32 torch reference from the bf16-rounded operands (NHWC x, kernel-layout w)"""
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), b, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("name,n,hw,ci,co,k,stride", [
+    ("D16 block2, dual-M tiles", 256, 16, 512, 512, 3, 1),
+    ("D32 block2, wide N", 64, 32, 256, 256, 3, 1),
+    ("D64 block2, mid channels", 32, 64, 128, 128, 3, 1),
+    ("predictor 4x4, batch-spanning tiles", 512, 4, 512, 512, 3, 1),
+    ("attention ff1 1x1", 64, 32, 256, 1024, 1, 1),
+    ("downsample 2x2 stride 2", 128, 16, 512, 512, 2, 2),
+    ("residual 1x1 stride 2", 128, 16, 256, 512, 1, 2),
+])
+def test_wide_tcgen05_conv_vs_torch(name, n, hw, ci, co, k, stride):
+    """fprop / dgrad / wgrad of the layers that carry the step's FLOPs, bf16 tcgen05 vs torch fp32 on the same
+    (bf16-rounded) operands: only the fp32-accumulated bf16 output rounding separates them (<= 2^-8 relative)"""
+    from gigagan_pytorch_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(n, hw, hw, ci, device=dev()).to(torch.bfloat16)
+    w = (torch.randn(co, k, k, ci, device=dev()) * (ci * k * k) ** -0.5).to(torch.bfloat16)
+    b = torch.randn(co, device=dev())
+    pad = k // 2 if stride == 1 else 0
+    g = ops.ConvGeom(k, k, stride, pad, False, act=0)
+    y = ops._conv_fprop_raw(x, w, b, None, g, co)
+    xr = x.float().requires_grad_()
+    wr = w.float().requires_grad_()
+    yr = _conv_ref(xr, wr, b, stride, pad)
+    assert relmax(y, yr) < 6e-3, name
+    gy = torch.randn_like(yr).to(torch.bfloat16)
+    gxr, gwr = torch.autograd.grad(yr, (xr, wr), gy.float())
+    gx = ops._conv_dgrad_raw(gy, w, g, tuple(x.shape))
+    assert relmax(gx, gxr) < 6e-3, name
+    gw = ops._conv_wgrad_raw(x, gy, g)                    # fp32 kernel layout
+    assert relmax(gw, gwr) < 2e-3, name
+
+
+@pytest.mark.parametrize("n,tokens,l2", [(8, 1024, True), (8, 256, True), (4, 1024, False)])
+def test_fused_attention_wide_vs_torch(n, tokens, l2):
+    """the discriminator's res-32 / res-16 attention shapes (8 heads x 64, shared QK L2 logits, null key/value) and the
+    generator's dot-product form: fused tcgen05 forward AND backward against the reference formula in torch fp32
+    (ref gigagan_pytorch.py:562-592) on the same bf16-rounded q/k/v"""
+    from gigagan_pytorch_b200 import ops
+    torch.manual_seed(0)
+    heads, d = 8, 64
+    q = (torch.randn(n, tokens, heads * d, device=dev()) * 0.5).to(torch.bfloat16).requires_grad_()
+    k = q if l2 else (torch.randn(n, tokens, heads * d, device=dev()) * 0.5).to(torch.bfloat16).requires_grad_()
+    v = torch.randn(n, tokens, heads * d, device=dev()).to(torch.bfloat16).requires_grad_()
+    nkv = torch.randn(2, heads, d, device=dev()).requires_grad_()
+    scale = d ** -0.5
+    o = ops.fused_attention(q, k, v, nkv, heads, scale, l2=l2)
+    go = torch.randn_like(o)
+    ins = (q, v, nkv) if l2 else (q, k, v, nkv)
+    grads = torch.autograd.grad(o, ins, go)
+
+    def ref(qf, kf, vf, nk):
+        sp = lambda t: t.view(n, tokens, heads, d).permute(0, 2, 1, 3)
+        q4, k4, v4 = sp(qf), sp(kf), sp(vf)
+        k4 = torch.cat((nk[0][None, :, None, :].expand(n, -1, -1, -1), k4), dim=2)
+        v4 = torch.cat((nk[1][None, :, None, :].expand(n, -1, -1, -1), v4), dim=2)
+        if l2:
+            sim = -(torch.cdist(q4, k4, p=2) ** 2)
+        else:
+            sim = q4 @ k4.transpose(-1, -2)
+        return ((sim * scale).softmax(dim=-1) @ v4).permute(0, 2, 1, 3).reshape(n, tokens, heads * d)
+
+    qf = q.detach().float().requires_grad_()
+    kf = qf if l2 else k.detach().float().requires_grad_()
+    vf = v.detach().float().requires_grad_()
+    nf = nkv.detach().clone().requires_grad_()
+    orf = ref(qf, kf, vf, nf)
+    rins = (qf, vf, nf) if l2 else (qf, kf, vf, nf)
+    rgrads = torch.autograd.grad(orf, rins, go.float())
+    assert relmax(o, orf) < 1e-2
+    for a, b, nm in zip(grads, rgrads, ("dq", "dv", "dnull") if l2 else ("dq", "dk", "dv", "dnull")):
+        assert relmax(a, b) < 2e-2, (nm, relmax(a, b))
+
+
+def test_aux_reconstruction_decoder_matches_reference():
+    """SimpleDecoder (ref gigagan_pytorch.py:1290-1317, called from :1812-1827) with calc_aux_loss=True against the
+    reference's value and decoder gradients (fixture ka5b: eval mode, so the only randomness is the CPU randn patch
+    permutation, reproduced by seeding the host generator exactly as the fixture did)"""
+    import gigagan_pytorch_b200 as g
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "ka5b_aux_decoder.pt"), weights_only=False)
+    for dtype, tol in ((torch.float32, 2e-4), (torch.bfloat16, 3e-2)):
+        g.set_compute_dtype(dtype)
+        D = g.Discriminator(**fx["cfg"]).to(dev())
+        D.load_state_dict(fx["sd"])
+        D.eval()
+        img = fx["img"].to(dev())
+        torch.manual_seed(fx["patch_seed"])
+        logits, ms, aux = D(img, D.real_images_to_rgbs(img), calc_aux_loss=True)
+        assert len(aux) == len(fx["aux"]) == 1
+        assert relmax(aux[0], fx["aux"][0]) < tol, (dtype, aux[0].item(), fx["aux"][0].item())
+        D.zero_grad()
+        aux[0].backward()
+        named = dict(D.named_parameters())
+        worst = max((relmax(named[k].grad, v), k) for k, v in fx["grads"].items())
+        assert worst[0] < tol * 5, (dtype, worst)

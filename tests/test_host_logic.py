@@ -68,15 +68,16 @@ def test_trainer_refreshes_only_stale_banks():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (oracle port on the host cores, bounded) at a tiny size: one JSON line with the
-    contract keys; never touches CUDA"""
+    """`bench.py --impl reference` (the unmodified reference from baseline/_ref on the host cores when installed, else
+    the oracle port; bounded) at a tiny size: one JSON line with the contract keys; never touches CUDA"""
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--image-size", "64",
                           "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=280, env=env)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    has_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "gigagan_pytorch"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if has_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
 
 
@@ -163,4 +164,101 @@ def test_checkpoints_interchange_with_the_reference_trainer(tmp_path):
     back = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False)
     back.load(p2)
     assert all(torch.equal(a, b) for a, b in zip(mine.G.state_dict().values(), back.G.state_dict().values()))
+    assert back.G_opt is None                 # optimiser state is held until the flat buffers are built (first step),
+    back._ensure_optimizers()                 # so that load() followed by .cuda()/.to() stays valid
     assert torch.equal(back.G_opt.m, mine.G_opt.m) and torch.equal(back.G_opt.v, mine.G_opt.v) and int(back.G_opt.step_t) == 7
+
+
+def test_checkpoints_with_ema_interchange_with_the_reference_trainer(tmp_path):
+    """with the default create_ema_generator_at_init=True the checkpoint carries G_ema in ema_pytorch's
+    wrapper schema ('ema_model.*', 'initted', 'step'); save -> load restores the EMA weights and its step counter, and
+    checkpoints move between this trainer and the reference trainer in both directions with EMA enabled"""
+    import pytest
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import import_reference
+    ref = import_reference()
+    import gigagan_pytorch_b200 as g
+    gen = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    disc = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8))
+    g.set_compute_dtype(torch.float32)
+    torch.manual_seed(0)
+    mine = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9)
+    mine._ensure_optimizers()
+    assert mine.has_ema_generator
+    with torch.no_grad():                                   # EMA weights that differ from the online generator
+        for pe in mine.G_ema.parameters():
+            pe.add_(0.25)
+    mine._ema_step, mine._ema_initted = 137, True
+    p1 = str(tmp_path / "mine.pt")
+    mine.save(p1)
+    pkg = torch.load(p1, weights_only=False)
+    assert {"initted", "step"} <= set(pkg["G_ema"]) and int(pkg["G_ema"]["step"]) == 137
+    assert all(("ema_model." + k) in pkg["G_ema"] for k in mine.G.state_dict())
+    # this trainer -> this trainer: EMA weights and counter survive (they used to be dropped)
+    torch.manual_seed(3)
+    again = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9)
+    again.load(p1)
+    assert again._ema_step == 137 and again._ema_initted
+    for a, b, o in zip(mine.G_ema.parameters(), again.G_ema.parameters(), again.G.parameters()):
+        assert torch.equal(a, b) and not torch.equal(b, o)
+    # this trainer -> reference trainer (strict load of G_ema in the reference, gp.py:2081-2082)
+    torch.manual_seed(1)
+    theirs = ref.GigaGAN(generator=dict(gen), discriminator=dict(disc), amp=False)
+    theirs.load(p1)
+    for a, b in zip(mine.G_ema.parameters(), theirs.G_ema.ema_model.parameters()):
+        assert torch.equal(a, b)
+    assert int(theirs.G_ema.step) == 137
+    # reference trainer -> this trainer
+    with torch.no_grad():
+        for pe in theirs.G_ema.ema_model.parameters():
+            pe.mul_(0.5)
+        theirs.G_ema.step.fill_(211)
+    p2 = str(tmp_path / "theirs.pt")
+    theirs.save(p2)
+    torch.manual_seed(2)
+    back = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9)
+    back.load(p2)
+    assert back._ema_step == 211
+    for a, b in zip(theirs.G_ema.ema_model.parameters(), back.G_ema.parameters()):
+        assert torch.equal(a, b)
+
+
+def test_moving_the_trainer_after_load_keeps_the_optimizer_state():
+    """`gan.load(ckpt); gan.to(device)` (nn.Module._apply replaces every p.data) must not detach the
+    parameters from the flat AdamW buffers: the flat buffers are torn down with their state carried over and rebuilt"""
+    import gigagan_pytorch_b200 as g
+    gen = dict(dim_capacity=2, style_network=dict(dim=16, depth=2), image_size=32, dim_max=16, dim_latent=16,
+               num_skip_layers_excite=2, unconditional=True, self_attn_resolutions=(16,), self_attn_dim_head=8, self_attn_heads=2)
+    disc = dict(dim_capacity=2, dim_max=16, image_size=32, num_skip_layers_excite=2, unconditional=True,
+                attn_resolutions=(8,), attn_dim_head=8, attn_heads=2, multiscale_input_resolutions=(16, 8))
+    g.set_compute_dtype(torch.float32)
+    torch.manual_seed(0)
+    gan = g.GigaGAN(generator=gen, discriminator=disc, amp=False, log_steps_every=10 ** 9, create_ema_generator_at_init=False)
+    gan._ensure_optimizers()
+    gan.D_opt.m.normal_(generator=torch.Generator().manual_seed(1))
+    gan.D_opt.v.uniform_(generator=torch.Generator().manual_seed(2))
+    gan.D_opt.step_t.fill_(9)
+    m, v = gan.D_opt.m.clone(), gan.D_opt.v.clone()
+    w = [p.detach().clone() for p in gan.D.parameters()]
+    gan.double().float()                                     # any _apply: what .cuda() / .to(device) do
+    assert gan.D_opt is None and "D_opt" in gan._pending_opt_state
+    gan._ensure_optimizers()
+    assert torch.equal(gan.D_opt.m, m) and torch.equal(gan.D_opt.v, v) and int(gan.D_opt.step_t) == 9
+    off = 0
+    for p, w0 in zip(gan.D_opt.params, w):                   # parameters are views of the NEW flat buffer, values intact
+        assert p.data_ptr() == gan.D_opt.flat.data_ptr() + 4 * off and torch.equal(p.detach(), w0)
+        off += p.numel()
+
+
+def test_ema_decay_warmup_matches_ema_pytorch_formula():
+    from gigagan_pytorch_b200.trainer import ema_current_decay
+    # EMA.get_current_decay of ema-pytorch (inv_gamma 1, power 2/3, min 0): 0 until update_after_step + 1, then
+    # 1 - (1 + epoch)^(-2/3) capped at beta
+    assert ema_current_decay(100, 100, 0.995) == 0.0 and ema_current_decay(101, 100, 0.995) == 0.0
+    assert abs(ema_current_decay(102, 100, 0.995) - (1 - 2 ** (-2 / 3))) < 1e-12
+    assert abs(ema_current_decay(111, 100, 0.995) - (1 - 11 ** (-2 / 3))) < 1e-12
+    assert ema_current_decay(10 ** 6, 100, 0.995) == 0.995
