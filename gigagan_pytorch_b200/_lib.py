@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgigagan_sm100.so")
+LIB_PATH = os.environ.get("GG_LIB") or os.path.join(_HERE, "libgigagan_sm100.so")     # GG_LIB: A/B a second build
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gigagan_sm100.h")
 
 _CT = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "gg_stream_t": ctypes.c_void_p}

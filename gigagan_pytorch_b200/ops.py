@@ -199,16 +199,35 @@ class ConvProfiler:
     def __exit__(self, *a):
         _PROFILER[0] = None
 
-    def summary(self, dtype=torch.bfloat16):
+    def summary(self, dtype=torch.bfloat16, kinds=("fprop", "dgrad_s2")):
         torch.cuda.synchronize()
         ms = fl = 0.0
         n = 0
-        for kind, flops, e0, e1, dt in self.records:
-            if dt == dtype:
+        for kind, flops, e0, e1, dt, *_ in self.records:
+            if dt == dtype and kind in kinds:
                 ms += e0.elapsed_time(e1)
                 fl += flops
                 n += 1
         return dict(ms=ms, tflops=(fl / ms / 1e9) if ms else 0.0, launches=n)
+
+
+class _Timed:
+    """records one launch group into the active ConvProfiler (no-op otherwise)"""
+
+    def __init__(self, kind, flops, dtype, desc):
+        self.prof = _PROFILER[0]
+        self.args = (kind, flops, dtype, desc)
+
+    def __enter__(self):
+        if self.prof is not None:
+            self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.prof is not None:
+            self.e1.record()
+            kind, flops, dtype, desc = self.args
+            self.prof.records.append((kind, flops, self.e0, self.e1, dtype, desc))
 
 
 def _conv_fprop_raw(x, wk, bias, res, g, out_c):
@@ -223,7 +242,8 @@ def _conv_fprop_raw(x, wk, bias, res, g, out_c):
          g.pad, int(g.per_sample), g.act, float(g.gain), _dt(x), _st())
     if prof is not None:
         e1.record()
-        prof.records.append(("fprop", 2.0 * n * oh * ow * out_c * cin * g.kh * g.kw, e0, e1, x.dtype))
+        prof.records.append(("fprop", 2.0 * n * oh * ow * out_c * cin * g.kh * g.kw, e0, e1, x.dtype,
+                             f"n{n} {h}x{w} {cin}->{out_c} k{g.kh} s{g.stride} ps{int(g.per_sample)} act{g.act} res{int(res is not None)}"))
     return y
 
 
@@ -240,11 +260,13 @@ def _conv_dgrad_raw(gy, wk, g, in_shape):
     if g.stride == 2 and g.pad == 0 and g.kh == g.kw and g.kh <= 2 and not g.per_sample and h == 2 * oh and w == 2 * ow:
         # non-overlapping stride-2 taps: one 1x1 GEMM per tap, scattered into the interleaved gradient tensor
         dx = (torch.empty if g.kh == 2 else torch.zeros)(in_shape, dtype=gy.dtype, device=gy.device)
-        for ky in range(g.kh):
-            for kx in range(g.kw):
-                wt = wk[:, ky, kx, :].t().contiguous()                       # (Cin, Cout) = 1x1 kernel layout
-                call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, cin, 1, 1, 1, 0,
-                     0, 0, 1.0, (ky * w + kx) * cin, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
+        with _Timed("dgrad_s2", 2.0 * n * oh * ow * cout * cin * g.kh * g.kw, gy.dtype,
+                    f"dgrad n{n} {h}x{w} {cin}<-{cout} k{g.kh} s2"):
+            for ky in range(g.kh):
+                for kx in range(g.kw):
+                    wt = wk[:, ky, kx, :].t().contiguous()                       # (Cin, Cout) = 1x1 kernel layout
+                    call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, cin, 1, 1, 1,
+                         0, 0, 0, 1.0, (ky * w + kx) * cin, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
         return dx
     dx = torch.empty(in_shape, dtype=gy.dtype, device=gy.device)
     call("gg_conv2d_dgrad", _p(gy), _p(wk), _p(dx), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
@@ -257,8 +279,10 @@ def _conv_wgrad_raw(x, gy, g):
     _, oh, ow, cout = gy.shape
     shape = (n, cout, g.kh, g.kw, cin) if g.per_sample else (cout, g.kh, g.kw, cin)
     dw = torch.empty(shape, dtype=torch.float32, device=x.device)
-    call("gg_conv2d_wgrad", _p(x), _p(gy), _p(dw), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
-         int(g.per_sample), _dt(x), _st())
+    with _Timed("wgrad", 2.0 * n * oh * ow * cout * cin * g.kh * g.kw, x.dtype,
+                f"wgrad n{n} {h}x{w} {cin}->{cout} k{g.kh} s{g.stride} ps{int(g.per_sample)}"):
+        call("gg_conv2d_wgrad", _p(x), _p(gy), _p(dw), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
+             int(g.per_sample), _dt(x), _st())
     return dw
 
 
