@@ -694,9 +694,15 @@ class GigaGAN(nn.Module):
         from . import _lib
         st = self._graphs.get(key)
         if st is None:
-            self._graphs[key] = "warm"
-            return work()
-        if st == "warm":
+            outs = work()
+            # the step's loss scalars are read by the caller AFTER later graphs have replayed.  All graphs share one
+            # memory pool and are not replayed in capture order (G is captured before D's second variant, D replays
+            # first), so a later replay may use the block behind an earlier graph's output as scratch: results are
+            # therefore copied, inside the graph, into buffers that live outside the pool.
+            self._graphs[key] = ("warm", [torch.empty_like(o) for o in outs])
+            return outs
+        if st[0] == "warm":
+            static = st[1]
             if self._graph_pool is None:
                 self._graph_pool = torch.cuda.graph_pool_handle()
             graph = torch.cuda.CUDAGraph()
@@ -704,9 +710,11 @@ class GigaGAN(nn.Module):
             l0 = _lib.launch_count
             with torch.cuda.graph(graph, pool=self._graph_pool):
                 outs = work()
+                for dst, src in zip(static, outs):
+                    dst.copy_(src)
             n = _lib.launch_count - l0
             _lib.launch_count = l0
-            st = self._graphs[key] = (graph, outs, n)
+            st = self._graphs[key] = (graph, static, n)
         graph, outs, n = st
         graph.replay()
         self.graph_kernel_launches += n

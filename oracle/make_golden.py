@@ -172,9 +172,19 @@ def make_aux_decoder():
     logits, ms, aux = D(img, D.real_images_to_rgbs(img), calc_aux_loss=True)
     assert len(aux) == 1
     aux[0].backward()
-    torch.save(dict(cfg=dcfg, sd=sd_of(D), img=img, patch_seed=7, aux=[a.detach() for a in aux],
-                    grads={k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}),
-               os.path.join(OUT, "ka5b_aux_decoder.pt"))
+    grads = {k: p.grad.clone() for k, p in D.named_parameters() if p.grad is not None}
+    # the same quantities under CPU bf16 autocast (what amp=True runs): their deviation from the fp32 run is the yardstick
+    # of the GPU bf16 test (|ours_bf16 - ref_fp32| <= K * |ref_bf16 - ref_fp32| per tensor)
+    D.zero_grad()
+    torch.manual_seed(7)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        _, _, aux16 = D(img, D.real_images_to_rgbs(img), calc_aux_loss=True)
+    aux16[0].float().backward()
+    rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30)).item()
+    dev = dict(aux=rel(aux16[0].detach(), aux[0].detach()),
+               grads={k: rel(p.grad, grads[k]) for k, p in D.named_parameters() if p.grad is not None})
+    torch.save(dict(cfg=dcfg, sd=sd_of(D), img=img, patch_seed=7, aux=[a.detach() for a in aux], grads=grads,
+                    bf16_dev=dev), os.path.join(OUT, "ka5b_aux_decoder.pt"))
 
 
 def make_text_step():
