@@ -1,0 +1,224 @@
+// Small fused kernels of the generator / discriminator glue (HBM- or latency-bound; one launch replaces a chain of
+// pointwise / reduction launches of the composed operators).  extern "C" surface declared in include/gigagan_sm100.h.
+#include "../../include/gigagan_sm100.h"
+#include "gg_common.cuh"
+
+#define ST ((cudaStream_t)stream)
+
+// ------------------------------------------------------------------ shared-bank AdaptiveConv2DMod (4x4 / 8x8 layers)
+// prep.  grid (O + XB), 256 threads.  Blocks x < O: demodulation statistics of output channel o for ALL images (the
+// bank row [n][I*KK] is read once and reused for every image; one block per (b, o) re-read the 19 MB bank B times);
+// blocks x >= O: xs = x * (mod + 1) over a slice of the whole batch.  attn = softmax over the n <= 8 kernel logits.
+#define SB_BCH 16
+template <typename T>
+__global__ void sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+                                  const float* __restrict__ kmod, const T* __restrict__ x, T* __restrict__ xs,
+                                  float* __restrict__ attn, float* __restrict__ dinv, int B, int n, int O, int I, int KK,
+                                  int HW, int demod, float eps, long ldm, long ldk, int XB) {
+  __shared__ float sa[SB_BCH * 8];
+  __shared__ float red[8][SB_BCH];
+  if ((int)blockIdx.x >= O) {
+    const long per = (long)HW * I, tot = per * B;
+    for (long e = (long)(blockIdx.x - O) * blockDim.x + threadIdx.x; e < tot; e += (long)XB * blockDim.x) {
+      int i = (int)(e % I);
+      int b = (int)(e / per);
+      stf(xs + e, ldf(x + e) * (mod[(long)b * ldm + i] + 1.f));
+    }
+    return;
+  }
+  const int o = blockIdx.x, E = I * KK;
+  for (int b0 = 0; b0 < B; b0 += SB_BCH) {
+    const int nb = min(SB_BCH, B - b0);
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {                          // softmax over the kernel logits of image b0 + t
+      const int b = b0 + threadIdx.x;
+      if (n == 1) sa[threadIdx.x * 8] = 1.f;
+      else {
+        float m = -INFINITY, ssum = 0.f, ev[8];
+        for (int j = 0; j < n; ++j) m = fmaxf(m, kmod[(long)b * ldk + j]);
+        for (int j = 0; j < n; ++j) { ev[j] = expf(kmod[(long)b * ldk + j] - m); ssum += ev[j]; }
+        for (int j = 0; j < n; ++j) sa[threadIdx.x * 8 + j] = ev[j] / ssum;
+      }
+      if (o == 0) for (int j = 0; j < n; ++j) attn[b * n + j] = sa[threadIdx.x * 8 + j];
+    }
+    __syncthreads();
+    if (!demod) { if ((int)threadIdx.x < nb) dinv[(long)(b0 + threadIdx.x) * O + o] = 1.f; continue; }
+    float ss[SB_BCH];
+#pragma unroll
+    for (int t = 0; t < SB_BCH; ++t) ss[t] = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int i = e / KK;
+      float w[8];
+      for (int j = 0; j < n; ++j) w[j] = bank[((long)j * O + o) * E + e];
+#pragma unroll
+      for (int t = 0; t < SB_BCH; ++t)
+        if (t < nb) {
+          float v = 0.f;
+          for (int j = 0; j < n; ++j) v += sa[t * 8 + j] * w[j];
+          const float u = v * (mod[(long)(b0 + t) * ldm + i] + 1.f);
+          ss[t] += u * u;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < SB_BCH; ++t) {
+      const float r = warp_sum(ss[t]);
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = r;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+      float tsum = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += red[w][threadIdx.x];
+      dinv[(long)(b0 + threadIdx.x) * O + o] = rsqrtf(fmaxf(tsum, eps));
+    }
+  }
+}
+
+// y[b,p,o] = dinv[b,o] * sum_j attn[b,j] * ycat[b,p,j*O+o]
+template <typename T>
+__global__ void sbank_combine_fwd_kernel(const T* __restrict__ ycat, const float* __restrict__ attn,
+                                         const float* __restrict__ dinv, T* __restrict__ y, int HW, int n, int O, long tot) {
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x) {
+    int o = (int)(e % O);
+    long bp = e / O;
+    int b = (int)(bp / HW);
+    float z = 0.f;
+    for (int j = 0; j < n; ++j) z += attn[b * n + j] * ldf(ycat + bp * ((long)n * O) + (long)j * O + o);
+    stf(y + e, z * dinv[(long)b * O + o]);
+  }
+}
+
+// grid (cdiv(O,256), B), thread = output channel o, loop over the image's HW pixels
+template <typename T>
+__global__ void sbank_combine_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ ycat,
+                                         const float* __restrict__ attn, const float* __restrict__ dinv,
+                                         T* __restrict__ gyn, float* __restrict__ gdinv, float* __restrict__ gattn, int B,
+                                         int HW, int n, int O) {
+  __shared__ float red[8][8];
+  const int b = blockIdx.y, o = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = o < O;
+  float a[8], ga[8];
+  for (int j = 0; j < n; ++j) { a[j] = attn[b * n + j]; ga[j] = 0.f; }
+  const float d = live ? dinv[(long)b * O + o] : 0.f;
+  float gd = 0.f;
+  if (live)
+    for (int p = 0; p < HW; ++p) {
+      const long bp = (long)b * HW + p;
+      const float g = ldf(gy + bp * O + o);
+      float z = 0.f;
+      for (int j = 0; j < n; ++j) {
+        float yj = ldf(ycat + bp * ((long)n * O) + (long)j * O + o);
+        z += a[j] * yj;
+        ga[j] += g * d * yj;
+        stf(gyn + ((long)j * B * HW + bp) * O + o, g * d * a[j]);
+      }
+      gd += g * z;
+    }
+  if (live) gdinv[(long)b * O + o] = gd;
+  for (int j = 0; j < n; ++j) {
+    float t = warp_sum(ga[j]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = t;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
+    atomicAdd(gattn + b * n + threadIdx.x, t);
+  }
+}
+
+// gx = gxs * (mod + 1);  dmod[b,i] += sum_p gxs[b,p,i] * x[b,p,i].   grid (cdiv(I,256), B), thread = channel i
+template <typename T>
+__global__ void sbank_bwd_x_kernel(const T* __restrict__ gxs, const T* __restrict__ x, const float* __restrict__ mod,
+                                   T* __restrict__ gx, float* __restrict__ dmod, int HW, int I, long ldm) {
+  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  const float s = mod[(long)b * ldm + i] + 1.f;
+  float acc = 0.f;
+  for (int p = 0; p < HW; ++p) {
+    const long e = ((long)b * HW + p) * I + i;
+    const float g = ldf(gxs + e);
+    acc += g * ldf(x + e);
+    stf(gx + e, g * s);
+  }
+  dmod[(long)b * I + i] += acc;
+}
+
+// ------------------------------------------------------------------ aux-decoder patch selection (gigagan_pytorch.py:1300-1312)
+// t (B, pd*hh, pd*ww, C) viewed as pd x pd patches; out (B*nsel, hh, ww, C) row (b*nsel + s) = patch sel[b*nsel+s] of image b.
+// transposed != 0: the gradient - gt (B, pd*hh, pd*ww, C) gets the rows of g scattered back, zero elsewhere (gt is fully
+// written: every pixel belongs to exactly one patch, which is either selected once or not at all).
+template <typename T>
+__global__ void patch_select_kernel(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ sel, int B,
+                                    int nsel, int pd, int hh, int ww, int C, int transposed, long tot) {
+  const int H = pd * hh, W = pd * ww;
+  if (!transposed) {                                   // tot = B*nsel*hh*ww*C
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x) {
+      int c = (int)(e % C);
+      long r = e / C;
+      int xw = (int)(r % ww); r /= ww;
+      int yh = (int)(r % hh); r /= hh;
+      int s = (int)(r % nsel), b = (int)(r / nsel);
+      int pi = sel[b * nsel + s], py = pi / pd, px = pi % pd;
+      dst[e] = src[(((long)b * H + py * hh + yh) * W + px * ww + xw) * C + c];
+    }
+  } else {                                             // tot = B*H*W*C
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long)gridDim.x * blockDim.x) {
+      int c = (int)(e % C);
+      long r = e / C;
+      int X = (int)(r % W); r /= W;
+      int Y = (int)(r % H);
+      int b = (int)(r / H);
+      int pi = (Y / hh) * pd + X / ww;
+      float v = 0.f;
+      for (int s = 0; s < nsel; ++s)
+        if (sel[b * nsel + s] == pi)
+          v = ldf(src + ((((long)b * nsel + s) * hh + Y % hh) * ww + X % ww) * C + c);
+      stf(dst + e, v);
+    }
+  }
+}
+
+extern "C" {
+int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const void* x, void* xs, float* attn, float* dinv,
+                  int B, int n, int O, int I, int KK, int HW, int demod, float eps, int64_t mod_ld, int64_t kmod_ld,
+                  int dtype, gg_stream_t stream) {
+  if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
+  if (n > 1 && !kmod) return gg_fail("gg_sbank_prep: kmod missing");
+  int XB = gg_cdiv((long)B * HW * I, 256 * 4);
+  if (XB < 1) XB = 1;
+  if (XB > 512) XB = 512;
+  GG_DISPATCH(dtype, (sbank_prep_kernel<T><<<O + XB, 256, 0, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I,
+                                                                   KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB)));
+  return gg_check_launch("sbank_prep");
+}
+int gg_sbank_combine_fwd(const void* ycat, const float* attn, const float* dinv, void* y, int B, int HW, int n, int O,
+                         int dtype, gg_stream_t stream) {
+  long tot = (long)B * HW * O;
+  GG_DISPATCH(dtype, (sbank_combine_fwd_kernel<T><<<gg_blocks(tot, 256), 256, 0, ST>>>((const T*)ycat, attn, dinv, (T*)y, HW, n,
+                                                                                       O, tot)));
+  return gg_check_launch("sbank_combine_fwd");
+}
+int gg_sbank_combine_bwd(const void* gy, const void* ycat, const float* attn, const float* dinv, void* gyn, float* gdinv,
+                         float* gattn_ws, int B, int HW, int n, int O, int dtype, gg_stream_t stream) {
+  if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
+  cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, ST);
+  dim3 grid(gg_cdiv(O, 256), B);
+  GG_DISPATCH(dtype, (sbank_combine_bwd_kernel<T><<<grid, 256, 0, ST>>>((const T*)gy, (const T*)ycat, attn, dinv, (T*)gyn, gdinv,
+                                                                        gattn_ws, B, HW, n, O)));
+  return gg_check_launch("sbank_combine_bwd");
+}
+int gg_sbank_bwd_x(const void* gxs, const void* x, const float* mod, void* gx, float* dmod, int B, int HW, int I,
+                   int64_t mod_ld, int dtype, gg_stream_t stream) {
+  dim3 grid(gg_cdiv(I, 256), B);
+  GG_DISPATCH(dtype, (sbank_bwd_x_kernel<T><<<grid, 256, 0, ST>>>((const T*)gxs, (const T*)x, mod, (T*)gx, dmod, HW, I,
+                                                                  (long)mod_ld)));
+  return gg_check_launch("sbank_bwd_x");
+}
+int gg_patch_select(const void* src, void* dst, const int* sel, int B, int nsel, int pd, int hh, int ww, int C,
+                    int transposed, int dtype, gg_stream_t stream) {
+  long tot = transposed ? (long)B * pd * hh * pd * ww * C : (long)B * nsel * hh * ww * C;
+  GG_DISPATCH(dtype, (patch_select_kernel<T><<<gg_blocks(tot, 256), 256, 0, ST>>>((const T*)src, (T*)dst, sel, B, nsel, pd, hh, ww,
+                                                                                  C, transposed, tot)));
+  return gg_check_launch("patch_select");
+}
+}

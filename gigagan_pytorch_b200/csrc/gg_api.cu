@@ -139,13 +139,25 @@ int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx
   return ggi_noise_act_bwd(y, gy, noise, dx, dwn, R, C, dtype, ST);
 }
 int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, gg_stream_t stream) {
-  return ggi_adaconv_weights_fwd(bank, mod, kmod, w, attn, dinv, B, n, O, I, KK, demod, eps, Opad, dtype, ST);
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int64_t mod_ld,
+                           int64_t kmod_ld, int dtype, gg_stream_t stream) {
+  return ggi_adaconv_weights_fwd(bank, mod, kmod, w, attn, dinv, B, n, O, I, KK, demod, eps, Opad, (long)mod_ld,
+                                 (long)kmod_ld, dtype, ST);
 }
 int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, int Opad, gg_stream_t stream) {
-  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, Opad, ST);
+                           int demod, float eps, int Opad, int64_t mod_ld, gg_stream_t stream) {
+  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, gw, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, demod, eps, Opad,
+                                 (long)mod_ld, nullptr, nullptr, ST);
+}
+int gg_sbank_bwd_stats(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gdinv,
+                       const float* dw_add, float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O,
+                       int I, int KK, float eps, int64_t mod_ld, gg_stream_t stream) {
+  return ggi_adaconv_weights_bwd(bank, mod, attn, dinv, nullptr, dbank, dmod, dkmod, gattn_ws, B, n, O, I, KK, 1, eps, O,
+                                 (long)mod_ld, gdinv, dw_add, ST);
+}
+int gg_red_dot_sc_acc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype, gg_stream_t stream) {
+  return ggi_red_dot_sc_acc(a, b, out, R, C, P, Ns, 1, dtype, ST);
 }
 int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale,
@@ -189,8 +201,9 @@ int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const vo
 }
 int gg_debug_mma_chain(int N, int nacc, int iters, void* out, gg_stream_t stream) { return ggi_debug_mma_chain(N, nacc, iters, (unsigned long long*)out, ST); }
 int gg_debug_thin_trace(void* buf) { return ggi_debug_thin_trace((unsigned long long*)buf); }
-int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int dtype, gg_stream_t stream) {
-  return ggi_lrelu_bwd_bias(y, gy, out, dbias, (long)R, C, dtype, ST);
+int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int accumulate, int dtype,
+                      gg_stream_t stream) {
+  return ggi_lrelu_bwd_bias(y, gy, out, dbias, (long)R, C, accumulate, dtype, ST);
 }
 int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, gg_stream_t stream) {
   return ggi_wgrad_sink(dw, dst, O, I, KK, Ipad, ST);

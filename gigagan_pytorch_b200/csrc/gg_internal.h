@@ -25,10 +25,14 @@ int ggi_nhwc_to_nchw(const void* src, float* dst, int N, int C, int HW, int Cp, 
 int ggi_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, long R, int C, int dtype, cudaStream_t st);
 int ggi_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, long R, int C, int dtype, cudaStream_t st);
 int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                            int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, cudaStream_t st);
+                            int B, int n, int O, int I, int KK, int demod, float eps, int Opad, long ldm, long ldk, int dtype,
+                            cudaStream_t st);
 int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                             float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                            int demod, float eps, int Opad, cudaStream_t st);
+                            int demod, float eps, int Opad, long ldm, const float* q_ext, const float* dw_add,
+                            cudaStream_t st);
+int ggi_red_dot_sc_acc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int accumulate, int dtype,
+                       cudaStream_t st);
 int ggi_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, int B, int heads,
                  int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale, int mode, int dtype,
                  cudaStream_t st);
@@ -48,7 +52,8 @@ int ggi_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const v
                     float s, int dtype, cudaStream_t st);
 int ggi_debug_thin_trace(unsigned long long* buf);
 int ggi_debug_mma_chain(int N, int nacc, int iters, unsigned long long* out, cudaStream_t st);
-int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int dtype, cudaStream_t st);
+int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int accumulate, int dtype,
+                       cudaStream_t st);
 int ggi_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, cudaStream_t st);
 int ggi_tc_conv_thin(const void* x, const void* w, const float* bias, const void* res, void* y, int N, int H, int W, int Cin,
                      int OH, int OW, int Cout, int KH, int KW, int stride, int pad, int per_sample_w, int act, float gain,

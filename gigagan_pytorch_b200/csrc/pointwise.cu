@@ -332,10 +332,17 @@ __global__ void dot_sc_flat_kernel(const T* __restrict__ a, const T* __restrict_
     atomicAdd(out + (long)ns * C + t, sres);
   }
 }
+int ggi_red_dot_sc_acc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int accumulate, int dtype,
+                       cudaStream_t st);
 int ggi_red_dot_sc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int dtype, cudaStream_t st) {
+  return ggi_red_dot_sc_acc(a, b, out, R, C, P, Ns, 0, dtype, st);
+}
+// accumulate != 0: out += the sums (out holds a running gradient); 0: out is overwritten
+int ggi_red_dot_sc_acc(const void* a, const void* b, float* out, long R, int C, int P, int Ns, int accumulate, int dtype,
+                       cudaStream_t st) {
   long N = R / P;
   long rows_per_out = (N / Ns) * P;
-  cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Ns * C, st);
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)Ns * C, st);
   int V = dtype == GG_F32 ? 4 : 8;
   dim3 block(32, 8);
   if (C % V == 0 && al16(a) && (!b || al16(b)) && C / V <= 32 && ((C / V) & (C / V - 1)) == 0 && C <= 256) {
@@ -701,22 +708,22 @@ int ggi_noise_act_bwd(const void* y, const void* gy, const float* noise, void* d
 // ------------------------------------------------------------------ AdaptiveConv2DMod weight builder (K1)
 // bank [n][o][i][kk] fp32 (reference layout, kk = k*k); mod [B][I]; kmod [B][n] (null when n == 1)
 // out w [B][o][kk][i] (T, kernel layout), attn [B][n], dinv [B][o] (fp32 stats kept for backward)
-__global__ void adaconv_attn_kernel(const float* __restrict__ kmod, float* __restrict__ attn, int B, int n) {
+__global__ void adaconv_attn_kernel(const float* __restrict__ kmod, float* __restrict__ attn, int B, int n, long ldk) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   if (n == 1) { attn[b] = 1.f; return; }
   float m = -INFINITY;
-  for (int j = 0; j < n; ++j) m = fmaxf(m, kmod[b * n + j]);
+  for (int j = 0; j < n; ++j) m = fmaxf(m, kmod[b * ldk + j]);
   float s = 0.f;
-  for (int j = 0; j < n; ++j) s += expf(kmod[b * n + j] - m);
-  for (int j = 0; j < n; ++j) attn[b * n + j] = expf(kmod[b * n + j] - m) / s;
+  for (int j = 0; j < n; ++j) s += expf(kmod[b * ldk + j] - m);
+  for (int j = 0; j < n; ++j) attn[b * n + j] = expf(kmod[b * ldk + j] - m) / s;
 }
 
 template <typename T>
 __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
                                            const float* __restrict__ attn, T* __restrict__ w,
                                            float* __restrict__ dinv, int n, int O, int I, int KK, int demod, float eps,
-                                           int Opad) {
+                                           int Opad, long ldm) {
   __shared__ float red[32];
   int b = blockIdx.y, o = blockIdx.x;
   int E = I * KK;
@@ -725,7 +732,7 @@ __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const
     int i = e / KK;
     float v = 0.f;
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
-    float u = v * (mod[(long)b * I + i] + 1.f);
+    float u = v * (mod[(long)b * ldm + i] + 1.f);
     ss += u * u;
   }
   float d = 1.f;
@@ -742,7 +749,7 @@ __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const
     int i = e / KK, kk = e % KK;
     float v = 0.f;
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[((long)j * O + o) * E + e];
-    float u = v * (mod[(long)b * I + i] + 1.f);
+    float u = v * (mod[(long)b * ldm + i] + 1.f);
     stf(w + (((long)b * Opad + o) * KK + kk) * I + i, u * d);
   }
 }
@@ -750,7 +757,7 @@ __global__ void adaconv_weights_fwd_kernel(const float* __restrict__ bank, const
 // backward, pass 1 (demod only): q[b,o] = sum_{i,kk} gw * u        (one CTA per (b,o))
 __global__ void adaconv_q_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
                                  const float* __restrict__ attn, const float* __restrict__ gw, float* __restrict__ q,
-                                 int n, int O, int I, int KK, int Opad) {
+                                 int n, int O, int I, int KK, int Opad, long ldm) {
   __shared__ float red[32];
   int b = blockIdx.y, o = blockIdx.x;
   int E = I * KK;
@@ -759,7 +766,7 @@ __global__ void adaconv_q_kernel(const float* __restrict__ bank, const float* __
     int kk = e / I, i = e - kk * I;                        // i fastest: coalesced over gw's kernel layout
     float v = 0.f;
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * bank[(((long)j * O + o) * I + i) * KK + kk];
-    acc += gw[(((long)b * Opad + o) * KK + kk) * I + i] * v * (mod[(long)b * I + i] + 1.f);
+    acc += gw[(((long)b * Opad + o) * KK + kk) * I + i] * v * (mod[(long)b * ldm + i] + 1.f);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -778,7 +785,7 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
                                            const float* __restrict__ q, const float* __restrict__ gw,
                                            float* __restrict__ dbank, float* __restrict__ dmod,
                                            float* __restrict__ gattn, int B, int n, int O, int I, int KK, int demod,
-                                           float eps, int Opad) {
+                                           float eps, int Opad, long ldm, const float* __restrict__ dw_add) {
   extern __shared__ float sm[];              // [KK*32] partial dmod terms, then [B*n] gattn partials
   float* sm_dm = sm;
   float* sm_ga = sm + KK * 32;
@@ -794,8 +801,8 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
     float d = dinv[(long)b * O + o];
     float v = 0.f;
     for (int j = 0; j < n; ++j) v += attn[b * n + j] * wb[j];
-    float s = live ? mod[(long)b * I + i] + 1.f : 0.f;
-    float g = live ? gw[(((long)b * Opad + o) * KK + kk) * I + i] : 0.f;
+    float s = live ? mod[(long)b * ldm + i] + 1.f : 0.f;
+    float g = (live && gw) ? gw[(((long)b * Opad + o) * KK + kk) * I + i] : 0.f;
     float gu = d * g;
     if (demod && d * d * eps < 0.999999f) gu -= d * d * d * (v * s) * q[(long)b * O + o];
     float gv = gu * s;
@@ -813,9 +820,124 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
     }
     __syncthreads();
   }
-  if (live)
-    for (int j = 0; j < n; ++j) dbank[(((long)j * O + o) * I + i) * KK + kk] = acc[j];
+  if (live)                 // dw_add: kernel-layout [n][O][KK][I] weight gradients of the shared-bank convolutions, folded in
+    for (int j = 0; j < n; ++j)
+      dbank[(((long)j * O + o) * I + i) * KK + kk] = acc[j] + (dw_add ? dw_add[(((long)j * O + o) * KK + kk) * I + i] : 0.f);
   for (int t = threadIdx.x; t < B * n; t += blockDim.x) atomicAdd(gattn + t, sm_ga[t]);
+}
+
+// Restructured pass 2 (KK = 1 or 9, batch chunks of <= 16 images): lane = input channel of a 32-channel tile, each of
+// the 8 warps walks output channels o0+w, o0+w+8, ... of the block's OC-channel range.  dmod is accumulated over the
+// whole o range in registers (one atomic per (block, b, i) instead of one per (b, o, i): the 512-way contention on
+// dmod made the 512x512 layers take 330 us), gattn through per-warp shared-memory slots.  accumulate != 0: dbank +=.
+#define AB_BCH 16
+#define AB_OC 32
+template <int KK, int NK>
+__global__ void __launch_bounds__(256)
+adaconv_weights_bwd2_kernel(const float* __restrict__ bank, const float* __restrict__ mod, const float* __restrict__ attn,
+                            const float* __restrict__ dinv, const float* __restrict__ q, const float* __restrict__ gw,
+                            float* __restrict__ dbank, float* __restrict__ dmod, float* __restrict__ gattn, int b0, int nb,
+                            int n, int O, int I, int demod, float eps, int Opad, long ldm,
+                            const float* __restrict__ dw_add, int accumulate) {
+  __shared__ float sa[AB_BCH][8];
+  __shared__ float sm_ga[8][AB_BCH][8];
+  __shared__ float sm_dm[8][AB_BCH][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane, o0 = blockIdx.y * AB_OC;
+  const bool live = i < I;
+  for (int t = threadIdx.x; t < AB_BCH * 8; t += blockDim.x) {
+    int bb = t >> 3, j = t & 7;
+    sa[bb][j] = (bb < nb && j < n) ? attn[(b0 + bb) * n + j] : 0.f;
+    for (int w = 0; w < 8; ++w) sm_ga[w][bb][j] = 0.f;
+  }
+  __syncthreads();
+  float dm[AB_BCH], sv[AB_BCH];
+#pragma unroll
+  for (int t = 0; t < AB_BCH; ++t) { dm[t] = 0.f; sv[t] = (live && t < nb) ? mod[(long)(b0 + t) * ldm + i] + 1.f : 0.f; }
+  for (int oo = warp; oo < AB_OC && o0 + oo < O; oo += 8) {
+    const int o = o0 + oo;
+    float wb[NK][KK], acc[NK][KK];
+#pragma unroll
+    for (int j = 0; j < NK; ++j)
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        wb[j][kk] = (live && j < n) ? bank[(((long)j * O + o) * I + i) * KK + kk] : 0.f;
+        acc[j][kk] = 0.f;
+      }
+#pragma unroll
+    for (int t = 0; t < AB_BCH; ++t) {
+      if (t >= nb) break;
+      const int b = b0 + t;
+      const float d = dinv[(long)b * O + o], s = sv[t];
+      const float qv = demod ? q[(long)b * O + o] : 0.f;
+      const bool clamp = !(demod && d * d * eps < 0.999999f);
+      float dmv = 0.f, gvw[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) gvw[j] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) v += sa[t][j] * wb[j][kk];
+        const float g = (live && gw) ? gw[(((long)b * Opad + o) * KK + kk) * I + i] : 0.f;
+        float gu = d * g;
+        if (!clamp) gu -= d * d * d * (v * s) * qv;
+        const float gv = gu * s;
+        dmv += gu * v;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) { acc[j][kk] += sa[t][j] * gv; gvw[j] += gv * wb[j][kk]; }
+      }
+      dm[t] += dmv;
+#pragma unroll
+      for (int j = 0; j < NK; ++j) {
+        if (j < n) {
+          const float r = warp_sum(gvw[j]);
+          if (lane == 0) sm_ga[warp][t][j] += r;
+        }
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < NK; ++j)
+        if (j < n) {
+#pragma unroll
+          for (int kk = 0; kk < KK; ++kk) {
+            const long at = (((long)j * O + o) * I + i) * KK + kk;
+            float r = acc[j][kk] + (dw_add ? dw_add[(((long)j * O + o) * KK + kk) * I + i] : 0.f);
+            dbank[at] = accumulate ? dbank[at] + r : r;
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < AB_BCH; ++t) sm_dm[warp][t][lane] = dm[t];
+  __syncthreads();
+  for (int t = warp; t < nb; t += 8) {
+    float r = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sm_dm[w][t][lane];
+    if (live) atomicAdd(dmod + (long)(b0 + t) * I + i, r);
+  }
+  for (int t = threadIdx.x; t < nb * 8; t += blockDim.x) {
+    const int bb = t >> 3, j = t & 7;
+    if (j < n) {
+      float r = 0.f;
+      for (int w = 0; w < 8; ++w) r += sm_ga[w][bb][j];
+      atomicAdd(gattn + (b0 + bb) * n + j, r);
+    }
+  }
+}
+template <int KK>
+static void launch_bwd2(dim3 grid, cudaStream_t st, int nk, const float* bank, const float* mod, const float* attn,
+                        const float* dinv, const float* q, const float* gw, float* dbank, float* dmod, float* gattn, int b0,
+                        int nb, int n, int O, int I, int demod, float eps, int Opad, long ldm, const float* dw_add, int acc) {
+#define AB_GO(NK) adaconv_weights_bwd2_kernel<KK, NK><<<grid, 256, 0, st>>>(bank, mod, attn, dinv, q, gw, dbank, dmod, gattn, \
+                                                                           b0, nb, n, O, I, demod, eps, Opad, ldm, dw_add, acc)
+  if (nk <= 1) AB_GO(1);
+  else if (nk <= 2) AB_GO(2);
+  else if (nk <= 4) AB_GO(4);
+  else AB_GO(8);
+#undef AB_GO
 }
 
 // dkmod = attn * (gattn - sum_j attn_j gattn_j)
@@ -829,29 +951,45 @@ __global__ void adaconv_kmod_bwd_kernel(const float* __restrict__ attn, const fl
 }
 
 int ggi_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, cudaStream_t st) {
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, long ldm, long ldk, int dtype,
+                           cudaStream_t st) {
   if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
-  adaconv_attn_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(kmod, attn, B, n);
+  adaconv_attn_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(kmod, attn, B, n, ldk);
   dim3 grid(O, B);
-  GG_DISPATCH(dtype, (adaconv_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(bank, mod, attn, (T*)w, dinv, n, O, I, KK, demod, eps, Opad)));
+  GG_DISPATCH(dtype, (adaconv_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(bank, mod, attn, (T*)w, dinv, n, O, I, KK, demod, eps, Opad, ldm)));
   return gg_check_launch("adaconv_weights_fwd");
 }
+// gw != NULL: gradient of the materialised per-sample weights (q computed here);  gw == NULL: shared-bank form, only the
+// demodulation chain is differentiated: q_ext[b][o] = dL/d dinv, gattn_ws[0 .. B*n) already holds the caller's direct
+// dL/d attn (NOT cleared here), dw_add = kernel-layout weight gradients of the bank convolutions to fold into dbank.
 int ggi_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, int Opad, cudaStream_t st) {
+                           int demod, float eps, int Opad, long ldm, const float* q_ext, const float* dw_add,
+                           cudaStream_t st) {
   // gattn_ws: B*n floats of gattn followed by B*O floats for q
   float* q = gattn_ws + (size_t)B * n;
   cudaMemsetAsync(dmod, 0, sizeof(float) * (size_t)B * I, st);
-  cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, st);
+  if (gw) cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, st);
   if (KK > 32) return gg_fail("adaconv backward: kernel area %d unsupported", KK);
-  if (demod) {
+  if (demod && gw) {
     dim3 g1(O, B);
-    adaconv_q_kernel<<<g1, 256, 0, st>>>(bank, mod, attn, gw, q, n, O, I, KK, Opad);
+    adaconv_q_kernel<<<g1, 256, 0, st>>>(bank, mod, attn, gw, q, n, O, I, KK, Opad, ldm);
   }
-  dim3 grid(gg_cdiv(I, 32), O);
-  size_t smem = sizeof(float) * ((size_t)KK * 32 + (size_t)B * n);
-  adaconv_weights_bwd_kernel<<<grid, 32 * KK, smem, st>>>(bank, mod, attn, dinv, q, gw, dbank, dmod, gattn_ws, B, n, O, I,
-                                                         KK, demod, eps, Opad);
+  if (KK == 9 || KK == 1) {
+    dim3 grid(gg_cdiv(I, 32), gg_cdiv(O, AB_OC));
+    for (int b0 = 0; b0 < B; b0 += AB_BCH) {
+      int nb = B - b0 < AB_BCH ? B - b0 : AB_BCH;
+      if (KK == 9) launch_bwd2<9>(grid, st, n, bank, mod, attn, dinv, gw ? q : q_ext, gw, dbank, dmod, gattn_ws, b0, nb, n, O, I,
+                                  demod, eps, Opad, ldm, b0 == 0 ? dw_add : nullptr, b0 > 0);
+      else launch_bwd2<1>(grid, st, n, bank, mod, attn, dinv, gw ? q : q_ext, gw, dbank, dmod, gattn_ws, b0, nb, n, O, I, demod,
+                          eps, Opad, ldm, b0 == 0 ? dw_add : nullptr, b0 > 0);
+    }
+  } else {
+    dim3 grid(gg_cdiv(I, 32), O);
+    size_t smem = sizeof(float) * ((size_t)KK * 32 + (size_t)B * n);
+    adaconv_weights_bwd_kernel<<<grid, 32 * KK, smem, st>>>(bank, mod, attn, dinv, gw ? q : q_ext, gw, dbank, dmod, gattn_ws,
+                                                           B, n, O, I, KK, demod, eps, Opad, ldm, dw_add);
+  }
   if (n > 1 && dkmod) adaconv_kmod_bwd_kernel<<<gg_cdiv(B, 128), 128, 0, st>>>(attn, gattn_ws, dkmod, B, n);
   return gg_check_launch("adaconv_weights_bwd");
 }
@@ -985,12 +1123,13 @@ __global__ void lrelu_bwd_bias_kernel(const T* __restrict__ y, const T* __restri
   }
 }
 // returns 1 when the shape is not covered (caller composes unary + dot_sc)
-int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int dtype, cudaStream_t st) {
+int ggi_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, long R, int C, int accumulate, int dtype,
+                       cudaStream_t st) {
   int V = dtype == GG_F32 ? 4 : 8;
   if (C % V || !al16(y) || !al16(gy) || !al16(out)) return 1;
   int nvec = C / V;
   if (nvec > 256 || (nvec & (nvec - 1))) return 1;
-  cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
+  if (!accumulate) cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
   int lanes = 256 / nvec;
   int blocks = gg_blocks((R + lanes - 1) / lanes * 256, 256, 148 * 8);
   GG_DISPATCH(dtype, (lrelu_bwd_bias_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, (const T*)gy, (T*)out, dbias, R, C, nvec)));

@@ -114,7 +114,9 @@ class AdaptiveConv2DMod(nn.Module):
         self.demod = demod
         nn.init.kaiming_normal_(self.weights, a=0, mode="fan_in", nonlinearity="leaky_relu")
 
-    def forward_nhwc(self, x, mod, kernel_mod=None, out_pad=0):
+    def forward_nhwc(self, x, mod, kernel_mod=None, out_pad=0, fused=None):
+        """``fused`` (default: the first-order switch shared with the attention blocks): low-resolution layers run as
+        one fused autograd node (ops.SharedBankConvFn); False keeps the any-order differentiable composition."""
         b = x.shape[0]
         if mod.shape[0] != b:                       # scale-major repeat, ref :365-366
             mod = mod.repeat(b // mod.shape[0], 1)
@@ -127,6 +129,9 @@ class AdaptiveConv2DMod(nn.Module):
             kernel_mod = None
         hw = x.shape[1] * x.shape[2]
         if x.dtype == torch.bfloat16 and hw < 128 and self.eps == 1e-8:
+            fused = _COMPUTE["fused_attention"] if fused is None else fused
+            if fused and self.demod and out_pad <= self.dim_out:
+                return ops.shared_bank_conv(x, self.weights, mod, kernel_mod, self.eps)
             return self._forward_shared_bank(x, mod, kernel_mod, out_pad)
         w = ops.AdaConvWeightsFn.apply(self.weights, mod, kernel_mod, self.demod, self.eps, x.dtype, out_pad)
         return ops.conv2d_prepared(x, w, pad=(self.kernel - 1) // 2, per_sample=True)
@@ -476,7 +481,7 @@ class SimpleDecoder(nn.Module):
         super().__init__()
         assert 0 < frac_patches <= 1.
         self.patch_dim, self.frac_patches = patch_dim, frac_patches
-        self.static_onehot = None        # trainer-owned device buffer (nsel, B, total) when running under CUDA graphs
+        self.static_sel = None           # trainer-owned device buffer int32 (B, nsel) when running under CUDA graphs
         self.dropout = nn.Dropout(dropout)
         dims = [dim, *dims]
         layers = [nn.Conv2d(dim, dim, 3, padding=1)]
@@ -485,14 +490,13 @@ class SimpleDecoder(nn.Module):
                                         nn.LeakyReLU(0.2)))
         self.net = nn.Sequential(*layers)
 
-    def draw_patch_selection(self, b):
-        """one-hot (nsel, b, patches) of the randomly kept patches; CPU randn argsort like the reference (:1310)."""
+    def draw_patch_indices(self, b):
+        """int32 (b, nsel): indices p1*patch_dim+p2 of the randomly kept patches; CPU randn argsort like the reference
+        (:1310), same host RNG consumption."""
         total = self.patch_dim ** 2
         nsel = max(int(self.frac_patches * total), 1)
         perm = torch.randn((b, total)).sort(dim=-1).indices[:, :nsel]
-        onehot = torch.zeros((nsel, b, total))
-        onehot.scatter_(2, perm.t()[..., None], 1.0)
-        return onehot
+        return perm.to(torch.int32).contiguous()
 
     def forward_nhwc(self, fmap, image_nhwc):
         """fmap (B,h,w,C) compute dtype; image_nhwc (B,H,W,3).  RNG draws mirror ref :1295,:1310 (dropout on the
@@ -505,24 +509,13 @@ class SimpleDecoder(nn.Module):
             pd = self.patch_dim
             total = pd * pd
             nsel = max(int(self.frac_patches * total), 1)
-            if self.static_onehot is not None:
-                onehot = self.static_onehot
+            if self.static_sel is not None:
+                sel = self.static_sel
             else:
-                onehot = self.draw_patch_selection(b).to(fmap.device, non_blocking=True)
+                sel = self.draw_patch_indices(b).to(fmap.device, non_blocking=True)
 
-            def pick(t):   # '(b p) ...' selection as a one-hot weighted sum of the p1 x p2 sub-blocks
-                hh, ww = t.shape[1] // pd, t.shape[2] // pd
-                outs = []
-                for s in range(nsel):
-                    acc = None
-                    for pi in range(total):
-                        py, px = pi // pd, pi % pd
-                        blk = t[:, py * hh:(py + 1) * hh, px * ww:(px + 1) * ww, :]
-                        sel = onehot[s, :, pi].reshape(b, 1).expand(b, t.shape[-1]).contiguous()
-                        term = ops.scale_channels(blk, sel, hh * ww, b)
-                        acc = term if acc is None else ops.add(acc, term)
-                    outs.append(acc)
-                return outs[0] if nsel == 1 else torch.stack(outs, dim=1).flatten(0, 1)
+            def pick(t):   # '(b p) ...' selection of the kept p1 x p2 sub-blocks: one gather launch
+                return ops.patch_select(t, sel, pd)
 
             fmap, image_nhwc = pick(fmap), pick(image_nhwc)
         x = ops.conv2d(fmap, self.net[0].weight, self.net[0].bias, pad=1)
@@ -557,7 +550,7 @@ class Predictor(nn.Module):
                 self.layers.append(nn.ModuleList([c1, l1, c2, nn.LeakyReLU(0.2)]))
         self.to_logits = nn.Conv2d(dim, 1, 1)
 
-    def forward_nhwc(self, x, mod=None, kernel_mod=None):
+    def forward_nhwc(self, x, mod=None, kernel_mod=None, fused=None):
         residual = ops.conv2d(x, self.residual_fn.weight, self.residual_fn.bias)
         for conv1, _, conv2, _ in self.layers:
             inner = x
@@ -565,8 +558,8 @@ class Predictor(nn.Module):
                 x = ops.conv2d(x, conv1.weight, conv1.bias, pad=1, act=1)
                 x = ops.conv2d(x, conv2.weight, conv2.bias, pad=1, act=1)
             else:
-                x = ops.leaky_relu(conv1.forward_nhwc(x, mod, kernel_mod))
-                x = ops.leaky_relu(conv2.forward_nhwc(x, mod, kernel_mod))
+                x = ops.leaky_relu(conv1.forward_nhwc(x, mod, kernel_mod, fused=fused))
+                x = ops.leaky_relu(conv2.forward_nhwc(x, mod, kernel_mod, fused=fused))
             x = ops.axpby(self.residual_scale, x, self.residual_scale, inner)
         x = ops.add(x, residual)
         n, h, w, c = x.shape
@@ -733,7 +726,7 @@ class Discriminator(nn.Module):
             if exists(predictor):
                 pk = dict(mod=next(conv_mods), kernel_mod=next(conv_mods)) if exists(conv_mods) else {}
                 if return_multiscale_outputs:
-                    ms_outputs.append(predictor.forward_nhwc(x[:prev], **pk))
+                    ms_outputs.append(predictor.forward_nhwc(x[:prev], fused=fused_attention, **pk))
             if exists(downsample):     # pixel-unshuffle + 1x1 == 2x2 stride-2 conv (ref :289-293)
                 w = downsample[1].weight
                 w2 = w.view(w.shape[0], w.shape[1] // 4, 2, 2)

@@ -298,6 +298,7 @@ class Conv2dFn(Function):
         assert not (geom.act and (res is not None or geom.gain != 1.0)), "act and res/gain epilogues are exclusive"
         y = _conv_fprop_raw(x, wk, bias, None if res is None else _c(res), geom, out_c)
         ctx.geom, ctx.master, ctx.has_bias, ctx.has_res = geom, master, bias is not None, res is not None
+        ctx.bias_ref = bias if (bias is not None and getattr(bias, "_gg_sink1", False)) else None
         ctx.save_for_backward(x, weight, y if geom.act else None)
         return y
 
@@ -310,9 +311,14 @@ class Conv2dFn(Function):
         gres = gy if ctx.has_res else None
         gx = gw = gb = None
         want_gb = ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads()
+        bias_sink = None
+        if want_gb and not torch.is_grad_enabled():
+            bias_sink = _bias_sink(ctx.bias_ref)               # terminal pass: add straight into the flat gradient buffer
         if g.act:
             if want_gb and not torch.is_grad_enabled() and _lrelu_bias_fusable(y):
-                gy, gb = _lrelu_bwd_bias(y, gy)             # one pass: activation gradient + bias gradient
+                gy, gb = _lrelu_bwd_bias(y, gy, bias_sink)  # one pass: activation gradient + bias gradient
+                if bias_sink is not None:
+                    want_gb = False
             else:
                 gy = Unary1Fn.apply(U_LRELU, y, gy)
         pg = g.plain()
@@ -322,7 +328,12 @@ class Conv2dFn(Function):
             if not (ctx.master and _wgrad_to_sink(x, gy, pg, weight)):
                 gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
         if want_gb and gb is None:
-            gb = dot_sc(gy, None, gy.numel() // gy.shape[-1], 1).reshape(-1)
+            if bias_sink is not None:
+                gyc = _c(gy)
+                C = gyc.shape[-1]
+                call("gg_red_dot_sc_acc", _p(gyc), None, _p(bias_sink), gyc.numel() // C, C, gyc.numel() // C, 1, _dt(gyc), _st())
+            else:
+                gb = dot_sc(gy, None, gy.numel() // gy.shape[-1], 1).reshape(-1)
         return gx, gw, gb, gres, None, None
 
 
@@ -353,14 +364,27 @@ def _lrelu_bias_fusable(y):
     return y.shape[-1] % (8 if y.dtype == torch.bfloat16 else 4) == 0 and 0 < nvec <= 256 and (nvec & (nvec - 1)) == 0
 
 
-def _lrelu_bwd_bias(y, gy):
-    """terminal backward of a bias + LeakyReLU conv epilogue: (gy * lrelu'(y), column sums of it)"""
+def _bias_sink(bias):
+    """the fp32 .grad slice of a 1-D parameter that lives in an optimiser's flat gradient buffer (FlatAdamW marks those
+    with ``_gg_sink1``), or None: bias gradients are then ADDED there by the reduction kernel itself instead of going
+    through a temporary + autograd's AccumulateGrad (one launch instead of memset + kernel + add per bias)"""
+    if bias is None:
+        return None
+    dst = bias.grad
+    if dst is None or dst.dtype != torch.float32 or not dst.is_contiguous():
+        return None
+    return dst
+
+
+def _lrelu_bwd_bias(y, gy, sink=None):
+    """terminal backward of a bias + LeakyReLU conv epilogue: (gy * lrelu'(y), column sums of it).  With ``sink`` the
+    column sums are added to it and None is returned for them."""
     y, gy = _c(y), _c(gy)
     C = y.shape[-1]
     out = torch.empty_like(gy)
-    gb = torch.empty(C, dtype=torch.float32, device=y.device)
-    call("gg_lrelu_bwd_bias", _p(y), _p(gy), _p(out), _p(gb), y.numel() // C, C, _dt(y), _st())
-    return out, gb
+    gb = sink if sink is not None else torch.empty(C, dtype=torch.float32, device=y.device)
+    call("gg_lrelu_bwd_bias", _p(y), _p(gy), _p(out), _p(gb), y.numel() // C, C, int(sink is not None), _dt(y), _st())
+    return out, (None if sink is not None else gb)
 
 
 def _wgrad_to_sink(x, gy, geom, weight):
@@ -753,8 +777,12 @@ def mean_hw(x):
 
 
 def sum_all(x):
-    """scalar fp32 sum of any tensor"""
-    return dot_sc(x.reshape(-1, 1), None, x.numel(), 1).reshape(())
+    """scalar fp32 sum of any tensor (large tensors: 64 column sums with vector loads first, then their sum)"""
+    n = x.numel()
+    if n >= 4096 and n % 64 == 0:
+        x = dot_sc(x.reshape(-1, 64), None, n // 64, 1)
+        n = 64
+    return dot_sc(x.reshape(-1, 1), None, n, 1).reshape(())
 
 
 class SoftmaxFn(Function):
@@ -963,26 +991,36 @@ def to_nchw(x, c):
 
 
 # ============================================================================= generator-only fused ops (first-order)
+def _rows(t):
+    """fp32 2-D statistic (B, C) as the kernels read it: unit column stride, any row stride (column slices of the style
+    projection are used in place, no copy)"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        t = t.contiguous()
+    return t
+
+
 class AdaConvWeightsFn(Function):
     """Per-sample modulated / demodulated filter from the bank (ref gigagan_pytorch.py:378-400).
     bank (n,O,I,k,k) fp32; mod (B,I) fp32; kmod (B,n) fp32 or None -> (B,O,k,k,I) kernel layout, compute dtype."""
 
     @staticmethod
     def forward(ctx, bank, mod, kmod, demod, eps, dtype, opad=0):
-        bank, mod = _c(bank), _c(mod.float())
+        bank, mod = _c(bank), _rows(mod)
         n, O, I, k, _ = bank.shape
         B = mod.shape[0]
         opad = max(opad, O)
         if n > 1:
             assert kmod is not None and kmod.numel() > 0
-            kmod = _c(kmod.float())
+            kmod = _rows(kmod)
         else:
             kmod = None
         w = (torch.empty if opad == O else torch.zeros)((B, opad, k, k, I), dtype=dtype, device=bank.device)
         attn = torch.empty((B, n), dtype=torch.float32, device=bank.device)
         dinv = torch.empty((B, O), dtype=torch.float32, device=bank.device)
         call("gg_adaconv_weights_fwd", _p(bank), _p(mod), _p(kmod), _p(w), _p(attn), _p(dinv), B, n, O, I, k * k,
-             int(demod), float(eps), opad, _dt(w), _st())
+             int(demod), float(eps), opad, mod.stride(0), 0 if kmod is None else kmod.stride(0), _dt(w), _st())
         ctx.cfg = (demod, eps, kmod is not None, opad)
         ctx.save_for_backward(bank, mod, attn, dinv)
         return w
@@ -996,11 +1034,11 @@ class AdaConvWeightsFn(Function):
         B = mod.shape[0]
         gw = _c(gw.float())
         dbank = torch.empty_like(bank)
-        dmod = torch.empty_like(mod)
+        dmod = torch.empty((B, I), dtype=torch.float32, device=bank.device)
         dkmod = torch.empty((B, n), dtype=torch.float32, device=bank.device) if has_kmod else None
         ws = torch.empty((B * n + B * O,), dtype=torch.float32, device=bank.device)
         call("gg_adaconv_weights_bwd", _p(bank), _p(mod), _p(attn), _p(dinv), _p(gw), _p(dbank), _p(dmod), _p(dkmod),
-             _p(ws), B, n, O, I, k * k, int(demod), float(eps), opad, _st())
+             _p(ws), B, n, O, I, k * k, int(demod), float(eps), opad, mod.stride(0), _st())
         return dbank, dmod, dkmod, None, None, None, None
 
 
@@ -1078,6 +1116,116 @@ class FusedAttnFn(Function):
 def fused_attention(q, k, v, null_kv, heads, scale, l2=False):
     shared = k is q
     return FusedAttnFn.apply(q, k, v, null_kv, heads, scale, l2, shared)
+
+
+class SharedBankConvFn(Function):
+    """AdaptiveConv2DMod (ref gigagan_pytorch.py:378-409) of the 4x4 / 8x8 layers in shared-bank form, ONE autograd node:
+        y_b = dinv_b (.) sum_n attn_bn conv(x_b * (mod_b + 1), W_n)
+    forward: prep (attn, dinv, xs) -> one dense tcgen05 convolution over the concatenated bank [W_0; ..; W_{n-1}] whose
+    128-row tiles span images -> combine;  backward: combine^T, n data-gradient convolutions accumulated through the
+    residual epilogue, n weight-gradient launches into one [n][O][KK][I] buffer, the demodulation chain (which also
+    folds the weight gradients into the bank's layout), and the input scaling.  First-order only (the generator is never
+    inside the gradient penalty); ``AdaptiveConv2DMod._forward_shared_bank`` is the any-order composed form.
+    x (B,H,W,I) compute dtype; bank (n,O,I,k,k) fp32 master; mod (B,I), kmod (B,n) fp32 (column slices allowed)."""
+
+    @staticmethod
+    def forward(ctx, x, bank, mod, kmod, eps):
+        x, bank, mod = _c(x), _c(bank), _rows(mod)
+        B, H, W, I = x.shape
+        n, O, _, k, _ = bank.shape
+        kmod = _rows(kmod) if n > 1 else None
+        dev, dt = x.device, x.dtype
+        wks = [prep_weight(bank[j], I, dt) for j in range(n)]            # kernel layout (O,k,k,I) each
+        per = wks[0].numel() * wks[0].element_size()
+        if all(wks[j].data_ptr() == wks[0].data_ptr() + j * per for j in range(n)) and n > 1 and wks[0]._base is not None:
+            base = wks[0]._base                                          # views of the weight bank: already back to back
+            off = (wks[0].data_ptr() - base.data_ptr()) // base.element_size()
+            wcat = base[off:off + n * wks[0].numel()].view(n * O, k, k, I)
+        else:
+            wcat = wks[0] if n == 1 else torch.cat(wks, dim=0)
+        xs = torch.empty_like(x)
+        attn = torch.empty((B, n), dtype=torch.float32, device=dev)
+        dinv = torch.empty((B, O), dtype=torch.float32, device=dev)
+        call("gg_sbank_prep", _p(bank), _p(mod), _p(kmod), _p(x), _p(xs), _p(attn), _p(dinv), B, n, O, I, k * k, H * W, 1,
+             float(eps), mod.stride(0), 0 if kmod is None else kmod.stride(0), _dt(x), _st())
+        pad = (k - 1) // 2
+        ycat = _conv_fprop_raw(xs, wcat, None, None, ConvGeom(k, k, 1, pad), n * O)
+        y = torch.empty((B, H, W, O), dtype=dt, device=dev)
+        call("gg_sbank_combine_fwd", _p(ycat), _p(attn), _p(dinv), _p(y), B, H * W, n, O, _dt(x), _st())
+        ctx.cfg = (float(eps), kmod is not None)
+        ctx.wks = wks
+        ctx.save_for_backward(x, xs, ycat, attn, dinv, bank, mod)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, xs, ycat, attn, dinv, bank, mod = ctx.saved_tensors
+        eps, has_kmod = ctx.cfg
+        B, H, W, I = x.shape
+        n, O, _, k, _ = bank.shape
+        dev, dt = x.device, x.dtype
+        gy = _c(gy)
+        gyn = torch.empty((n, B, H, W, O), dtype=dt, device=dev)
+        ws = torch.empty((B * n + B * O,), dtype=torch.float32, device=dev)      # gattn | (unused q slot)
+        gdinv = torch.empty((B, O), dtype=torch.float32, device=dev)
+        call("gg_sbank_combine_bwd", _p(gy), _p(ycat), _p(attn), _p(dinv), _p(gyn), _p(gdinv), _p(ws), B, H * W, n, O,
+             _dt(x), _st())
+        pad = (k - 1) // 2
+        gt = ConvGeom(k, k, 1, k - 1 - pad)
+        gxs = None
+        for j in range(n):                      # d xs = sum_j conv^T(gy_j, W_j): accumulated by the residual epilogue
+            gxs = _conv_fprop_raw(gyn[j], flipped_weight(ctx.wks[j]), None, gxs, gt, I)
+        dwk = torch.empty((n, O, k, k, I), dtype=torch.float32, device=dev)
+        with _Timed("wgrad", 2.0 * n * B * H * W * O * I * k * k, dt, f"wgrad sbank n{B} {H}x{W} {I}->{n}x{O} k{k}"):
+            for j in range(n):
+                call("gg_conv2d_wgrad", _p(xs), _p(gyn[j]), dwk[j].data_ptr(), B, H, W, I, H, W, O, k, k, 1, pad, 0,
+                     _dt(x), _st())
+        dbank = torch.empty_like(bank)
+        dmod = torch.empty((B, I), dtype=torch.float32, device=dev)
+        dkmod = torch.empty((B, n), dtype=torch.float32, device=dev) if has_kmod else None
+        call("gg_sbank_bwd_stats", _p(bank), _p(mod), _p(attn), _p(dinv), _p(gdinv), _p(dwk), _p(dbank), _p(dmod),
+             _p(dkmod), _p(ws), B, n, O, I, k * k, eps, mod.stride(0), _st())
+        gx = torch.empty_like(x)
+        call("gg_sbank_bwd_x", _p(gxs), _p(x), _p(mod), _p(gx), _p(dmod), B, H * W, I, mod.stride(0), _dt(x), _st())
+        return gx, dbank, dmod, dkmod, None
+
+
+def shared_bank_conv(x, bank, mod, kmod, eps):
+    return SharedBankConvFn.apply(x, bank, mod, kmod, eps)
+
+
+class PatchSelectFn(Function):
+    """rows (b, s) of the output = patch sel[b, s] of image b (the auxiliary decoder's random patch subset, ref
+    gigagan_pytorch.py:1300-1312).  t (B, pd*hh, pd*ww, C); sel int32 (B, nsel) on the device.  Linear: the backward is
+    the adjoint scatter (also differentiable: it is this same operator with the roles swapped)."""
+
+    @staticmethod
+    def forward(ctx, t, sel, pd, transposed):
+        t = _c(t)
+        B, nsel = sel.shape
+        assert sel.dtype == torch.int32 and sel.is_contiguous()
+        if not transposed:
+            _, H, W, C = t.shape
+            hh, ww = H // pd, W // pd
+            out = torch.empty((B * nsel, hh, ww, C), dtype=t.dtype, device=t.device)
+        else:
+            _, hh, ww, C = t.shape
+            out = torch.empty((B, pd * hh, pd * ww, C), dtype=t.dtype, device=t.device)
+        call("gg_patch_select", _p(t), _p(out), _p(sel), B, nsel, pd, hh, ww, C, int(transposed), _dt(t), _st())
+        ctx.cfg = (pd, transposed)
+        ctx.save_for_backward(sel)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (sel,) = ctx.saved_tensors
+        pd, transposed = ctx.cfg
+        return PatchSelectFn.apply(g, sel, pd, not transposed), None, None, None
+
+
+def patch_select(t, sel, pd):
+    return PatchSelectFn.apply(t, sel, pd, False)
 
 
 # ============================================================================= GAN objective (first-order)

@@ -139,6 +139,7 @@ class FlatAdamW:
             p.data = self.flat[off:off + n].view(p.shape)
             p.grad = self.grad[off:off + n].view(p.shape)
             p._gg_sink = p.ndim == 4            # conv weights: wgrad kernels accumulate straight into the flat gradient
+            p._gg_sink1 = p.ndim == 1           # biases: the reduction kernels add straight into it as well
             decay = 1 if p.ndim >= 2 else 0
             for s in range(0, n, self.CHUNK):
                 o = off + s
@@ -745,16 +746,16 @@ class GigaGAN(nn.Module):
         for layer in self.D.layers:               # fresh random patch selection for the aux decoder (host RNG)
             dec = layer[6]
             if dec is not None and dec.frac_patches < 1.:
-                sel = dec.draw_patch_selection(real.shape[0])
-                if dec.static_onehot is None or dec.static_onehot.shape != sel.shape:
-                    dec.static_onehot = torch.empty(sel.shape, dtype=torch.float32, device=self.device)
-                    dec._pinned_sel = torch.empty(sel.shape, dtype=torch.float32).pin_memory()
+                sel = dec.draw_patch_indices(real.shape[0])
+                if dec.static_sel is None or dec.static_sel.shape != sel.shape:
+                    dec.static_sel = torch.empty(sel.shape, dtype=torch.int32, device=self.device)
+                    dec._pinned_sel = torch.empty(sel.shape, dtype=torch.int32).pin_memory()
                     dec._pinned_evt = None
                     self._graphs.clear()
                 if dec._pinned_evt is not None:   # the previous step's H2D copy may still be queued (no host sync per step)
                     dec._pinned_evt.synchronize()
                 dec._pinned_sel.copy_(sel)
-                dec.static_onehot.copy_(dec._pinned_sel, non_blocking=True)
+                dec.static_sel.copy_(dec._pinned_sel, non_blocking=True)
                 dec._pinned_evt = torch.cuda.Event()
                 dec._pinned_evt.record()
 

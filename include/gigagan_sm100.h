@@ -76,6 +76,9 @@ int gg_pw_bcast(const void* x, const float* s, void* out, int64_t R, int C, int 
 int gg_red_rowdot(const void* a, const void* b, float* out, int64_t R, int C, int dtype, gg_stream_t stream);
 int gg_red_dot_sc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype,
                   gg_stream_t stream);
+/* same reduction ADDED to out (a running fp32 gradient, e.g. a bias's slice of the flat gradient buffer) */
+int gg_red_dot_sc_acc(const void* a, const void* b, float* out, int64_t R, int C, int P, int Ns, int dtype,
+                      gg_stream_t stream);
 /* row softmax over the last axis of [R,C] of (s + bias); bias fp32 [Ns][C] (nullable), row r uses bias row
  * (r / P) % Ns  (gigagan_pytorch.py:584-588 with the key bias of the L2 logits, :649; attend.py:104) */
 int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C, int P, int Ns, int dtype,
@@ -109,12 +112,41 @@ int gg_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx
  * modulation, demodulation.  bank [n][O][I][KK] fp32; mod [B][I]; kmod [B][n] (NULL if n==1);
  * w [B][Opad][KK][I] (rows O..Opad-1 are left untouched: pre-zeroed padding so Cout is a multiple of 16);
  * attn [B][n], dinv [B][O] saved for backward. */
+/* mod_ld / kmod_ld: row strides (elements) of mod / kmod, so that column slices of the style projection
+ * (gigagan_pytorch.py:1196 `conv_mods = ...split(...)`) are read in place. */
 int gg_adaconv_weights_fwd(const float* bank, const float* mod, const float* kmod, void* w, float* attn, float* dinv,
-                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int dtype, gg_stream_t stream);
-/* gattn_ws: workspace of B*n + B*O floats */
+                           int B, int n, int O, int I, int KK, int demod, float eps, int Opad, int64_t mod_ld,
+                           int64_t kmod_ld, int dtype, gg_stream_t stream);
+/* gattn_ws: workspace of B*n + B*O floats; dmod [B][I] and dkmod [B][n] are dense outputs */
 int gg_adaconv_weights_bwd(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gw,
                            float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O, int I, int KK,
-                           int demod, float eps, int Opad, gg_stream_t stream);
+                           int demod, float eps, int Opad, int64_t mod_ld, gg_stream_t stream);
+
+/* ---- AdaptiveConv2DMod in "shared bank" form for the low-resolution layers (4x4, 8x8), same function as
+ * gigagan_pytorch.py:378-409:   y_b = dinv_b (.) sum_n attn_bn conv(x_b * (mod_b + 1), W_n)
+ * (the convolution is linear in the filter, so modulation moves to the input and demodulation to the output): dense
+ * convolutions over the SHARED bank whose 128-row tiles span images, instead of B private 512x512x9 filters.
+ *   prep:        attn = softmax(kmod), dinv[b][o] = rsqrt(max(sum_{i,kk} ((mod+1) sum_n attn W_n)^2, eps)), xs = x*(mod+1)
+ *   combine_fwd: y[b,p,o] = dinv[b,o] * sum_n attn[b,n] * ycat[b,p,n*O+o]   (ycat = conv(xs, [W_0;..;W_{n-1}]))
+ *   combine_bwd: gyn[n][b,p,o] = gy*dinv*attn_n;  gdinv[b,o] = sum_p gy * sum_n attn_n ycat_n;
+ *                gattn_ws[b*n+j] = sum_{p,o} gy*dinv*ycat_j   (gattn_ws: B*n floats, overwritten)
+ *   bwd_stats:   the demodulation chain's gradients: dbank = dw_add (kernel-layout [n][O][KK][I] fp32 weight gradients of
+ *                the n convolutions, transposed to the bank's layout) + chain term; dmod [B][I] (overwritten);
+ *                dkmod [B][n] = softmax backward of (gattn_ws + chain term); gattn_ws must hold combine_bwd's result and
+ *                B*O extra floats
+ *   bwd_x:       gx = gxs * (mod+1);  dmod[b,i] += sum_p gxs * x                                    */
+int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const void* x, void* xs, float* attn, float* dinv,
+                  int B, int n, int O, int I, int KK, int HW, int demod, float eps, int64_t mod_ld, int64_t kmod_ld,
+                  int dtype, gg_stream_t stream);
+int gg_sbank_combine_fwd(const void* ycat, const float* attn, const float* dinv, void* y, int B, int HW, int n, int O,
+                         int dtype, gg_stream_t stream);
+int gg_sbank_combine_bwd(const void* gy, const void* ycat, const float* attn, const float* dinv, void* gyn, float* gdinv,
+                         float* gattn_ws, int B, int HW, int n, int O, int dtype, gg_stream_t stream);
+int gg_sbank_bwd_stats(const float* bank, const float* mod, const float* attn, const float* dinv, const float* gdinv,
+                       const float* dw_add, float* dbank, float* dmod, float* dkmod, float* gattn_ws, int B, int n, int O,
+                       int I, int KK, float eps, int64_t mod_ld, gg_stream_t stream);
+int gg_sbank_bwd_x(const void* gxs, const void* x, const float* mod, void* gx, float* dmod, int B, int HW, int I,
+                   int64_t mod_ld, int dtype, gg_stream_t stream);
 
 /* ---- fused attention (gigagan_pytorch.py:562-592 with null key/value and L2-distance logits; attend.py:64-110)
  * q,k,v,o: [B, n, heads, d] rows with the given row strides (elements); null_kv [2][heads][d] fp32 or NULL.
@@ -159,10 +191,12 @@ int gg_rmsnorm_bwd(const void* x, const float* gamma, const float* inv, const vo
                    float s, int dtype, gg_stream_t stream);
 
 /* Backward of the conv epilogue "bias + LeakyReLU(0.2)" (nn.Conv2d followed by leaky_relu, gigagan_pytorch.py:1608-1620,
- * :1454-1470): out = gy * lrelu'(y) and dbias[c] = sum over rows of out (fp32, overwritten) in one pass.
+ * :1454-1470): out = gy * lrelu'(y) and dbias[c] = sum over rows of out (fp32; overwritten, or added to when
+ * accumulate != 0: dbias is then the bias's slice of the flat gradient buffer) in one pass.
  * Returns 1 (nothing done) when C / (16-byte vector) is not a power of two <= 256: the caller then composes
  * gg_pw_unary(level 1) + gg_red_dot_sc. */
-int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int dtype, gg_stream_t stream);
+int gg_lrelu_bwd_bias(const void* y, const void* gy, void* out, float* dbias, int64_t R, int C, int accumulate, int dtype,
+                      gg_stream_t stream);
 
 /* Accumulate a kernel-layout fp32 weight gradient dw[O][KK][Ipad] (output of gg_conv2d_wgrad) into the master-layout
  * gradient buffer dst[O][I][KK] (+=): the .grad accumulation of nn.Conv2d weights (torch autograd AccumulateGrad under
@@ -176,6 +210,13 @@ int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, g
  * one block re-lays the (32 output channels) x (TI input channels) x KK tile through shared memory. */
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream);
+
+/* ---- random patch selection of the auxiliary reconstruction decoder (gigagan_pytorch.py:1300-1312: rearrange into
+ * patch_dim^2 patches, keep the nsel randomly chosen ones per image).  src [B][pd*hh][pd*ww][C] -> dst [B*nsel][hh][ww][C],
+ * row b*nsel+s = patch sel[b*nsel+s] (= py*pd+px) of image b.  transposed != 0: the adjoint (dst [B][pd*hh][pd*ww][C] fully
+ * written: selected patches get the rows of src [B*nsel][hh][ww][C], the rest zeros). */
+int gg_patch_select(const void* src, void* dst, const int* sel, int B, int nsel, int pd, int hh, int ww, int C,
+                    int transposed, int dtype, gg_stream_t stream);
 
 /* ---- GAN hinge objective over all logit tensors of a pass in ONE launch (replaces discriminator_hinge_loss /
  * generator_hinge_loss gigagan_pytorch.py:159-163 and their weighted sums :2327-2347, :2538-2551).

@@ -68,13 +68,21 @@ def table(fn, title):
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         fn()
         torch.cuda.synchronize()
-    rows = [(k.self_device_time_total / 1e3, k.count, k.key[:100]) for k in prof.key_averages() if k.self_device_time_total > 0]
+    from torch.autograd import DeviceType
+    evs = [k for k in prof.key_averages() if k.self_device_time_total > 0]
+    rows = [(k.self_device_time_total / 1e3, k.count, k.key[:100]) for k in evs if k.device_type == DeviceType.CUDA]
+    ops_ = [(k.self_device_time_total / 1e3, k.count, k.key[:100]) for k in evs if k.device_type != DeviceType.CUDA]
     tot, n = sum(r[0] for r in rows), sum(r[1] for r in rows)
-    print(f"===== {title}: {tot:.2f} ms kernel time in {n} launches (ms, count, name)")
-    for r in sorted(rows, reverse=True)[:48]:
+    print(f"===== {title}: {tot:.2f} ms kernel time in {n} launches (ms, count, kernel)")
+    for r in sorted(rows, reverse=True)[:70]:
         print(f"{r[0]:9.3f} {r[1]:6d}  {r[2]}")
     small = [r for r in rows if r[0] / r[1] < 0.02]
-    print(f"      launches averaging < 20 us: {sum(r[1] for r in small)} launches, {sum(r[0] for r in small):.2f} ms")
+    print(f"      kernels averaging < 20 us: {sum(r[1] for r in small)} launches, {sum(r[0] for r in small):.2f} ms")
+    at = [r for r in rows if "at::" in r[2] or r[2].startswith("Mem")]
+    print(f"      ATen / memset / memcpy nodes: {sum(r[1] for r in at)} launches, {sum(r[0] for r in at):.2f} ms")
+    print(f"  --- by launching operator (device ms attributed, calls)")
+    for r in sorted(ops_, key=lambda r: -r[1])[:40]:
+        print(f"{r[0]:9.3f} {r[1]:6d}  {r[2]}")
 
 
 table(lambda: gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=False), "D step (plain)")
@@ -96,6 +104,6 @@ for rec in prof.records:
     b[1] += e0.elapsed_time(e1)
     b[2] += flops
 print("===== convolution fprop/dgrad launches of a plain step by shape (count, ms, TFLOP/s, shape)")
-for k, (n, ms, fl) in sorted(by.items(), key=lambda kv: -kv[1][1])[:40]:
+for k, (n, ms, fl) in sorted(by.items(), key=lambda kv: -kv[1][1]):
     print(f"{n:4d} {ms:8.3f} {fl / ms / 1e9 if ms else 0:8.0f}  {k}")
 print(f"total {sum(v[1] for v in by.values()):.2f} ms, {sum(v[2] for v in by.values()) / 1e12:.2f} TFLOP")
