@@ -26,7 +26,8 @@ struct TcP {
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+#define CONV_THREADS 320          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                      const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                      const __grid_constant__ CUtensorMap tmB, const TcP p, const float* __restrict__ bias,
@@ -45,7 +46,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -130,10 +131,15 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       if (++acc == nacc) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5 -> TMEM lane quarter warp % 4)
+    // ===================================================== epilogue (warps 2..9 -> TMEM lane quarter warp % 4; warps 2..5
+    // take the first half of the tile's columns, warps 6..9 the second: two warps per SM sub-partition so that one's
+    // tcgen05.ld latency overlaps the other's conversions / stores; 32 columns per TMEM load)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = q * 32 + lane;
     const int ww = m % p.Wt, hh = (m / p.Wt) % p.Ht, nn = m / (p.Wt * p.Ht);
+    const int cspan = p.Ntile >= 32 ? p.Ntile / 2 : p.Ntile;       // columns per warp group (Ntile 16: group 0 only)
+    const int cbeg = half * cspan, cend = (p.Ntile >= 32 || half == 0) ? cbeg + cspan : cbeg;
     int acc = 0; uint32_t acc_phase = 0;
     const int nacc = p.mdual == 2 ? 1 : 2;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -148,37 +154,43 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_cons
       long pix = p.y_off + (long)n * p.y_sn + (long)(th * p.Ht + hh) * p.y_sh + (long)(tw * p.Wt + ww) * p.y_sw;
       bool live = n < p.N && mt < p.m_tiles;
       uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.Ntile * p.mdual + d * p.Ntile);
-      for (int c0 = 0; c0 < p.Ntile; c0 += 16) {
-        uint32_t r[16];
-        tc_ld16(taddr + c0, r);
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        const bool two = c0 + 16 < cend;                 // warp-uniform: 32 columns, or a 16-column tail
+        uint32_t r[32];
+        if (two) tc_ld32(taddr + c0, r); else tc_ld16(taddr + c0, r);
         if (live) {
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-          if (bias) {
+          for (int h2 = 0; h2 < 2; ++h2) {
+            if (h2 == 1 && !two) break;
+            const int cc = c0 + 16 * h2;
+            float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + co0 + c0 + j);
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[16 * h2 + j]);
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + co0 + cc + j);
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+            }
+            bf16* dst = y + pix + co0 + cc;
+            if (res) {
+              uint4 r0, r1;
+              ld_global_256(res + pix + co0 + cc, r0, r1);
+              const bf16* rb0 = (const bf16*)&r0; const bf16* rb1 = (const bf16*)&r1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(rb0[j]); v[8 + j] += __bfloat162float(rb1[j]); }
+            }
+            uint4 o0, o1;
+            __nv_bfloat162* ob0 = (__nv_bfloat162*)&o0; __nv_bfloat162* ob1 = (__nv_bfloat162*)&o1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ob0[j] = __floats2bfloat162_rn(v[2 * j] * p.gain, v[2 * j + 1] * p.gain);
+              ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j] * p.gain, v[8 + 2 * j + 1] * p.gain);
+            }
+            st_global_256(dst, o0, o1);
           }
-          if (p.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-          }
-          bf16* dst = y + pix + co0 + c0;
-          if (res) {
-            uint4 r0, r1;
-            ld_global_256(res + pix + co0 + c0, r0, r1);
-            const bf16* rb0 = (const bf16*)&r0; const bf16* rb1 = (const bf16*)&r1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { v[j] += __bfloat162float(rb0[j]); v[8 + j] += __bfloat162float(rb1[j]); }
-          }
-          uint4 o0, o1;
-          __nv_bfloat162* ob0 = (__nv_bfloat162*)&o0; __nv_bfloat162* ob1 = (__nv_bfloat162*)&o1;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            ob0[j] = __floats2bfloat162_rn(v[2 * j] * p.gain, v[2 * j + 1] * p.gain);
-            ob1[j] = __floats2bfloat162_rn(v[8 + 2 * j] * p.gain, v[8 + 2 * j + 1] * p.gain);
-          }
-          st_global_256(dst, o0, o1);
         }
       }
      }
@@ -265,11 +277,22 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
   p.tiles_w = OW / Wt; p.tiles_h = OH / Ht; p.tiles_n = (N + Nt - 1) / Nt;
   p.Ntile = Ntile; p.n_tiles_n = Cout / Ntile;
   p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  // under-filled grids (low-resolution layers: few pixel tiles): halve the N tile while that still fits one wave, so
+  // that twice as many SMs share the layer (n256 4x4 512->512 ran 64 tiles on 148 SMs)
+  while (Ntile > 32 && (long)p.m_tiles * (Cout / Ntile) * 2 <= tc_num_sms()) Ntile /= 2;
+  p.Ntile = Ntile; p.n_tiles_n = Cout / Ntile;
   // L2 -> SM operand traffic bounds the 128x256 tile (85 flop/B): when the layer is wide and deep, let two pixel
   // tiles share every weight slab (256x256 effective tile, 128 flop/B), using all 512 TMEM columns
   // (only for long K loops - the epilogue is not overlapped in this mode - and when >= 2 full waves of tile pairs remain)
-  p.mdual = (Ntile == 256 && KH * KW * (Cin / chunk) >= 32 && !per_sample_w &&
-             (p.m_tiles / 2) * p.n_tiles_n >= 2 * tc_num_sms()) ? 2 : 1;
+  // ... or when the pair schedule simply needs fewer waves: a pair tile takes ~1.6x a single tile (measured 1.25x the
+  // throughput), so pairs win whenever waves(pairs) * 1.6 < waves(singles)
+  {
+    const int nsm = tc_num_sms();
+    const long singles = (long)p.m_tiles * p.n_tiles_n, pairs = (long)((p.m_tiles + 1) / 2) * p.n_tiles_n;
+    const long w1 = (singles + nsm - 1) / nsm, w2 = (pairs + nsm - 1) / nsm;
+    const bool ok = Ntile == 256 && KH * KW * (Cin / chunk) >= 32 && !per_sample_w && p.m_tiles >= 2;
+    p.mdual = (ok && (pairs >= 2 * nsm || w2 * 16 < w1 * 10)) ? 2 : 1;
+  }
   p.total_tiles = ((p.m_tiles + p.mdual - 1) / p.mdual) * p.n_tiles_n;
   p.chunk = chunk; p.cchunks = Cin / chunk; p.KH = KH; p.KW = KW; p.pad = pad; p.stride = stride;
   p.per_sample = per_sample_w;
@@ -336,7 +359,7 @@ int ggi_tc_conv_fprop(const void* x, const void* w, const float* bias, const voi
     attr_set = true;
   }
   int grid = p.total_tiles < tc_num_sms() ? p.total_tiles : tc_num_sms();
-  conv_fprop_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p, bias, (const bf16*)res, (bf16*)y);
+  conv_fprop_tc_kernel<<<grid, CONV_THREADS, smem, st>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p, bias, (const bf16*)res, (bf16*)y);
   return gg_check_launch("conv_fprop_tc");
 }
 

@@ -262,11 +262,17 @@ def _conv_dgrad_raw(gy, wk, g, in_shape):
         dx = (torch.empty if g.kh == 2 else torch.zeros)(in_shape, dtype=gy.dtype, device=gy.device)
         with _Timed("dgrad_s2", 2.0 * n * oh * ow * cout * cin * g.kh * g.kw, gy.dtype,
                     f"dgrad n{n} {h}x{w} {cin}<-{cout} k{g.kh} s2"):
-            for ky in range(g.kh):
-                for kx in range(g.kw):
-                    wt = wk[:, ky, kx, :].t().contiguous()                       # (Cin, Cout) = 1x1 kernel layout
-                    call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, cin, 1, 1, 1,
-                         0, 0, 0, 1.0, (ky * w + kx) * cin, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
+            if g.kh == 2:
+                # per filter row ky ONE 1x1 GEMM with 2*Cin output channels (kx, ci): for a fixed input row 2*oy+ky the
+                # pixels 2*ox and 2*ox+1 are adjacent, so each output pixel's result is one contiguous 2*Cin run
+                for ky in range(2):
+                    wt = wk[:, ky].reshape(cout, 2 * cin).t().contiguous()       # ((kx, ci), Cout) = 1x1 kernel layout
+                    call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, 2 * cin, 1, 1, 1,
+                         0, 0, 0, 1.0, ky * w * cin, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
+            else:
+                wt = wk[:, 0, 0, :].t().contiguous()                             # (Cin, Cout) = 1x1 kernel layout
+                call("gg_conv2d_fprop_strided", _p(gy), _p(wt), None, _p(dx), n, oh, ow, cout, oh, ow, cin, 1, 1, 1,
+                     0, 0, 0, 1.0, 0, h * w * cin, 2 * w * cin, 2 * cin, _dt(gy), _st())
         return dx
     dx = torch.empty(in_shape, dtype=gy.dtype, device=gy.device)
     call("gg_conv2d_dgrad", _p(gy), _p(wk), _p(dx), n, h, w, cin, oh, ow, cout, g.kh, g.kw, g.stride, g.pad,
