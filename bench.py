@@ -204,12 +204,13 @@ def ref_worker(args):
             torch.cuda.synchronize()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
-            gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=gp)
-            gan.train_generator_step(batch_size=b, dl_iter=it)
+            dl = gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=gp)
+            gl = gan.train_generator_step(batch_size=b, dl_iter=it)
         if dev != "cpu":
             torch.cuda.synchronize()
-        print(json.dumps({"event": "step", "index": s, "timed": s >= args.warmup, "gp": gp,
-                          "seconds": time.perf_counter() - t0}), flush=True)
+        secs = time.perf_counter() - t0
+        print(json.dumps({"event": "step", "index": s, "timed": s >= args.warmup, "gp": gp, "seconds": secs,
+                          "d_divergence": float(dl.divergence), "g_divergence": float(gl.divergence)}), flush=True)
 
 
 def _oracle_trainer(size):
@@ -290,8 +291,11 @@ def run_ref_steps(args, device, batch, warmup, steps, budget_s, kind="auto"):
     secs = sum(r["seconds"] for r in use)
     desc = (f"{len(use)} {'timed' if timed else 'warm-up'} G+D step(s) of batch {batch} at {size}x{size}, {what}, {prec}, "
             f"{cores} threads, {sum(1 for r in use if r['gp'])} with gradient penalty; wall budget {budget_s:.0f} s")
-    return dict(value=batch * len(use) / secs, cores=cores, used=len(use), kind="reference" if use_ref else "port",
-                sample=desc, ms_per_step=1e3 * secs / len(use))
+    out = dict(value=batch * len(use) / secs, cores=cores, used=len(use), kind="reference" if use_ref else "port",
+               sample=desc, ms_per_step=1e3 * secs / len(use))
+    if "d_divergence" in use[-1]:          # the reference's own losses after the same number of steps (plausibility only:
+        out["losses_last"] = [use[-1]["d_divergence"], use[-1]["g_divergence"]]     # the noise streams are not shared)
+    return out
 
 
 def run_reference(args):
@@ -486,6 +490,7 @@ def run_ours(args):
             r = run_ref_steps(args, f"cuda:{local}", B, 4, 8, budget_s=150.0, kind="reference")
             if r is not None:
                 gpu_ref = {"value": r["value"], "unit": "images/s", "batch": B, "ms_per_step": r.get("ms_per_step"),
+                           "losses_last": r.get("losses_last"),
                            "steps": r["used"], "sample": r["sample"], "speedup_e2e": e2e / r["value"] if not r.get("failed") else None}
         if not args.no_cpu_baseline:
             r = run_ref_steps(args, "cpu", 2, 0, 2, budget_s=100.0)

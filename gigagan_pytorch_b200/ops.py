@@ -12,6 +12,7 @@ Conventions: activations are NHWC tensors (N,H,W,C) in the compute dtype (fp32 o
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 from torch.autograd import Function
@@ -328,11 +329,11 @@ class Conv2dFn(Function):
             else:
                 gy = Unary1Fn.apply(U_LRELU, y, gy)
         pg = g.plain()
-        if ctx.needs_input_grad[0]:
-            gx = ConvDgradFn.apply(gy, weight, pg, tuple(x.shape), ctx.master)
-        if ctx.needs_input_grad[1] and not _skip_param_grads():
+        if ctx.needs_input_grad[1] and not _skip_param_grads():      # first: it forks to the side stream when terminal
             if not (ctx.master and _wgrad_to_sink(x, gy, pg, weight)):
                 gw = ConvWgradFn.apply(x, gy, pg, weight if ctx.master else None)
+        if ctx.needs_input_grad[0]:
+            gx = ConvDgradFn.apply(gy, weight, pg, tuple(x.shape), ctx.master)
         if want_gb and gb is None:
             if bias_sink is not None:
                 gyc = _c(gy)
@@ -357,11 +358,11 @@ class ConvDgradFn(Function):
         gy, weight = ctx.saved_tensors
         g = ctx.geom
         d_gy = d_w = None
-        if ctx.needs_input_grad[0]:
-            d_gy = Conv2dFn.apply(ggx, weight, None, None, g, ctx.master)
         if ctx.needs_input_grad[1] and not _skip_param_grads():
             if not (ctx.master and _wgrad_to_sink(ggx, gy, g, weight)):
                 d_w = ConvWgradFn.apply(ggx, gy, g, weight if ctx.master else None)
+        if ctx.needs_input_grad[0]:
+            d_gy = Conv2dFn.apply(ggx, weight, None, None, g, ctx.master)
         return d_gy, d_w, None, None, None
 
 
@@ -393,6 +394,33 @@ def _lrelu_bwd_bias(y, gy, sink=None):
     return out, (None if sink is not None else gb)
 
 
+# ---- side stream for weight gradients.  dW is off the critical path of a backward pass (only the optimiser needs it),
+# while the data gradient chain is a sequence of persistent one-CTA-per-SM kernels whose tails, under-filled grids and
+# small pointwise launches leave SMs idle: the terminal weight-gradient launches therefore go to a second stream (also
+# inside CUDA-graph captures: fork/join through events) and fill those holes.  The join is queued as an autograd-engine
+# callback, i.e. it runs at the end of the backward pass that forked.
+SIDE_STREAM = {"on": os.environ.get("GG_SIDE_STREAM", "1") != "0", "stream": {}, "pending": [], "armed": False}
+
+
+def _side_stream(device):
+    if not SIDE_STREAM["on"]:
+        return None
+    st = SIDE_STREAM["stream"].get(device)
+    if st is None:
+        st = SIDE_STREAM["stream"][device] = torch.cuda.Stream(device=device)
+    return st
+
+
+def join_side_stream():
+    """the current stream waits for everything forked to the side stream; operands kept alive for it are released"""
+    SIDE_STREAM["armed"] = False
+    pend, SIDE_STREAM["pending"] = SIDE_STREAM["pending"], []
+    if pend:
+        dev = pend[0][0].device
+        torch.cuda.current_stream(dev).wait_stream(SIDE_STREAM["stream"][dev])
+    del pend
+
+
 def _wgrad_to_sink(x, gy, geom, weight):
     """Terminal (no higher-order graph) weight gradient of a parameter whose .grad is a view of an optimiser's flat
     gradient buffer (FlatAdamW marks those with ``_gg_sink``): run the wgrad kernel and accumulate its kernel-layout
@@ -402,9 +430,22 @@ def _wgrad_to_sink(x, gy, geom, weight):
     dst = weight.grad
     if dst is None or dst.dtype != torch.float32 or not dst.is_contiguous():
         return False
-    dw = _conv_wgrad_raw(_c(x), _c(gy), geom)                       # (O, KH, KW, Ipad) fp32
-    O, KH, KW, ipad = dw.shape
-    call("gg_wgrad_sink", _p(dw), _p(dst), O, weight.shape[1], KH * KW, ipad, _st())
+    x, gy = _c(x), _c(gy)
+    side = _side_stream(x.device) if _PROFILER[0] is None else None
+    if side is None:
+        dw = _conv_wgrad_raw(x, gy, geom)                           # (O, KH, KW, Ipad) fp32
+        O, KH, KW, ipad = dw.shape
+        call("gg_wgrad_sink", _p(dw), _p(dst), O, weight.shape[1], KH * KW, ipad, _st())
+        return True
+    side.wait_stream(torch.cuda.current_stream(x.device))           # x, gy (and the zeroed gradient buffer) are ready
+    with torch.cuda.stream(side):
+        dw = _conv_wgrad_raw(x, gy, geom)
+        O, KH, KW, ipad = dw.shape
+        call("gg_wgrad_sink", _p(dw), _p(dst), O, weight.shape[1], KH * KW, ipad, _st())
+    SIDE_STREAM["pending"].append((x, gy, dw))      # alive until the join: their memory must not be reused before it
+    if not SIDE_STREAM["armed"]:
+        SIDE_STREAM["armed"] = True
+        torch.autograd.Variable._execution_engine.queue_callback(join_side_stream)
     return True
 
 

@@ -25,3 +25,17 @@ for name, t in sorted(tot.items(), key=lambda kv: -kv[1]["ms"])[:45]:
     mb = (t["rd"] + t["wr"]) / max(t["n"], 1) / 1e6
     gbs = (t["rd"] + t["wr"]) / max(t["ms"], 1e-9) / 1e6
     print(f"{name:70s} {t['n']:8d} {t['ms']:9.3f} {100 * t['ms'] / allms:6.1f}% {mb:15.2f} {gbs:8.0f}")
+
+# optional second argument: write the per-step / per-class DRAM traffic that bench.py reports as roofline.traffic
+if len(sys.argv) > 2:
+    import json
+    conv = [t for name, t in tot.items() if name.startswith("conv_fprop_tc") or name.startswith("void conv_thin_tc")
+            or name.startswith("conv_thin_tc")]
+    cn = sum(t["n"] for t in conv)
+    out = {"source": "ncu launch list of one plain G+D step (tools/run_ncu.sh, --clock-control none): " + sys.argv[1].split("/")[-1],
+           "launches_per_step": sum(v["n"] for v in tot.values()),
+           "dram_bytes_per_step": sum(v["rd"] + v["wr"] for v in tot.values()),
+           "conv_launches": cn,
+           "conv_dram_bytes_per_launch": (sum(t["rd"] + t["wr"] for t in conv) / cn) if cn else None,
+           "kernel_ms_ncu": allms}
+    json.dump(out, open(sys.argv[2], "w"), indent=1)
