@@ -10,13 +10,14 @@
 // bank row [n][I*KK] is read once and reused for every image; one block per (b, o) re-read the 19 MB bank B times);
 // blocks x >= O: xs = x * (mod + 1) over a slice of the whole batch.  attn = softmax over the n <= 8 kernel logits.
 #define SB_BCH 16
-template <typename T>
-__global__ void sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
+template <typename T, int NK>
+__global__ void __launch_bounds__(512)
+sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
                                   const float* __restrict__ kmod, const T* __restrict__ x, T* __restrict__ xs,
                                   float* __restrict__ attn, float* __restrict__ dinv, int B, int n, int O, int I, int KK,
-                                  int HW, int demod, float eps, long ldm, long ldk, int XB) {
+                                  int HW, int demod, float eps, long ldm, long ldk, int XB, int use_ssm) {
   __shared__ float sa[SB_BCH * 8];
-  __shared__ float red[8][SB_BCH];
+  __shared__ float red[16][SB_BCH];
   if ((int)blockIdx.x >= O) {
     const long per = (long)HW * I, tot = per * B;
     for (long e = (long)(blockIdx.x - O) * blockDim.x + threadIdx.x; e < tot; e += (long)XB * blockDim.x) {
@@ -26,19 +27,20 @@ __global__ void sbank_prep_kernel(const float* __restrict__ bank, const float* _
     }
     return;
   }
+  extern __shared__ float ssm[];                          // [SB_BCH][I]: (mod + 1) of the current image chunk (use_ssm)
   const int o = blockIdx.x, E = I * KK;
   for (int b0 = 0; b0 < B; b0 += SB_BCH) {
     const int nb = min(SB_BCH, B - b0);
     __syncthreads();
+    if (use_ssm)
+      for (int t = threadIdx.x; t < nb * I; t += blockDim.x) ssm[t] = mod[(long)(b0 + t / I) * ldm + (t % I)] + 1.f;
     if ((int)threadIdx.x < nb) {                          // softmax over the kernel logits of image b0 + t
       const int b = b0 + threadIdx.x;
-      if (n == 1) sa[threadIdx.x * 8] = 1.f;
-      else {
-        float m = -INFINITY, ssum = 0.f, ev[8];
-        for (int j = 0; j < n; ++j) m = fmaxf(m, kmod[(long)b * ldk + j]);
-        for (int j = 0; j < n; ++j) { ev[j] = expf(kmod[(long)b * ldk + j] - m); ssum += ev[j]; }
-        for (int j = 0; j < n; ++j) sa[threadIdx.x * 8 + j] = ev[j] / ssum;
-      }
+      float m = -INFINITY, ssum = 0.f;
+      for (int j = 0; j < n; ++j) m = fmaxf(m, n == 1 ? 0.f : kmod[(long)b * ldk + j]);
+      for (int j = 0; j < n; ++j) ssum += n == 1 ? 1.f : expf(kmod[(long)b * ldk + j] - m);
+      for (int j = 0; j < 8; ++j)
+        sa[threadIdx.x * 8 + j] = j < n ? (n == 1 ? 1.f : expf(kmod[(long)b * ldk + j] - m) / ssum) : 0.f;
       if (o == 0) for (int j = 0; j < n; ++j) attn[b * n + j] = sa[threadIdx.x * 8 + j];
     }
     __syncthreads();
@@ -48,14 +50,16 @@ __global__ void sbank_prep_kernel(const float* __restrict__ bank, const float* _
     for (int t = 0; t < SB_BCH; ++t) ss[t] = 0.f;
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       const int i = e / KK;
-      float w[8];
-      for (int j = 0; j < n; ++j) w[j] = bank[((long)j * O + o) * E + e];
+      float w[NK];
+#pragma unroll
+      for (int j = 0; j < NK; ++j) w[j] = j < n ? bank[((long)j * O + o) * E + e] : 0.f;
 #pragma unroll
       for (int t = 0; t < SB_BCH; ++t)
         if (t < nb) {
           float v = 0.f;
-          for (int j = 0; j < n; ++j) v += sa[t * 8 + j] * w[j];
-          const float u = v * (mod[(long)(b0 + t) * ldm + i] + 1.f);
+#pragma unroll
+          for (int j = 0; j < NK; ++j) v += sa[t * 8 + j] * w[j];
+          const float u = v * (use_ssm ? ssm[t * I + i] : mod[(long)(b0 + t) * ldm + i] + 1.f);
           ss[t] += u * u;
         }
     }
@@ -87,21 +91,22 @@ __global__ void sbank_combine_fwd_kernel(const T* __restrict__ ycat, const float
   }
 }
 
-// grid (cdiv(O,256), B), thread = output channel o, loop over the image's HW pixels
+// grid (cdiv(O,64), B), 256 threads = 64 output channels x 4 pixel lanes (lane l takes pixels l, l+4, ...)
 template <typename T>
 __global__ void sbank_combine_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ ycat,
                                          const float* __restrict__ attn, const float* __restrict__ dinv,
                                          T* __restrict__ gyn, float* __restrict__ gdinv, float* __restrict__ gattn, int B,
                                          int HW, int n, int O) {
   __shared__ float red[8][8];
-  const int b = blockIdx.y, o = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sgd[4][64];
+  const int b = blockIdx.y, ol = threadIdx.x & 63, pl = threadIdx.x >> 6, o = blockIdx.x * 64 + ol;
   const bool live = o < O;
   float a[8], ga[8];
-  for (int j = 0; j < n; ++j) { a[j] = attn[b * n + j]; ga[j] = 0.f; }
+  for (int j = 0; j < 8; ++j) { a[j] = j < n ? attn[b * n + j] : 0.f; ga[j] = 0.f; }
   const float d = live ? dinv[(long)b * O + o] : 0.f;
   float gd = 0.f;
   if (live)
-    for (int p = 0; p < HW; ++p) {
+    for (int p = pl; p < HW; p += 4) {
       const long bp = (long)b * HW + p;
       const float g = ldf(gy + bp * O + o);
       float z = 0.f;
@@ -113,12 +118,13 @@ __global__ void sbank_combine_bwd_kernel(const T* __restrict__ gy, const T* __re
       }
       gd += g * z;
     }
-  if (live) gdinv[(long)b * O + o] = gd;
+  sgd[pl][ol] = gd;
   for (int j = 0; j < n; ++j) {
     float t = warp_sum(ga[j]);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][j] = t;
   }
   __syncthreads();
+  if (pl == 0 && live) gdinv[(long)b * O + o] = sgd[0][ol] + sgd[1][ol] + sgd[2][ol] + sgd[3][ol];
   if ((int)threadIdx.x < n) {
     float t = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w][threadIdx.x];
@@ -126,21 +132,25 @@ __global__ void sbank_combine_bwd_kernel(const T* __restrict__ gy, const T* __re
   }
 }
 
-// gx = gxs * (mod + 1);  dmod[b,i] += sum_p gxs[b,p,i] * x[b,p,i].   grid (cdiv(I,256), B), thread = channel i
+// gx = gxs * (mod + 1);  dmod[b,i] += sum_p gxs[b,p,i] * x[b,p,i].   grid (cdiv(I,64), B), 64 channels x 4 pixel lanes
 template <typename T>
 __global__ void sbank_bwd_x_kernel(const T* __restrict__ gxs, const T* __restrict__ x, const float* __restrict__ mod,
                                    T* __restrict__ gx, float* __restrict__ dmod, int HW, int I, long ldm) {
-  const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= I) return;
-  const float s = mod[(long)b * ldm + i] + 1.f;
+  __shared__ float sacc[4][64];
+  const int b = blockIdx.y, il = threadIdx.x & 63, pl = threadIdx.x >> 6, i = blockIdx.x * 64 + il;
+  const bool live = i < I;
+  const float s = live ? mod[(long)b * ldm + i] + 1.f : 0.f;
   float acc = 0.f;
-  for (int p = 0; p < HW; ++p) {
-    const long e = ((long)b * HW + p) * I + i;
-    const float g = ldf(gxs + e);
-    acc += g * ldf(x + e);
-    stf(gx + e, g * s);
-  }
-  dmod[(long)b * I + i] += acc;
+  if (live)
+    for (int p = pl; p < HW; p += 4) {
+      const long e = ((long)b * HW + p) * I + i;
+      const float g = ldf(gxs + e);
+      acc += g * ldf(x + e);
+      stf(gx + e, g * s);
+    }
+  sacc[pl][il] = acc;
+  __syncthreads();
+  if (pl == 0 && live) dmod[(long)b * I + i] += sacc[0][il] + sacc[1][il] + sacc[2][il] + sacc[3][il];
 }
 
 // ------------------------------------------------------------------ aux-decoder patch selection (gigagan_pytorch.py:1300-1312)
@@ -184,11 +194,16 @@ int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const 
                   int dtype, gg_stream_t stream) {
   if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
   if (n > 1 && !kmod) return gg_fail("gg_sbank_prep: kmod missing");
-  int XB = gg_cdiv((long)B * HW * I, 256 * 4);
+  int XB = gg_cdiv((long)B * HW * I, 512 * 4);
   if (XB < 1) XB = 1;
   if (XB > 512) XB = 512;
-  GG_DISPATCH(dtype, (sbank_prep_kernel<T><<<O + XB, 256, 0, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I,
-                                                                   KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB)));
+  size_t smem = sizeof(float) * (size_t)SB_BCH * I;
+  int use_ssm = smem <= 40 * 1024;
+  if (!use_ssm) smem = 0;
+#define SB_GO(NK) sbank_prep_kernel<T, NK><<<O + XB, 512, smem, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I, \
+                                                                     KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB, use_ssm)
+  GG_DISPATCH(dtype, (n <= 1 ? SB_GO(1) : n <= 2 ? SB_GO(2) : n <= 4 ? SB_GO(4) : SB_GO(8)));
+#undef SB_GO
   return gg_check_launch("sbank_prep");
 }
 int gg_sbank_combine_fwd(const void* ycat, const float* attn, const float* dinv, void* y, int B, int HW, int n, int O,
@@ -202,14 +217,14 @@ int gg_sbank_combine_bwd(const void* gy, const void* ycat, const float* attn, co
                          float* gattn_ws, int B, int HW, int n, int O, int dtype, gg_stream_t stream) {
   if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
   cudaMemsetAsync(gattn_ws, 0, sizeof(float) * (size_t)B * n, ST);
-  dim3 grid(gg_cdiv(O, 256), B);
+  dim3 grid(gg_cdiv(O, 64), B);
   GG_DISPATCH(dtype, (sbank_combine_bwd_kernel<T><<<grid, 256, 0, ST>>>((const T*)gy, (const T*)ycat, attn, dinv, (T*)gyn, gdinv,
                                                                         gattn_ws, B, HW, n, O)));
   return gg_check_launch("sbank_combine_bwd");
 }
 int gg_sbank_bwd_x(const void* gxs, const void* x, const float* mod, void* gx, float* dmod, int B, int HW, int I,
                    int64_t mod_ld, int dtype, gg_stream_t stream) {
-  dim3 grid(gg_cdiv(I, 256), B);
+  dim3 grid(gg_cdiv(I, 64), B);
   GG_DISPATCH(dtype, (sbank_bwd_x_kernel<T><<<grid, 256, 0, ST>>>((const T*)gxs, (const T*)x, mod, (T*)gx, dmod, HW, I,
                                                                   (long)mod_ld)));
   return gg_check_launch("sbank_bwd_x");

@@ -128,7 +128,10 @@ class AdaptiveConv2DMod(nn.Module):
             assert not exists(kernel_mod) or kernel_mod.numel() == 0
             kernel_mod = None
         hw = x.shape[1] * x.shape[2]
-        if x.dtype == torch.bfloat16 and hw < 128 and self.eps == 1e-8:
+        # shared-bank form: always for the 4x4 / 8x8 maps (B private filters leave the 128-row MMA tile empty); up to
+        # 16x16 for the demodulated 3x3 layers, where B private 512x512x9 filters cost more HBM traffic (filter write,
+        # two reads, a flipped copy, an fp32 gradient of twice that size) than the n-fold convolution costs tensor time
+        if x.dtype == torch.bfloat16 and self.eps == 1e-8 and (hw < 128 or (self.demod and hw <= 256)):
             fused = _COMPUTE["fused_attention"] if fused is None else fused
             if fused and self.demod and out_pad <= self.dim_out:
                 return ops.shared_bank_conv(x, self.weights, mod, kernel_mod, self.eps)
@@ -238,13 +241,33 @@ class SelfAttention(nn.Module):
         if self.dot_product:
             s = ops.bmm(q4, kt, alpha=self.scale)
             p = ops.softmax(s, mask, s.numel() // Lp, 1) if mask is not None else ops.softmax(s)
-        else:   # -|q-k|^2 * scale  ==  (2 q.k - |k|^2) * scale  up to a per-row constant (softmax-invariant)
-            s = ops.bmm(q4, kt, alpha=2.0 * self.scale)
+        else:
+            # -|q-k|^2 * scale == (2 q.k - |k|^2) * scale up to a per-row constant (softmax-invariant).  The key term is
+            # folded INTO the product: q' = [q, 1, 1, 0..], k' = [k, hi, lo, 0..] with hi + lo = -|k|^2 / 2 split into
+            # two storage-precision numbers (exact to ~2^-16 in bf16), padded keys get hi = -1e30.  The logit matrix
+            # then needs no bias: on the gradient-penalty path that removes a (tokens x keys)-sized column reduction in
+            # the first backward and a zero fill, a broadcast and an accumulation of that size in the second.
             ksq = ops.rowdot(kf, kf)                                        # (n, Lp, heads) fp32
-            bias = ops.axpby(-self.scale, ksq.permute(0, 2, 1).contiguous()).reshape(n * heads, Lp)
+            t = ops.axpby(-0.5, ksq)
             if mask is not None:
-                bias = ops.add_channels(bias, mask, n * heads, 1)
-            p = ops.softmax(s, bias, seq, n * heads)
+                mrow = mask.reshape(Lp, 1).expand(Lp, heads).reshape(1, Lp * heads).contiguous()
+                t = ops.add_channels(t.reshape(n, Lp * heads), mrow, n, 1).reshape(n, Lp, heads)
+            hi = t.to(q.dtype)
+            pad = d % 16 == 0 and q.dtype == torch.bfloat16
+            extra = [hi.unsqueeze(-1)]
+            if q.dtype == torch.bfloat16:
+                extra.append(ops.axpby(1.0, t, -1.0, hi.float()).to(q.dtype).unsqueeze(-1))
+            nx = len(extra)
+            width = 16 if pad else nx
+            if width > nx:
+                extra.append(torch.zeros((n, Lp, heads, width - nx), dtype=q.dtype, device=q.device))
+            ka = torch.cat([kf] + extra, dim=-1)                            # (n, Lp, heads, d + width)
+            qx = [q.view(n, seq, heads, d), torch.ones((n, seq, heads, nx), dtype=q.dtype, device=q.device)]
+            if width > nx:
+                qx.append(torch.zeros((n, seq, heads, width - nx), dtype=q.dtype, device=q.device))
+            qa = torch.cat(qx, dim=-1)
+            s = ops.bmm(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 3, 1), alpha=2.0 * self.scale)
+            p = ops.softmax(s)
         o = ops.bmm(p, vf.permute(0, 2, 1, 3), out_bmhn=True)             # physical (n, seq, heads, d)
         return o.permute(0, 2, 1, 3)
 

@@ -384,7 +384,7 @@ def test_fused_attention_matches_composed_large():
 
 
 @pytest.mark.parametrize("fused", [False, True])
-@pytest.mark.parametrize("nk,hw,ci,co", [(2, 8, 64, 32), (2, 4, 128, 128), (1, 8, 64, 48), (3, 4, 512, 512)])
+@pytest.mark.parametrize("nk,hw,ci,co", [(2, 8, 64, 32), (2, 4, 128, 128), (1, 8, 64, 48), (3, 4, 512, 512), (2, 16, 128, 64)])
 def test_adaptive_conv_shared_bank_identity_matches_per_sample(fused, nk, hw, ci, co):
     """low-resolution AdaptiveConv2DMod: shared-bank dense formulation (bf16, tcgen05) - the any-order composition and the
     single fused autograd node (ops.SharedBankConvFn) - vs the reference algorithm (oracle, fp32), forward and every
