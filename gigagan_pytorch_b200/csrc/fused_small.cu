@@ -16,40 +16,40 @@ __device__ __forceinline__ float gl_load(const void* p, int dt, long i) {
   return dt == GG_BF16 ? __bfloat162float(((const bf16*)p)[i]) : ((const float*)p)[i];
 }
 
-// one block: out[0] = L_0, out[1] = sum_{j>=1} L_j, out[2] = L_0 + w_ms * out[1]
+// one block per logit tensor j: L_j added into out (zeroed by the launcher): out[0] = L_0, out[1] = sum_{j>=1} L_j,
+// out[2] = L_0 + w_ms * out[1]   (a single block walking all tensors took 57 us; 32-bit index arithmetic)
 __global__ void __launch_bounds__(1024) gan_loss_fwd_kernel(GanLossArgs a, float* __restrict__ out) {
   __shared__ float red[2][32];
-  __shared__ float lj[GL_MAX];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = 0; j < a.k; ++j) {
-    float sr = 0.f, sf = 0.f;
-    const long n = a.n[j], row = a.row[j], split = a.split[j];
-    for (long i = threadIdx.x; i < n; i += blockDim.x) {
-      const float v = gl_load(a.x[j], a.dt[j], i);
+  const int j = blockIdx.x;
+  float sr = 0.f, sf = 0.f;
+  const long n = a.n[j];
+  const unsigned row = (unsigned)a.row[j], split = (unsigned)a.split[j];
+  for (long i0 = 0; i0 < n; i0 += 1u << 30) {                       // 32-bit modulo inside 2^30-element windows
+    const unsigned cnt = (unsigned)min((long)(1u << 30), n - i0), off = (unsigned)(i0 % row);
+    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float v = gl_load(a.x[j], a.dt[j], i0 + i);
       if (a.mode == 1) sr += v;
-      else if (i % row < split) sr += fmaxf(1.f + v, 0.f);
+      else if ((off + i) % row < split) sr += fmaxf(1.f + v, 0.f);
       else sf += fmaxf(1.f - v, 0.f);
     }
-    sr = warp_sum(sr); sf = warp_sum(sf);
-    if (lane == 0) { red[0][warp] = sr; red[1][warp] = sf; }
-    __syncthreads();
-    if (warp == 0) {
-      sr = red[0][lane]; sf = red[1][lane];            // blockDim.x == 1024: all 32 slots valid
-      sr = warp_sum(sr); sf = warp_sum(sf);
-      if (lane == 0) {
-        if (a.mode == 1) lj[j] = sr / (float)n;
-        else {
-          const long nr = n / row * split;
-          lj[j] = sr / (float)nr + sf / (float)(n - nr);
-        }
-      }
-    }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    float ms = 0.f;
-    for (int j = 1; j < a.k; ++j) ms += lj[j];
-    out[0] = lj[0]; out[1] = ms; out[2] = lj[0] + a.w_ms * ms;
+  sr = warp_sum(sr); sf = warp_sum(sf);
+  if (lane == 0) { red[0][warp] = sr; red[1][warp] = sf; }
+  __syncthreads();
+  if (warp == 0) {
+    sr = red[0][lane]; sf = red[1][lane];              // blockDim.x == 1024: all 32 slots valid
+    sr = warp_sum(sr); sf = warp_sum(sf);
+    if (lane == 0) {
+      float l;
+      if (a.mode == 1) l = sr / (float)n;
+      else {
+        const long nr = n / row * split;
+        l = sr / (float)nr + sf / (float)(n - nr);
+      }
+      if (j == 0) { atomicAdd(out + 0, l); atomicAdd(out + 2, l); }
+      else { atomicAdd(out + 1, l); atomicAdd(out + 2, a.w_ms * l); }
+    }
   }
 }
 
@@ -86,7 +86,8 @@ static int gl_fill(GanLossArgs& a, const void* const* x, void* const* dx, const 
 int ggi_gan_loss_fwd(const void* const* x, const long* meta, int k, int mode, float w_ms, float* out, cudaStream_t st) {
   GanLossArgs a;
   if (int r = gl_fill(a, x, nullptr, meta, k, mode, w_ms)) return r;
-  gan_loss_fwd_kernel<<<1, 1024, 0, st>>>(a, out);
+  cudaMemsetAsync(out, 0, 3 * sizeof(float), st);
+  gan_loss_fwd_kernel<<<k, 1024, 0, st>>>(a, out);
   return gg_check_launch("gan_loss_fwd");
 }
 

@@ -611,12 +611,66 @@ __global__ void resample_vec_kernel(const T* __restrict__ x, T* __restrict__ y, 
     stv(y + i * V, acc);
   }
 }
+// same, taps held in registers (MT >= Ty, Tx) and the MT loads of one input row issued back to back: the loop above
+// chained table load -> address -> data load for every tap (238 GB/s on the 16-channel 256x256 maps)
+template <typename T, int MT>
+__global__ void resample_vec2_kernel(const T* __restrict__ x, T* __restrict__ y, int N, int H, int W, int C, int OH, int OW,
+                                     const int* __restrict__ iy, const float* __restrict__ wy, int Ty,
+                                     const int* __restrict__ ix, const float* __restrict__ wx, int Tx) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
+  const long n = (long)N * OH * OW * CV;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long t = i / CV;
+    const int ox = (int)(t % OW); t /= OW;
+    const int oy = (int)(t % OH);
+    const int b = (int)(t / OH);
+    int xo[MT]; float xw[MT];
+#pragma unroll
+    for (int q = 0; q < MT; ++q) {
+      const bool on = q < Tx;
+      xw[q] = on ? wx[ox * Tx + q] : 0.f;
+      xo[q] = on ? ix[ox * Tx + q] * C : 0;
+    }
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    const T* img = x + (long)b * H * W * C + cv * V;
+#pragma unroll
+    for (int a = 0; a < MT; ++a) {
+      if (a < Ty) {
+        const float wa = wy[oy * Ty + a];
+        if (wa != 0.f) {
+          const T* row = img + (long)iy[oy * Ty + a] * W * C;
+          float v[MT][V];
+#pragma unroll
+          for (int q = 0; q < MT; ++q) ldv(row + xo[q], v[q]);            // zero-weight taps read pixel 0 (valid memory)
+#pragma unroll
+          for (int q = 0; q < MT; ++q) {
+            const float wq = xw[q] * wa;
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = fmaf(wq, v[q][k], acc[k]);
+          }
+        }
+      }
+    }
+    stv(y + i * V, acc);
+  }
+}
 int ggi_resample2d(const void* x, void* y, int N, int H, int W, int C, int OH, int OW, const int* iy, const float* wy,
                   int Ty, const int* ix, const float* wx, int Tx, int dtype, cudaStream_t st) {
   long n = (long)N * OH * OW * C;
   int V = dtype == GG_F32 ? 4 : 8;
   if (C % V == 0 && al16(x) && al16(y)) {
-    GG_DISPATCH(dtype, (resample_vec_kernel<T><<<gg_blocks(n / V, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+    int blocks = gg_blocks(n / V, 256, 148 * 32);
+    if (Ty <= 4 && Tx <= 4) {
+      GG_DISPATCH(dtype, (resample_vec2_kernel<T, 4><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+    } else if (Ty <= 8 && Tx <= 8) {
+      GG_DISPATCH(dtype, (resample_vec2_kernel<T, 8><<<blocks, 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+    } else {
+      GG_DISPATCH(dtype, (resample_vec_kernel<T><<<gg_blocks(n / V, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
+    }
     return gg_check_launch("resample2d_vec");
   }
   GG_DISPATCH(dtype, (resample_kernel<T><<<gg_blocks(n, 256), 256, 0, st>>>((const T*)x, (T*)y, N, H, W, C, OH, OW, iy, wy, Ty, ix, wx, Tx)));
@@ -691,13 +745,71 @@ __global__ void noise_act_bwd_kernel(const T* __restrict__ y, const T* __restric
     atomicAdd(dwn + c, t);
   }
 }
+// 16-byte vector forms (C % V == 0): thread = one channel vector of one pixel row
+template <typename T>
+__global__ void noise_act_fwd_vec_kernel(const T* __restrict__ x, const float* __restrict__ noise,
+                                         const float* __restrict__ wn, T* __restrict__ y, long R, int C) {
+  constexpr int V = VecN<T>::N;
+  const int CV = C / V;
+  const long n = R * CV;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    const float nz = noise[i / CV];
+    float v[V], o[V];
+    ldv(x + i * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) { float t = v[k] + __ldg(wn + cv * V + k) * nz; o[k] = t > 0.f ? t : 0.2f * t; }
+    stv(y + i * V, o);
+  }
+}
+// nvec = C / V channel vectors (a power of two <= 256): 256 threads = (256 / nvec row lanes) x nvec vectors
+template <typename T>
+__global__ void noise_act_bwd_vec_kernel(const T* __restrict__ y, const T* __restrict__ gy, const float* __restrict__ noise,
+                                         T* __restrict__ dx, float* __restrict__ dwn, long R, int C, int nvec) {
+  constexpr int V = VecN<T>::N;
+  __shared__ float sm[256 * V];
+  const int t = threadIdx.x, cv = t & (nvec - 1), rl = t / nvec, lanes = 256 / nvec;
+  float acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = 0.f;
+  for (long r = (long)blockIdx.x * lanes + rl; r < R; r += (long)gridDim.x * lanes) {
+    float yv[V], gv[V], ov[V];
+    ldv(y + r * C + cv * V, yv);
+    ldv(gy + r * C + cv * V, gv);
+    const float nz = noise[r];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { ov[k] = yv[k] > 0.f ? gv[k] : 0.2f * gv[k]; acc[k] = fmaf(ov[k], nz, acc[k]); }
+    stv(dx + r * C + cv * V, ov);
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) sm[rl * (nvec * V) + cv * V + k] = acc[k];
+  __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    float sres = 0.f;
+    for (int i = 0; i < lanes; ++i) sres += sm[i * C + c];
+    atomicAdd(dwn + c, sres);
+  }
+}
 int ggi_noise_act_fwd(const void* x, const float* noise, const float* wn, void* y, long R, int C, int dtype, cudaStream_t st) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V == 0 && al16(x) && al16(y)) {
+    GG_DISPATCH(dtype, (noise_act_fwd_vec_kernel<T><<<gg_blocks(R * (C / V), 256, 148 * 32), 256, 0, st>>>((const T*)x, noise, wn, (T*)y, R, C)));
+    return gg_check_launch("noise_act_fwd_vec");
+  }
   GG_DISPATCH(dtype, (noise_act_fwd_kernel<T><<<gg_blocks(R * C, 256), 256, 0, st>>>((const T*)x, noise, wn, (T*)y, R, C)));
   return gg_check_launch("noise_act_fwd");
 }
 int ggi_noise_act_bwd(const void* y, const void* gy, const float* noise, void* dx, float* dwn, long R, int C, int dtype,
                      cudaStream_t st) {
   cudaMemsetAsync(dwn, 0, sizeof(float) * C, st);
+  int V = dtype == GG_F32 ? 4 : 8;
+  int nvec = C % V == 0 ? C / V : 0;
+  if (nvec > 0 && nvec <= 256 && (nvec & (nvec - 1)) == 0 && al16(y) && al16(gy) && al16(dx)) {
+    int lanes = 256 / nvec;
+    int blocks = gg_blocks((R + lanes - 1) / lanes * 256, 256, 148 * 8);
+    GG_DISPATCH(dtype, (noise_act_bwd_vec_kernel<T><<<blocks, 256, 0, st>>>((const T*)y, (const T*)gy, noise, (T*)dx, dwn, R, C, nvec)));
+    return gg_check_launch("noise_act_bwd_vec");
+  }
   int splits = 1;
   while (gg_cdiv(C, 32) * splits < 148 * 4 && R / (splits * 2) >= 64) splits *= 2;
   dim3 grid(gg_cdiv(C, 32), splits), block(32, 8);
@@ -831,7 +943,7 @@ __global__ void adaconv_weights_bwd_kernel(const float* __restrict__ bank, const
 // whole o range in registers (one atomic per (block, b, i) instead of one per (b, o, i): the 512-way contention on
 // dmod made the 512x512 layers take 330 us), gattn through per-warp shared-memory slots.  accumulate != 0: dbank +=.
 #define AB_BCH 16
-#define AB_OC 32
+#define AB_OC 8      // one output channel per warp: the per-warp work is a serial chain (all launches took ~110 us at 32)
 template <int KK, int NK>
 __global__ void __launch_bounds__(256)
 adaconv_weights_bwd2_kernel(const float* __restrict__ bank, const float* __restrict__ mod, const float* __restrict__ attn,
@@ -1049,6 +1161,25 @@ __global__ void weight_prep_multi_kernel(const float* __restrict__ master, const
     for (int j = lane; j < ni * KK; j += 32) s[ol * pitch + j] = j < nir * KK ? row[j] : 0.f;
   }
   __syncthreads();
+  if (sizeof(T) == 2 && !((ni | i0 | Ip | no | o0 | O) & 1) && !((fo | bo) & 1)) {
+    // bf16: two neighbouring elements per 4-byte store (the scalar loops below were store-instruction bound at ~1 TB/s)
+    const int nh = ni >> 1, oh = no >> 1;
+    for (int t = threadIdx.x; t < no * KK * nh; t += blockDim.x) {         // fwd[o][kk][i, i+1]
+      int ih = t % nh, r = t / nh;
+      int kk = r % KK, ol = r / KK;
+      const float* sp = s + ol * pitch + (2 * ih) * KK + kk;
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(fwd) + fo + ((long)(o0 + ol) * KK + kk) * Ip + i0 + 2 * ih) =
+          __floats2bfloat162_rn(sp[0], sp[KK]);
+    }
+    for (int t = threadIdx.x; t < ni * KK * oh; t += blockDim.x) {         // bwd[i][KK-1-kk][o, o+1]
+      int o2 = t % oh, r = t / oh;
+      int kk = r % KK, il = r / KK;
+      const float* sp = s + (2 * o2) * pitch + il * KK + kk;
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(bwd) + bo + ((long)(i0 + il) * KK + (KK - 1 - kk)) * O + o0 + 2 * o2) =
+          __floats2bfloat162_rn(sp[0], sp[pitch]);
+    }
+    return;
+  }
   for (int t = threadIdx.x; t < no * KK * ni; t += blockDim.x) {           // fwd[o][kk][i]
     int il = t % ni, r = t / ni;
     int kk = r % KK, ol = r / KK;
@@ -1183,23 +1314,34 @@ __global__ void rmsnorm_bwd_kernel(const T* __restrict__ x, const float* __restr
   for (int k = 0; k < 4; ++k)
 #pragma unroll
     for (int i = 0; i < V; ++i) acc[k][i] = 0.f;
+  float gam[4][V];                                                 // s * gamma of this lane's columns
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane * V + k * 32 * V;
+#pragma unroll
+    for (int i = 0; i < V; ++i) gam[k][i] = c < C ? s * __ldg(gamma + c + i) : 0.f;
+  }
   for (long r = warp0; r < R; r += nwarps) {
     const T* xr = x + r * C;
     const T* gr = gy + r * C;
     const float iv = inv[r];
     const bool clamped = iv >= 1e12f;                              // ||x|| below eps: y = x / eps, no projection term
+    float vv[4][V], gg[4][V];                                      // the row is read from global memory ONCE
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane * V + k * 32 * V;
+      if (c < C) { ldv<T>(xr + c, vv[k]); ldv<T>(gr + c, gg[k]); }
+    }
     float dot = 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = lane * V + k * 32 * V;
       if (c < C) {
-        float v[V], g[V];
-        ldv<T>(xr + c, v); ldv<T>(gr + c, g);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          float xh = v[i] * iv;
-          dot += g[i] * s * __ldg(gamma + c + i) * xh;
-          acc[k][i] += g[i] * xh * s;
+          float xh = vv[k][i] * iv;
+          dot += gg[k][i] * gam[k][i] * xh;
+          acc[k][i] += gg[k][i] * xh * s;
         }
       }
     }
@@ -1209,10 +1351,9 @@ __global__ void rmsnorm_bwd_kernel(const T* __restrict__ x, const float* __restr
     for (int k = 0; k < 4; ++k) {
       const int c = lane * V + k * 32 * V;
       if (c < C) {
-        float v[V], g[V], o[V];
-        ldv<T>(xr + c, v); ldv<T>(gr + c, g);
+        float o[V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = iv * (g[i] * s * __ldg(gamma + c + i) - v[i] * iv * dot);
+        for (int i = 0; i < V; ++i) o[i] = iv * (gg[k][i] * gam[k][i] - vv[k][i] * iv * dot);
         stv<T>(or_ + c, o);
       }
     }
