@@ -5,25 +5,25 @@
 
 #define ST ((cudaStream_t)stream)
 
-// ------------------------------------------------------------------ shared-bank AdaptiveConv2DMod (4x4 / 8x8 layers)
-// prep.  grid (O * SB_ES + XB), 512 threads.  Blocks x < O*SB_ES: one SB_ES-th of the demodulation sum of output
-// channel o for ALL images (the bank row [n][I*KK] is read once and reused for every image), added atomically to dinv
-// (zeroed by the launcher; sbank_finish_kernel then applies rsqrt(max(., eps))): a block is a serial chain over its
-// elements x images, so the reduction is spread over SB_ES blocks.  Blocks beyond: xs = x * (mod + 1) over a slice of
-// the whole batch.  attn = softmax over the n <= 8 kernel logits.
+// ------------------------------------------------------------------ shared-bank AdaptiveConv2DMod (4x4 ... 16x16 layers)
+// prep.  grid (cdiv(O, SB_OB) + XB), 512 threads.  The first blocks compute the demodulation statistics of SB_OB output
+// channels for ALL images: (mod + 1) of an image chunk is staged in shared memory ONCE per block (that 32 KB fill is the
+// fixed cost of a block: with one block per channel, or per (image, channel), the kernel took ~105 us whatever its
+// size), every bank row [n][I*KK] is read once and reused for all images.  The remaining blocks write xs = x * (mod + 1)
+// over a slice of the whole batch.  attn = softmax over the n <= 8 kernel logits.
 #define SB_BCH 16
-#define SB_ES 4
+#define SB_OB 4
 template <typename T, int NK>
 __global__ void __launch_bounds__(512)
-sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
-                                  const float* __restrict__ kmod, const T* __restrict__ x, T* __restrict__ xs,
-                                  float* __restrict__ attn, float* __restrict__ dinv, int B, int n, int O, int I, int KK,
-                                  int HW, int demod, float eps, long ldm, long ldk, int XB, int use_ssm) {
+sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod, const float* __restrict__ kmod,
+                  const T* __restrict__ x, T* __restrict__ xs, float* __restrict__ attn, float* __restrict__ dinv, int B,
+                  int n, int O, int I, int KK, int HW, int demod, float eps, long ldm, long ldk, int XB, int use_ssm) {
   __shared__ float sa[SB_BCH * 8];
   __shared__ float red[16][SB_BCH];
-  if ((int)blockIdx.x >= O * SB_ES) {
+  const int OBL = (O + SB_OB - 1) / SB_OB;
+  if ((int)blockIdx.x >= OBL) {
     const long per = (long)HW * I, tot = per * B;
-    for (long e = (long)(blockIdx.x - O * SB_ES) * blockDim.x + threadIdx.x; e < tot; e += (long)XB * blockDim.x) {
+    for (long e = (long)(blockIdx.x - OBL) * blockDim.x + threadIdx.x; e < tot; e += (long)XB * blockDim.x) {
       int i = (int)(e % I);
       int b = (int)(e / per);
       stf(xs + e, ldf(x + e) * (mod[(long)b * ldm + i] + 1.f));
@@ -31,8 +31,7 @@ sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
     return;
   }
   extern __shared__ float ssm[];                          // [SB_BCH][I]: (mod + 1) of the current image chunk (use_ssm)
-  const int o = blockIdx.x / SB_ES, es = blockIdx.x % SB_ES, E = I * KK;
-  const int ech = (E + SB_ES - 1) / SB_ES, e_lo = es * ech, e_hi = min(E, e_lo + ech);
+  const int E = I * KK;
   for (int b0 = 0; b0 < B; b0 += SB_BCH) {
     const int nb = min(SB_BCH, B - b0);
     __syncthreads();
@@ -48,41 +47,42 @@ sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
       if (blockIdx.x == 0) for (int j = 0; j < n; ++j) attn[b * n + j] = sa[threadIdx.x * 8 + j];
     }
     __syncthreads();
-    if (!demod) continue;                                  // dinv is set to 1 by sbank_finish_kernel
-    float ss[SB_BCH];
+    for (int oo = 0; oo < SB_OB; ++oo) {
+      const int o = blockIdx.x * SB_OB + oo;
+      if (o >= O) break;
+      if (!demod) { if ((int)threadIdx.x < nb) dinv[(long)(b0 + threadIdx.x) * O + o] = 1.f; continue; }
+      float ss[SB_BCH];
 #pragma unroll
-    for (int t = 0; t < SB_BCH; ++t) ss[t] = 0.f;
-    for (int e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
-      const int i = e / KK;
-      float w[NK];
+      for (int t = 0; t < SB_BCH; ++t) ss[t] = 0.f;
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const int i = e / KK;
+        float w[NK];
 #pragma unroll
-      for (int j = 0; j < NK; ++j) w[j] = j < n ? bank[((long)j * O + o) * E + e] : 0.f;
+        for (int j = 0; j < NK; ++j) w[j] = j < n ? bank[((long)j * O + o) * E + e] : 0.f;
 #pragma unroll
-      for (int t = 0; t < SB_BCH; ++t)
-        if (t < nb) {
-          float v = 0.f;
+        for (int t = 0; t < SB_BCH; ++t)
+          if (t < nb) {
+            float v = 0.f;
 #pragma unroll
-          for (int j = 0; j < NK; ++j) v += sa[t * 8 + j] * w[j];
-          const float u = v * (use_ssm ? ssm[t * I + i] : mod[(long)(b0 + t) * ldm + i] + 1.f);
-          ss[t] += u * u;
-        }
-    }
+            for (int j = 0; j < NK; ++j) v += sa[t * 8 + j] * w[j];
+            const float u = v * (use_ssm ? ssm[t * I + i] : mod[(long)(b0 + t) * ldm + i] + 1.f);
+            ss[t] += u * u;
+          }
+      }
 #pragma unroll
-    for (int t = 0; t < SB_BCH; ++t) {
-      const float r = warp_sum(ss[t]);
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = r;
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < nb) {
-      float tsum = 0.f;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += red[w][threadIdx.x];
-      atomicAdd(dinv + (long)(b0 + threadIdx.x) * O + o, tsum);
+      for (int t = 0; t < SB_BCH; ++t) {
+        const float r = warp_sum(ss[t]);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = r;
+      }
+      __syncthreads();
+      if ((int)threadIdx.x < nb) {
+        float tsum = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tsum += red[w][threadIdx.x];
+        dinv[(long)(b0 + threadIdx.x) * O + o] = rsqrtf(fmaxf(tsum, eps));
+      }
+      __syncthreads();
     }
   }
-}
-__global__ void sbank_finish_kernel(float* __restrict__ dinv, int n, int demod, float eps) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dinv[i] = demod ? rsqrtf(fmaxf(dinv[i], eps)) : 1.f;
 }
 
 // y[b,p,o] = dinv[b,o] * sum_j attn[b,j] * ycat[b,p,j*O+o]
@@ -202,18 +202,17 @@ int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const 
                   int dtype, gg_stream_t stream) {
   if (n > 8) return gg_fail("num_conv_kernels > 8 unsupported");
   if (n > 1 && !kmod) return gg_fail("gg_sbank_prep: kmod missing");
-  cudaMemsetAsync(dinv, 0, sizeof(float) * (size_t)B * O, ST);
   int XB = gg_cdiv((long)B * HW * I, 512 * 4);
   if (XB < 1) XB = 1;
   if (XB > 512) XB = 512;
   size_t smem = sizeof(float) * (size_t)SB_BCH * I;
   int use_ssm = smem <= 40 * 1024;
   if (!use_ssm) smem = 0;
-#define SB_GO(NK) sbank_prep_kernel<T, NK><<<O * SB_ES + XB, 512, smem, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I, \
-                                                                     KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB, use_ssm)
+  const int OBL = gg_cdiv(O, SB_OB);
+#define SB_GO(NK) sbank_prep_kernel<T, NK><<<OBL + XB, 512, smem, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I, \
+                                                                       KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB, use_ssm)
   GG_DISPATCH(dtype, (n <= 1 ? SB_GO(1) : n <= 2 ? SB_GO(2) : n <= 4 ? SB_GO(4) : SB_GO(8)));
 #undef SB_GO
-  sbank_finish_kernel<<<gg_cdiv((long)B * O, 256), 256, 0, ST>>>(dinv, B * O, demod, eps);
   return gg_check_launch("sbank_prep");
 }
 int gg_sbank_combine_fwd(const void* ycat, const float* attn, const float* dinv, void* y, int B, int HW, int n, int O,

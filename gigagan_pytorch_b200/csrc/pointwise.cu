@@ -978,8 +978,11 @@ adaconv_weights_bwd2_kernel(const float* __restrict__ bank, const float* __restr
       }
 #pragma unroll
     for (int t = 0; t < AB_BCH; ++t) {
-      if (t >= nb) break;
+      if (t < nb) {
       const int b = b0 + t;
+      float gq[KK];                          // the KK gradient loads of this (image, channel) go out back to back
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) gq[kk] = (live && gw) ? __ldg(gw + (((long)b * Opad + o) * KK + kk) * I + i) : 0.f;
       const float d = dinv[(long)b * O + o], s = sv[t];
       const float qv = demod ? q[(long)b * O + o] : 0.f;
       const bool clamp = !(demod && d * d * eps < 0.999999f);
@@ -991,7 +994,7 @@ adaconv_weights_bwd2_kernel(const float* __restrict__ bank, const float* __restr
         float v = 0.f;
 #pragma unroll
         for (int j = 0; j < NK; ++j) v += sa[t][j] * wb[j][kk];
-        const float g = (live && gw) ? gw[(((long)b * Opad + o) * KK + kk) * I + i] : 0.f;
+        const float g = gq[kk];
         float gu = d * g;
         if (!clamp) gu -= d * d * d * (v * s) * qv;
         const float gv = gu * s;
@@ -1006,6 +1009,7 @@ adaconv_weights_bwd2_kernel(const float* __restrict__ bank, const float* __restr
           const float r = warp_sum(gvw[j]);
           if (lane == 0) sm_ga[warp][t][j] += r;
         }
+      }
       }
     }
     if (live) {

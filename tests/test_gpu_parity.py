@@ -600,7 +600,8 @@ def test_trainer_steps_run_and_cuda_graph_replay_matches_eager(upsampler, amp):
             torch.manual_seed(100 + step)          # device noise (also inside graph replays) and host patch selection
             d = gan.train_discriminator_step(dl_iter=it, apply_gradient_penalty=gp)
             gd = gan.D_opt.grad.clone()
-            gl = gan.train_generator_step(batch_size=4, dl_iter=it)
+            torch.manual_seed(200 + step)          # the generator step's noise must not depend on how many Philox offsets
+            gl = gan.train_generator_step(batch_size=4, dl_iter=it)   # the (eager / captured / replayed) D step consumed
             gg = gan.G_opt.grad.clone()
             torch.cuda.synchronize()
             res.append((torch.stack([d.divergence.float(), d.multiscale_divergence.float(), d.gradient_penalty.float(),
