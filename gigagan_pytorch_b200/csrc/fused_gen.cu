@@ -196,6 +196,85 @@ __global__ void patch_select_kernel(const T* __restrict__ src, T* __restrict__ d
   }
 }
 
+// ------------------------------------------------------------------ one-output-channel heads (to_logits 1x1 convs / Linear -> 1)
+// y[r] = sum_c x[r,c] * w[c] + bias.  The batched-GEMM route pads the single output to a 16-wide tile; its weight
+// gradient is then a (C x R) x (R x 16) product whose whole reduction over R = 10^4..10^5 rows lands on ONE CTA.
+// Here: one warp per row forwards; the backward writes dx[r,c] = gy[r] * w[c] and accumulates dw[c] = sum_r gy[r] x[r,c]
+// and dbias = sum_r gy[r] in the same pass over x (column sums in registers, one atomic per block and column).
+template <typename T>
+__global__ void row_linear_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                      float* __restrict__ y, long R, int C) {
+  constexpr int V = 16 / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const float b = bias ? bias[0] : 0.f;
+  for (long r = warp0; r < R; r += nwarps) {
+    float acc = 0.f;
+    for (int c = lane * V; c < C; c += 32 * V) {
+      if (sizeof(T) == 2) {
+        uint4 u = *reinterpret_cast<const uint4*>(x + r * C + c);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); acc += f.x * w[c + 2 * k] + f.y * w[c + 2 * k + 1]; }
+      } else {
+        float4 f = *reinterpret_cast<const float4*>(x + r * C + c);
+        acc += f.x * w[c] + f.y * w[c + 1] + f.z * w[c + 2] + f.w * w[c + 3];
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) y[r] = acc + b;
+  }
+}
+template <typename T>
+__global__ void row_linear_bwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const float* __restrict__ gy,
+                                      T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dbias, long R, int C,
+                                      int nvec) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float sm[256 * V];
+  const int t = threadIdx.x, cv = t & (nvec - 1), rl = t / nvec, lanes = 256 / nvec;
+  float acc[V], wv[V], gsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < V; ++k) { acc[k] = 0.f; wv[k] = w[cv * V + k]; }
+  for (long r = (long)blockIdx.x * lanes + rl; r < R; r += (long)gridDim.x * lanes) {
+    const float g = gy[r];
+    float xv[V], o[V];
+    if (sizeof(T) == 2) {
+      uint4 u = *reinterpret_cast<const uint4*>(x + r * C + cv * V);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); xv[2 * k] = f.x; xv[2 * k + 1] = f.y; }
+    } else {
+      float4 f = *reinterpret_cast<const float4*>(x + r * C + cv * V);
+      xv[0] = f.x; xv[1] = f.y; xv[2] = f.z; xv[3] = f.w;
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) { acc[k] = fmaf(g, xv[k], acc[k]); o[k] = g * wv[k]; }
+    if (dx) {
+      if (sizeof(T) == 2) {
+        uint4 u;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+        *reinterpret_cast<uint4*>(dx + r * C + cv * V) = u;
+      } else {
+        *reinterpret_cast<float4*>(dx + r * C + cv * V) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    if (cv == 0) gsum += g;
+  }
+  if (dw) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) sm[rl * (nvec * V) + cv * V + k] = acc[k];
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+      float sres = 0.f;
+      for (int i = 0; i < lanes; ++i) sres += sm[i * C + c];
+      atomicAdd(dw + c, sres);
+    }
+  }
+  if (dbias && cv == 0) atomicAdd(dbias, gsum);
+}
+
 extern "C" {
 int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const void* x, void* xs, float* attn, float* dinv,
                   int B, int n, int O, int I, int KK, int HW, int demod, float eps, int64_t mod_ld, int64_t kmod_ld,
@@ -244,5 +323,23 @@ int gg_patch_select(const void* src, void* dst, const int* sel, int B, int nsel,
   GG_DISPATCH(dtype, (patch_select_kernel<T><<<gg_blocks(tot, 256), 256, 0, ST>>>((const T*)src, (T*)dst, sel, B, nsel, pd, hh, ww,
                                                                                   C, transposed, tot)));
   return gg_check_launch("patch_select");
+}
+int gg_row_linear_fwd(const void* x, const float* w, const float* bias, float* y, int64_t R, int C, int dtype,
+                      gg_stream_t stream) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  if (C % V || (((uintptr_t)x) & 15)) return gg_fail("gg_row_linear_fwd: C %% %d != 0 or unaligned", V);
+  GG_DISPATCH(dtype, (row_linear_fwd_kernel<T><<<gg_blocks(R * 32, 256, 148 * 16), 256, 0, ST>>>((const T*)x, w, bias, y, R, C)));
+  return gg_check_launch("row_linear_fwd");
+}
+int gg_row_linear_bwd(const void* x, const float* w, const float* gy, void* dx, float* dw, float* dbias, int64_t R, int C,
+                      int dtype, gg_stream_t stream) {
+  int V = dtype == GG_F32 ? 4 : 8;
+  int nvec = C % V == 0 ? C / V : 0;
+  if (nvec <= 0 || nvec > 256 || (nvec & (nvec - 1)) || (((uintptr_t)x | (uintptr_t)dx) & 15))
+    return gg_fail("gg_row_linear_bwd: C / %d must be a power of two <= 256, 16-byte aligned tensors", V);
+  int lanes = 256 / nvec;
+  int blocks = gg_blocks((R + lanes - 1) / lanes * 256, 256, 148 * 8);
+  GG_DISPATCH(dtype, (row_linear_bwd_kernel<T><<<blocks, 256, 0, ST>>>((const T*)x, w, gy, (T*)dx, dw, dbias, R, C, nvec)));
+  return gg_check_launch("row_linear_bwd");
 }
 }

@@ -586,7 +586,9 @@ class Predictor(nn.Module):
             x = ops.axpby(self.residual_scale, x, self.residual_scale, inner)
         x = ops.add(x, residual)
         n, h, w, c = x.shape
-        y = ops.linear_rows(x.reshape(n * h * w, c), self.to_logits.weight.reshape(1, c), self.to_logits.bias)
+        fz = _COMPUTE["fused_attention"] if fused is None else fused
+        y = ops.linear_rows(x.reshape(n * h * w, c), self.to_logits.weight.reshape(1, c), self.to_logits.bias, fused=fz,
+                            w_param=self.to_logits.weight)
         return y.reshape(n, h, w, 1)
 
 
@@ -762,7 +764,8 @@ class Discriminator(nn.Module):
         lw = self.to_logits[2].weight                                                   # (1, c*h*w) in (c h w) order
         c = x.shape[-1]
         lw = lw.view(1, c, 4, 4).permute(0, 2, 3, 1).reshape(1, 16 * c)                  # -> (h w c) like NHWC rows
-        logits = ops.linear_rows(x.reshape(x.shape[0], 16 * c), lw, self.to_logits[2].bias)
+        fz = _COMPUTE["fused_attention"] if fused_attention is None else fused_attention
+        logits = ops.linear_rows(x.reshape(x.shape[0], 16 * c), lw, self.to_logits[2].bias, fused=fz)
         logits = logits.float().reshape(-1, batch)
         return logits, ms_outputs, aux_losses
 

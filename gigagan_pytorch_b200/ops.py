@@ -581,10 +581,61 @@ def bmm(a, b, alpha=1.0, out_bmhn=False):
     return BmmFn.apply(a, b, None, alpha, out_bmhn)
 
 
-def linear_rows(x2d, weight, bias=None):
-    """(R,K) activations (compute dtype) @ fp32 master weight (O,K)^T + bias -> (R,O).  In bf16 the output width is
-    padded to 16 so the product runs on the tcgen05 batched GEMM (used for 1-channel logit heads)."""
+class RowLinearFn(Function):
+    """y[r] = x[r,:] . w + b for ONE output channel (the logit heads), fp32 output (R,1).  First-order only.  The weight /
+    bias gradients are added straight into the flat gradient buffer when ``w_param`` / ``bias`` are sink parameters."""
+
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, w_param):
+        x = _c(x2d)
+        R, K = x.shape
+        w = _c(weight.detach().reshape(-1).float())
+        b = None if bias is None else _c(bias.detach().reshape(-1).float())
+        y = torch.empty((R, 1), dtype=torch.float32, device=x.device)
+        call("gg_row_linear_fwd", _p(x), _p(w), _p(b), _p(y), R, K, _dt(x), _st())
+        ctx.save_for_backward(x, w)
+        ctx.wshape, ctx.w_param = tuple(weight.shape), w_param
+        ctx.bias_ref = bias if (bias is not None and getattr(bias, "_gg_sink1", False)) else None
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        R, K = x.shape
+        gy = _c(gy.float().reshape(-1))
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = db = dw_ret = db_ret = None
+        if ctx.needs_input_grad[1] and not _skip_param_grads():
+            wp = ctx.w_param
+            sink = wp.grad if (wp is not None and getattr(wp, "_gg_sink", False) and wp.grad is not None
+                               and wp.grad.dtype == torch.float32 and wp.grad.is_contiguous() and wp.numel() == K) else None
+            dw = sink if sink is not None else torch.zeros(K, dtype=torch.float32, device=x.device)
+            dw_ret = None if sink is not None else dw.reshape(ctx.wshape)
+        if ctx.has_bias and ctx.needs_input_grad[2] and not _skip_param_grads():
+            sink = _bias_sink(ctx.bias_ref)
+            db = sink if sink is not None else torch.zeros(1, dtype=torch.float32, device=x.device)
+            db_ret = None if sink is not None else db
+        if dx is not None or dw is not None or db is not None:
+            call("gg_row_linear_bwd", _p(x), _p(w), _p(gy), _p(dx), _p(dw), _p(db), R, K, _dt(x), _st())
+        return dx, dw_ret, db_ret, None
+
+
+def _row_linear_ok(x2d, weight):
+    K = x2d.shape[-1]
+    v = 8 if x2d.dtype == torch.bfloat16 else 4
+    nv = K // v
+    return weight.shape[0] == 1 and K % v == 0 and 0 < nv <= 256 and (nv & (nv - 1)) == 0
+
+
+def linear_rows(x2d, weight, bias=None, fused=False, w_param=None):
+    """(R,K) activations (compute dtype) @ fp32 master weight (O,K)^T + bias -> (R,O).  ``fused`` (first-order passes,
+    one output channel): a bandwidth kernel pair instead of a padded batched GEMM.  Otherwise in bf16 the output width is
+    padded to 16 so the product runs on the tcgen05 batched GEMM."""
     O, K = weight.shape
+    if fused and _row_linear_ok(x2d, weight):
+        return RowLinearFn.apply(x2d, weight, bias, w_param)
     if x2d.dtype == torch.float32:
         return linear(x2d, weight, bias)
     opad = (O + 15) // 16 * 16

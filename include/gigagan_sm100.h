@@ -211,6 +211,15 @@ int gg_wgrad_sink(const float* dw, float* dst, int O, int I, int KK, int Ipad, g
 int gg_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                          int dtype, gg_stream_t stream);
 
+/* ---- heads with ONE output channel (Predictor.to_logits 1x1 conv gigagan_pytorch.py:1470/:1497, Discriminator.to_logits
+ * Linear :1658): y[r] = sum_c x[r,c] w[c] + bias[0] (fp32 y), rows = pixels or flattened maps.
+ * bwd: dx[r,c] = gy[r] w[c] (dx NULL: skipped);  dw[c] += sum_r gy[r] x[r,c] and dbias[0] += sum_r gy[r] (fp32, ADDED:
+ * pass zeroed buffers or the parameters' slices of the flat gradient buffer; NULL: skipped). */
+int gg_row_linear_fwd(const void* x, const float* w, const float* bias, float* y, int64_t R, int C, int dtype,
+                      gg_stream_t stream);
+int gg_row_linear_bwd(const void* x, const float* w, const float* gy, void* dx, float* dw, float* dbias, int64_t R, int C,
+                      int dtype, gg_stream_t stream);
+
 /* ---- random patch selection of the auxiliary reconstruction decoder (gigagan_pytorch.py:1300-1312: rearrange into
  * patch_dim^2 patches, keep the nsel randomly chosen ones per image).  src [B][pd*hh][pd*ww][C] -> dst [B*nsel][hh][ww][C],
  * row b*nsel+s = patch sel[b*nsel+s] (= py*pd+px) of image b.  transposed != 0: the adjoint (dst [B][pd*hh][pd*ww][C] fully

@@ -418,6 +418,27 @@ def test_adaptive_conv_shared_bank_identity_matches_per_sample(fused, nk, hw, ci
     assert gm[2][:, ci + max(nk, 1):].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("r,k", [(300, 64), (4096, 256), (1000, 512)])
+def test_row_linear_head_matches_torch(dtype, tol, r, k):
+    """one-output-channel logit heads (ref gigagan_pytorch.py:1470, :1497): the bandwidth kernel pair against torch fp32 on
+    the same (storage-rounded) activations: y, dx, dw, dbias"""
+    from gigagan_pytorch_b200 import ops
+    x = rn(1, r, k).to(dtype).to(dev()).requires_grad_()
+    w = (rn(2, 1, k) * k ** -0.5).to(dev()).requires_grad_()
+    b = rn(3, 1).to(dev()).requires_grad_()
+    y = ops.linear_rows(x, w, b, fused=True)
+    assert y.dtype == torch.float32 and y.shape == (r, 1)
+    xr = x.detach().float().requires_grad_()
+    yr = xr @ w.t() + b
+    assert relmax(y, yr) < tol
+    gy = torch.randn_like(yr)
+    g = torch.autograd.grad(y, (x, w, b), gy)
+    gr = torch.autograd.grad(yr, (xr, w, b), gy)
+    for a_, b_ in zip(g, gr):
+        assert relmax(a_, b_) < tol
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_patch_select_matches_rearrange(dtype):
     """the aux decoder's patch subset (ref gigagan_pytorch.py:1300-1312: 'b c (p1 h) (p2 w) -> b (p1 p2) c h w', per-image
