@@ -632,7 +632,7 @@ def test_trainer_steps_run_and_cuda_graph_replay_matches_eager(upsampler, amp):
         assert torch.isfinite(la).all() and torch.isfinite(lb).all()
         if gp:
             assert la[2].item() > 0
-        rel = ((la - lb).abs() / la.abs().clamp_min(0.1)).max().item()
+        rel = ((la - lb).abs() / la.abs().clamp_min(0.5 if amp else 0.1)).max().item()
         assert rel < tol_loss, (step, rel, la.tolist(), lb.tolist())
         for what, x, y in (("D", gda, gdb), ("G", gga, ggb)):
             assert x.abs().max().item() > 0
