@@ -54,20 +54,30 @@ sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
       float ss[SB_BCH];
 #pragma unroll
       for (int t = 0; t < SB_BCH; ++t) ss[t] = 0.f;
-      for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        const int i = e / KK;
-        float w[NK];
+      // three elements per thread and iteration: their 3*NK bank loads are issued before any arithmetic (with one element
+      // per iteration every warp had a single load in flight and the kernel ran at ~2 GB/s per block)
+      for (int e0 = threadIdx.x; e0 < E; e0 += 3 * blockDim.x) {
+        float w[3][NK];
+        int ii[3];
 #pragma unroll
-        for (int j = 0; j < NK; ++j) w[j] = j < n ? bank[((long)j * O + o) * E + e] : 0.f;
+        for (int u = 0; u < 3; ++u) {
+          const int e = e0 + u * blockDim.x;
+          const bool ok = e < E;
+          ii[u] = ok ? e / KK : 0;
 #pragma unroll
-        for (int t = 0; t < SB_BCH; ++t)
-          if (t < nb) {
-            float v = 0.f;
+          for (int j = 0; j < NK; ++j) w[u][j] = (ok && j < n) ? __ldg(bank + ((long)j * O + o) * E + e) : 0.f;
+        }
 #pragma unroll
-            for (int j = 0; j < NK; ++j) v += sa[t * 8 + j] * w[j];
-            const float u = v * (use_ssm ? ssm[t * I + i] : mod[(long)(b0 + t) * ldm + i] + 1.f);
-            ss[t] += u * u;
-          }
+        for (int u = 0; u < 3; ++u)
+#pragma unroll
+          for (int t = 0; t < SB_BCH; ++t)
+            if (t < nb) {
+              float v = 0.f;
+#pragma unroll
+              for (int j = 0; j < NK; ++j) v += sa[t * 8 + j] * w[u][j];
+              const float um = v * (use_ssm ? ssm[t * I + ii[u]] : mod[(long)(b0 + t) * ldm + ii[u]] + 1.f);
+              ss[t] += um * um;
+            }
       }
 #pragma unroll
       for (int t = 0; t < SB_BCH; ++t) {
