@@ -605,7 +605,9 @@ class GigaGAN(nn.Module):
             fake, rgbs = self._generate(noise, real_n.detach(), text)
         fake = fake.detach().requires_grad_(gp_on)
         rgbs = [t.detach() for t in rgbs]
-        fused = False if gp_on else None      # gradient penalty needs the any-order-differentiable attention
+        # gradient penalty needs the any-order-differentiable forms (attention, shared-bank AdaConv, logit heads);
+        # _force_composed: tests compare the first-order fast paths with them on the same objective
+        fused = False if (gp_on or getattr(self, "_force_composed", False)) else None
         te = None if text is None else D.encode_text(text_encodings=text)
         zero = torch.zeros((), device=real.device)
         w_ms = self.multiscale_divergence_loss_weight

@@ -200,6 +200,42 @@ def test_ka8_discriminator_step_readme256(dtype, merged):
     finish(rep, f"D step README-256 {dtype} merged={merged}", dtype == torch.bfloat16)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 3e-2)])
+def test_plain_step_fast_paths_match_composed(dtype, tol):
+    """the first-order fast paths of a PLAIN discriminator step at README-256 (fused attention + RMSNorm, one-channel logit
+    heads, fused LeakyReLU-backward/bias gradient, weight / bias gradient sinks into the flat buffer, side-stream weight
+    gradients) against the composed any-order forms on the same objective (those are pinned to the reference by the
+    gradient-penalty tests above): loss and the whole flat gradient buffer"""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import ops
+    from gigagan_pytorch_b200.modules import img_cpad
+    fx = fixture()
+    G, D = build_models(dtype)
+    D.train()
+    img = torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(fx["seeds"]["img"])).to(dev())
+    fake = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(fx["seeds"]["fake"])) * 2 - 1).to(dev())
+    gan = g.GigaGAN(generator=G, discriminator=D, amp=(dtype == torch.bfloat16), mixed_precision_type="bf16",
+                    log_steps_every=10 ** 9, create_ema_generator_at_init=False, discr_aux_recon_loss_weight=0.).to(dev())
+    gan._ensure_optimizers()
+    fake_n = ops.to_nhwc(fake, img_cpad(3), dtype)
+    gan._generate = lambda noise, real_n=None, text=None: (fake_n, D.real_images_to_rgbs_nhwc(fake_n))
+    res = []
+    for composed in (False, True):
+        gan._force_composed = composed
+        for p in gan.D_opt.params:                       # composed run: ordinary autograd accumulation, no sinks
+            p._gg_sink, p._gg_sink1 = (p.ndim == 4 and not composed), (p.ndim == 1 and not composed)
+        gan._begin_work(gan._stale_banks())
+        gan.D_opt.zero_grad()
+        total, _ = gan._d_objective(img, None, False, True)
+        total.backward(inputs=gan.D_opt.params)
+        torch.cuda.synchronize()
+        res.append((total.detach().float().clone(), gan.D_opt.grad.clone()))
+    (lf, gf), (lc, gc) = res
+    assert abs(lf.item() - lc.item()) <= tol * abs(lc.item())
+    assert gc.abs().max().item() > 0
+    assert (gf - gc).abs().max().item() <= tol * gc.abs().max().item()
+
+
 # ------------------------------------------------------------------ wide tcgen05 paths against torch directly
 def _conv_ref(x, w, b, stride, pad):
     """fp32 torch reference from the bf16-rounded operands (NHWC x, kernel-layout w)"""

@@ -3,8 +3,10 @@
 N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader > gpurun_out/multi_smi.txt
-timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --tb=short 2>&1 | grep -v "^    " | tail -40 > gpurun_out/tests_multi.log
-tail -6 gpurun_out/tests_multi.log
+if [ "$2" != "notests" ]; then
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --tb=short 2>&1 | grep -v "^    " | tail -40 > gpurun_out/tests_multi.log
+  tail -6 gpurun_out/tests_multi.log
+fi
 run() {  # config steps warmup
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29507 \
       bench.py --gpus $N --config $1 --steps $2 --warmup $3 --no-cpu-baseline --no-gpu-reference \
