@@ -164,7 +164,10 @@ int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_k
                 int mode, int dtype, gg_stream_t stream) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    int r = ggi_tc_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
+    // flag 8: first-generation kernels (8 softmax warps, chunked TMEM reads); flag 16: second generation with 8 warps
+    int r = (g_flags & 8) ? ggi_tc_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST)
+                          : ggi_tc2_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode,
+                                             (g_flags & 16) ? 8 : 16, ST);
     if (r <= 0) return r;
   }
 #endif
@@ -176,7 +179,9 @@ int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_k
                 int mode, int dtype, gg_stream_t stream) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    int r = ggi_tc_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST);
+    int r = (g_flags & 8) ? ggi_tc_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST)
+                          : ggi_tc2_attn_bwd(q, k, v, null_kv, o, go, lse, dq, dk, dv, dnull_kv, delta_ws, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode,
+                                             (g_flags & 16) ? 8 : 16, ST);
     if (r <= 0) return r;
   }
 #endif

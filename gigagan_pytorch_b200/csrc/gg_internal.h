@@ -75,6 +75,13 @@ int ggi_tc_attn_bwd(const void* q, const void* k, const void* v, const float* nu
                     const float* lse2, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
                     int mode, cudaStream_t st);
+int ggi_tc2_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,
+                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
+                     int mode, int nsw, cudaStream_t st);
+int ggi_tc2_attn_bwd(const void* q, const void* k, const void* v, const float* null_kv, const void* o, const void* go,
+                     const float* lse2, void* dq, void* dk, void* dv, float* dnull_kv, float* delta_ws, float* ksq_ws,
+                     int B, int heads, int nq, int nk, int d, long q_rs, long k_rs, long v_rs, long o_rs, float scale,
+                     int mode, int nsw, cudaStream_t st);
 int ggi_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, long R, int C, int dtype,
                           cudaStream_t st);
 int ggi_maxpool2_fwd(const void* x, void* y, int N, int H, int W, int C, int dtype, cudaStream_t st);
