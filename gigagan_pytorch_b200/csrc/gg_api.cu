@@ -118,7 +118,11 @@ int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C,
   return ggi_softmax_rows(s, bias, p, R, C, P, Ns, dtype, ST);
 }
 int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream) {
-  return ggi_softmax_bwd_rows(p, gp, ds, R, C, dtype, ST);
+  return ggi_softmax_bwd_rows(p, gp, nullptr, ds, R, C, dtype, ST);
+}
+int gg_softmax_bwd_rows_add(const void* p, const void* gp, const void* gp2, void* ds, int64_t R, int C, int dtype,
+                            gg_stream_t stream) {
+  return ggi_softmax_bwd_rows(p, gp, gp2, ds, R, C, dtype, ST);
 }
 int gg_softmax_bwd2_rows(const void* p, const void* gp, const void* G, void* d_p, void* d_gp, int64_t R, int C, int dtype,
                          gg_stream_t stream) {

@@ -65,7 +65,7 @@ int ggi_tc_conv_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
                       int KH, int KW, int stride, int pad, int per_sample_w, cudaStream_t st);
 int ggi_tc_bmm(const void* A, const void* B, const float* bias, void* C, int b1, int b2, int M, int N, int K,
                const long* sa, const long* sb, const long* sc, float alpha, cudaStream_t st);
-int ggi_softmax_bwd_rows(const void* p, const void* gp, void* ds, long R, int C, int dtype, cudaStream_t st);
+int ggi_softmax_bwd_rows(const void* p, const void* gp, const void* gp2, void* ds, long R, int C, int dtype, cudaStream_t st);
 int ggi_weight_prep_multi(const float* master, const void* entries, const void* chunks, int nchunks, void* fwd, void* bwd,
                           int dtype, cudaStream_t st);
 int ggi_tc_attn_fwd(const void* q, const void* k, const void* v, const float* null_kv, void* o, float* lse, float* ksq_ws,

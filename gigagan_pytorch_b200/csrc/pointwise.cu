@@ -452,9 +452,11 @@ int ggi_softmax_rows(const void* s, const float* bias, void* p, long R, int C, i
 }
 
 // dS = P * (gP - sum_j P_j gP_j), one warp per row, rows in registers
+// gp2 (nullable): a second gradient of the same shape added to gp on the fly (the gradient-penalty pass hands the
+// probabilities' own second-order gradient in this way instead of materialising the sum)
 template <typename T, int MAXV>
-__global__ void softmax_bwd_rows_warp_kernel(const T* __restrict__ p, const T* __restrict__ gp, T* __restrict__ ds,
-                                             long R, int C) {
+__global__ void softmax_bwd_rows_warp_kernel(const T* __restrict__ p, const T* __restrict__ gp, const T* __restrict__ gp2,
+                                             T* __restrict__ ds, long R, int C) {
   constexpr int V = VecN<T>::N;
   long r = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -467,6 +469,12 @@ __global__ void softmax_bwd_rows_warp_kernel(const T* __restrict__ p, const T* _
     if (vi < nvec) {
       ldv(p + r * C + vi * V, pv[i]);
       ldv(gp + r * C + vi * V, gv[i]);
+      if (gp2) {
+        float g2[V];
+        ldv(gp2 + r * C + vi * V, g2);
+#pragma unroll
+        for (int j = 0; j < V; ++j) gv[i][j] += g2[j];
+      }
 #pragma unroll
       for (int j = 0; j < V; ++j) dot = fmaf(pv[i][j], gv[i][j], dot);
     }
@@ -483,25 +491,28 @@ __global__ void softmax_bwd_rows_warp_kernel(const T* __restrict__ p, const T* _
   }
 }
 template <typename T>
-__global__ void softmax_bwd_rows_kernel(const T* __restrict__ p, const T* __restrict__ gp, T* __restrict__ ds, int C) {
+__global__ void softmax_bwd_rows_kernel(const T* __restrict__ p, const T* __restrict__ gp, const T* __restrict__ gp2,
+                                        T* __restrict__ ds, int C) {
   __shared__ float red[32];
   long r = blockIdx.x;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float dot = 0.f;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) dot += ldf(p + r * C + c) * ldf(gp + r * C + c);
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    dot += ldf(p + r * C + c) * (ldf(gp + r * C + c) + (gp2 ? ldf(gp2 + r * C + c) : 0.f));
   dot = warp_sum(dot);
   if (lane == 0) red[wid] = dot;
   __syncthreads();
   dot = 0.f;
   for (int i = 0; i < nw; ++i) dot += red[i];
-  for (int c = threadIdx.x; c < C; c += blockDim.x) stf(ds + r * C + c, ldf(p + r * C + c) * (ldf(gp + r * C + c) - dot));
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    stf(ds + r * C + c, ldf(p + r * C + c) * (ldf(gp + r * C + c) + (gp2 ? ldf(gp2 + r * C + c) : 0.f) - dot));
 }
-int ggi_softmax_bwd_rows(const void* p, const void* gp, void* ds, long R, int C, int dtype, cudaStream_t st) {
+int ggi_softmax_bwd_rows(const void* p, const void* gp, const void* gp2, void* ds, long R, int C, int dtype, cudaStream_t st) {
   int V = dtype == GG_F32 ? 4 : 8;
-  if (C % V == 0 && C / V <= 32 * 6 && al16(p) && al16(gp) && al16(ds)) {
-    GG_DISPATCH(dtype, (softmax_bwd_rows_warp_kernel<T, 6><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)p, (const T*)gp, (T*)ds, R, C)));
+  if (C % V == 0 && C / V <= 32 * 6 && al16(p) && al16(gp) && al16(ds) && (!gp2 || al16(gp2))) {
+    GG_DISPATCH(dtype, (softmax_bwd_rows_warp_kernel<T, 6><<<gg_cdiv(R, 8), 256, 0, st>>>((const T*)p, (const T*)gp, (const T*)gp2, (T*)ds, R, C)));
   } else {
-    GG_DISPATCH(dtype, (softmax_bwd_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)p, (const T*)gp, (T*)ds, C)));
+    GG_DISPATCH(dtype, (softmax_bwd_rows_kernel<T><<<(unsigned)R, 128, 0, st>>>((const T*)p, (const T*)gp, (const T*)gp2, (T*)ds, C)));
   }
   return gg_check_launch("softmax_bwd_rows");
 }

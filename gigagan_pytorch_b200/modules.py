@@ -8,6 +8,7 @@ reference's NCHW fp32 tensors.  ``forward_nhwc`` is the layout-preserving entry 
 from __future__ import annotations
 
 import math
+import os
 from functools import partial
 from typing import Dict, List, Optional, Tuple
 
@@ -18,7 +19,10 @@ from torch import nn
 from . import ops
 from .ops import U_GELU, U_INVNORM, U_RSQRT_EPS8, U_SIGMOID, U_SILU
 
-_COMPUTE = {"dtype": torch.float32, "fused_attention": True}
+_COMPUTE = {"dtype": torch.float32, "fused_attention": True,
+            # gradient-penalty attention as one any-order autograd node (ops.ComposedAttnFn); GG_ATTN_NODE=0 keeps the
+            # composition from primitives (A/B measurements, parity cross-checks)
+            "attention_node": os.environ.get("GG_ATTN_NODE", "1") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -238,7 +242,10 @@ class SelfAttention(nn.Module):
         if Lp > L:
             mask = torch.zeros((1, Lp), dtype=torch.float32, device=q.device)
             mask[:, L:] = -1e30
+        node = _COMPUTE["attention_node"]                                  # one any-order node instead of primitives
         if self.dot_product:
+            if node:
+                return ops.composed_attention(q4, kf.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3), mask, self.scale)
             s = ops.bmm(q4, kt, alpha=self.scale)
             p = ops.softmax(s, mask, s.numel() // Lp, 1) if mask is not None else ops.softmax(s)
         else:
@@ -266,6 +273,9 @@ class SelfAttention(nn.Module):
             if width > nx:
                 qx.append(torch.zeros((n, seq, heads, width - nx), dtype=q.dtype, device=q.device))
             qa = torch.cat(qx, dim=-1)
+            if node:
+                return ops.composed_attention(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3),
+                                              None, 2.0 * self.scale)
             s = ops.bmm(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 3, 1), alpha=2.0 * self.scale)
             p = ops.softmax(s)
         o = ops.bmm(p, vf.permute(0, 2, 1, 3), out_bmhn=True)             # physical (n, seq, heads, d)

@@ -509,28 +509,35 @@ def _strides4(t):
     return (torch.tensor if False else list)(t.stride())
 
 
+def _bmm_raw(a, b, bias=None, alpha=1.0, out_bmhn=False):
+    """The batched-GEMM kernel call itself (no autograd): C = alpha * A @ B (+ bias).  ``out_bmhn``: a tensor whose
+    strides the result takes, True for a physical (b1, M, b2, N) layout, False for a contiguous result."""
+    import ctypes
+    b1, b2, m, k = a.shape
+    n = b.shape[-1]
+    assert b.shape[:3] == (b1, b2, k) and a.dtype == b.dtype
+    if isinstance(out_bmhn, torch.Tensor):      # lay the result out like this tensor (same shape, last dim dense)
+        c = torch.empty_strided((b1, b2, m, n), out_bmhn.stride(), dtype=a.dtype, device=a.device)
+    elif out_bmhn:
+        c = torch.empty((b1, m, b2, n), dtype=a.dtype, device=a.device).permute(0, 2, 1, 3)
+    else:
+        c = torch.empty((b1, b2, m, n), dtype=a.dtype, device=a.device)
+    sa = (ctypes.c_int64 * 4)(*a.stride())
+    sb = (ctypes.c_int64 * 4)(*b.stride())
+    sc = (ctypes.c_int64 * 3)(*c.stride()[:3])
+    assert c.stride(3) == 1
+    call("gg_bmm", _p(a), _p(b), _p(bias), _p(c), b1, b2, m, n, k, ctypes.cast(sa, ctypes.c_void_p),
+         ctypes.cast(sb, ctypes.c_void_p), ctypes.cast(sc, ctypes.c_void_p), float(alpha), _dt(a), _st())
+    return c
+
+
 class BmmFn(Function):
     """C[b1,b2] = alpha * A[b1,b2] @ B[b1,b2] (+ bias over the last axis).  A (b1,b2,M,K), B (b1,b2,K,N): any
     strides.  ``out_bmhn``: lay C out physically as (b1, M, b2, N) (returned view is still (b1,b2,M,N))."""
 
     @staticmethod
     def forward(ctx, a, b, bias, alpha, out_bmhn):
-        import ctypes
-        b1, b2, m, k = a.shape
-        n = b.shape[-1]
-        assert b.shape[:3] == (b1, b2, k) and a.dtype == b.dtype
-        if isinstance(out_bmhn, torch.Tensor):      # lay the result out like this tensor (same shape, last dim dense)
-            c = torch.empty_strided((b1, b2, m, n), out_bmhn.stride(), dtype=a.dtype, device=a.device)
-        elif out_bmhn:
-            c = torch.empty((b1, m, b2, n), dtype=a.dtype, device=a.device).permute(0, 2, 1, 3)
-        else:
-            c = torch.empty((b1, b2, m, n), dtype=a.dtype, device=a.device)
-        sa = (ctypes.c_int64 * 4)(*a.stride())
-        sb = (ctypes.c_int64 * 4)(*b.stride())
-        sc = (ctypes.c_int64 * 3)(*c.stride()[:3])
-        assert c.stride(3) == 1
-        call("gg_bmm", _p(a), _p(b), _p(bias), _p(c), b1, b2, m, n, k, ctypes.cast(sa, ctypes.c_void_p),
-             ctypes.cast(sb, ctypes.c_void_p), ctypes.cast(sc, ctypes.c_void_p), float(alpha), _dt(a), _st())
+        c = _bmm_raw(a, b, bias, alpha, out_bmhn)
         ctx.alpha, ctx.has_bias = alpha, bias is not None
         ctx.save_for_backward(a, b)
         return c
@@ -945,6 +952,161 @@ class SoftmaxBwdFn(Function):
 
 def softmax(s, bias=None, rows_per_sample=1, num_samples=1):
     return SoftmaxFn.apply(s, bias, rows_per_sample, num_samples)
+
+
+# ============================================================================= any-order attention node
+# Attention for the gradient-penalty pass as ONE autograd node with a hand-written first and second derivative.  The same
+# kernels as the composed form (batched GEMM, row softmax and its first / second order backward), but the
+# (tokens x keys)-sized traffic of the double backward drops from ~40 to ~30 passes per layer:
+#   * the two products that make up d/d(dS) (u_q k^T + q u_k^T) are ONE GEMM over concatenated K axes;
+#   * the probabilities' three gradient contributions (second-order softmax term, dO u_v^T from dV = P^T dO, and u_o v^T
+#     from O = P V) are never summed in memory: the two rank-d terms are one GEMM over concatenated K axes, the softmax
+#     term is added on the fly inside the softmax-backward kernel (gg_softmax_bwd_rows_add);
+#   * no autograd accumulation (ATen add) on any (tokens x keys) tensor.
+# Raw kernel calls are module-level callables so that tests/ can check the derivative plumbing against torch autograd
+# with stand-ins on a machine without a GPU; the product path has no such stand-ins.
+def _k_softmax(s, bias, P, Ns):
+    s = _c(s)
+    C = s.shape[-1]
+    p = torch.empty_like(s)
+    call("gg_softmax_rows", _p(s), _p(bias), _p(p), s.numel() // C, C, P, Ns, _dt(s), _st())
+    return p
+
+
+def _k_softmax_bwd(p, gp, gp2=None):
+    p, gp = _c(p), _c(gp)
+    C = p.shape[-1]
+    ds = torch.empty_like(p)
+    if gp2 is None:
+        call("gg_softmax_bwd_rows", _p(p), _p(gp), _p(ds), p.numel() // C, C, _dt(p), _st())
+    else:
+        call("gg_softmax_bwd_rows_add", _p(p), _p(gp), _p(_c(gp2)), _p(ds), p.numel() // C, C, _dt(p), _st())
+    return ds
+
+
+def _k_softmax_bwd2(p, gp, G):
+    """(d_p, d_gp) of dS = p * (gp - rowdot(p, gp)) for the upstream G; one pass when the row fits the kernel."""
+    C = p.shape[-1]
+    V = 4 if p.dtype == torch.float32 else 8
+    if C % V == 0 and C // V <= 160:
+        p, gp, G = _c(p), _c(gp), _c(G)
+        d_p, d_gp = torch.empty_like(p), torch.empty_like(p)
+        call("gg_softmax_bwd2_rows", _p(p), _p(gp), _p(G), _p(d_p), _p(d_gp), p.numel() // C, C, _dt(p), _st())
+        return d_p, d_gp
+    with torch.no_grad():
+        d_gp = _k_softmax_bwd(p, G)
+        r = rowdot(p, gp)
+        t = axpby(1.0, mul(G, gp), -1.0, scale_rows(G, r))
+        d_p = axpby(1.0, t, -1.0, scale_rows(gp, rowdot(G, p)))
+    return d_p, d_gp
+
+
+def _k_bmm(a, b, alpha=1.0, out=False):
+    return _bmm_raw(a, b, None, alpha, out)
+
+
+def _t(x):
+    return x.transpose(-1, -2)
+
+
+def _attn_first_order(qa, ka, v, p, go, alpha, gp_extra=None, lowrank=None):
+    """dqa, dka, dv of o = softmax(alpha qa ka^T) v for the cotangent go; gp_extra / lowrank: further gradients of the
+    probabilities ((tokens x keys) tensor added inside the softmax backward; (a, b) meaning a b^T folded into the dP GEMM)."""
+    if lowrank is None:
+        dP = _k_bmm(go, _t(v))
+    else:
+        a2, b2 = lowrank
+        dP = _k_bmm(torch.cat((go, a2), dim=-1), _t(torch.cat((v, b2), dim=-1)))
+    dv = _k_bmm(_t(p), go, 1.0, v if _dense_like(v) else False)
+    dS = _k_softmax_bwd(p, dP, gp_extra)
+    dqa = _k_bmm(dS, ka, alpha, qa if _dense_like(qa) else False)
+    dka = _k_bmm(_t(dS), qa, alpha, ka if _dense_like(ka) else False)
+    return dqa, dka, dv, dP, dS
+
+
+class ComposedAttnFn(Function):
+    """(o, p) = attention(qa, ka, v): p = softmax(alpha * qa @ ka^T + mask), o = p @ v.  qa (b, h, n, D), ka (b, h, m, D),
+    v (b, h, m, d), any strides; mask fp32 (1, m) or None (constant).  o is laid out physically as (b, n, h, d).  p is
+    returned so that it is part of the graph (the second-order node differentiates through it); callers ignore it."""
+
+    @staticmethod
+    def forward(ctx, qa, ka, v, mask, alpha, holder):
+        s = _k_bmm(qa, _t(ka), alpha)
+        p = _k_softmax(s, mask, s.numel() // s.shape[-1], 1) if mask is not None else _k_softmax(s, None, 1, 1)
+        del s
+        o = _k_bmm(p, v, 1.0, True)
+        ctx.save_for_backward(qa, ka, v, p)
+        ctx.alpha, ctx.holder = alpha, holder
+        ctx.set_materialize_grads(False)
+        return o, p
+
+    @staticmethod
+    def backward(ctx, go, gp):
+        qa, ka, v, p = ctx.saved_tensors
+        if go is None:
+            go = torch.zeros((qa.shape[0], qa.shape[2], qa.shape[1], v.shape[-1]), dtype=v.dtype,
+                             device=v.device).permute(0, 2, 1, 3)
+        if torch.is_grad_enabled():          # create_graph=True: the first derivative as a differentiable node
+            assert gp is None
+            dqa, dka, dv = ComposedAttnBwdFn.apply(qa, ka, v, p, go, ctx.alpha, ctx.holder)
+        else:
+            lowrank = ctx.holder.pop("lowrank", None)
+            dqa, dka, dv, _, _ = _attn_first_order(qa, ka, v, p, go, ctx.alpha, gp, lowrank)
+        return dqa, dka, dv, None, None, None
+
+
+class ComposedAttnBwdFn(Function):
+    """The first derivative of ComposedAttnFn as a node: (dqa, dka, dv) from (qa, ka, v, p, go); its backward is the
+    second derivative (terminal: a third order is never needed)."""
+
+    @staticmethod
+    def forward(ctx, qa, ka, v, p, go, alpha, holder):
+        dqa, dka, dv, dP, dS = _attn_first_order(qa, ka, v, p, go, alpha)
+        ctx.save_for_backward(qa, ka, v, p, go, dP, dS)
+        ctx.alpha, ctx.holder = alpha, holder
+        ctx.set_materialize_grads(False)
+        return dqa, dka, dv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, uq, uk, uv):
+        qa, ka, v, p, go, dP, dS = ctx.saved_tensors
+        alpha = ctx.alpha
+        g_qa = g_ka = g_v = g_p = g_go = None
+        # d/d(dS) = alpha (uq ka^T + qa uk^T): one GEMM over the concatenated K axes
+        if uq is not None and uk is not None:
+            G = _k_bmm(torch.cat((uq, qa), dim=-1), _t(torch.cat((ka, uk), dim=-1)), alpha)
+        elif uq is not None:
+            G = _k_bmm(uq, _t(ka), alpha)
+        elif uk is not None:
+            G = _k_bmm(qa, _t(uk), alpha)
+        else:
+            G = None
+        if G is not None:
+            g_p, g_dP = _k_softmax_bwd2(p, dP, G)
+            del G
+            g_v = _k_bmm(_t(g_dP), go, 1.0, v if _dense_like(v) else False)          # dP = go v^T
+            g_go = _k_bmm(g_dP, v)
+            del g_dP
+            if uk is not None:
+                g_qa = _k_bmm(dS, uk, alpha, qa if _dense_like(qa) else False)       # dka = alpha dS^T qa
+            if uq is not None:
+                g_ka = _k_bmm(_t(dS), uq, alpha, ka if _dense_like(ka) else False)   # dqa = alpha dS ka
+        if uv is not None:                                                             # dv = p^T go
+            t = _k_bmm(p, uv)
+            g_go = t if g_go is None else axpby(1.0, g_go, 1.0, t)
+            if g_p is None:
+                g_p = _k_bmm(go, _t(uv))
+            else:
+                # go uv^T is a rank-d gradient of the probabilities: handed to the forward node, which folds it into
+                # its dP GEMM (K axes concatenated) instead of a (tokens x keys)-sized accumulation here
+                ctx.holder["lowrank"] = (go, uv)
+        return g_qa, g_ka, g_v, g_p, g_go, None, None
+
+
+def composed_attention(qa, ka, v, mask, alpha):
+    o, _ = ComposedAttnFn.apply(qa, ka, v, mask, alpha, {})
+    return o
 
 
 # ============================================================================= resampling (separable, sparse)

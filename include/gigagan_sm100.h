@@ -88,6 +88,11 @@ int gg_softmax_rows(const void* s, const float* bias, void* p, int64_t R, int C,
 
 /* ds = p * (gp - rowsum(p * gp)): softmax backward for one [R,C] matrix (autograd of the softmax at :588) */
 int gg_softmax_bwd_rows(const void* p, const void* gp, void* ds, int64_t R, int C, int dtype, gg_stream_t stream);
+/* same with a second gradient of the same shape added to gp on the fly: ds = p * ((gp + gp2) - rowsum(p * (gp + gp2)));
+ * gp2 may be NULL.  Used by the attention node of the gradient-penalty pass (the probabilities collect a second-order
+ * gradient besides the one arriving through the value product). */
+int gg_softmax_bwd_rows_add(const void* p, const void* gp, const void* gp2, void* ds, int64_t R, int C, int dtype,
+                            gg_stream_t stream);
 
 /* second-order softmax backward (double backward of :588 inside the gradient penalty), one pass:
  * d_gp = p*(G - <G,p>), d_p = G*(gp - <p,gp>) - gp*<G,p>.  Row length must be a multiple of the 16-byte vector and

@@ -371,6 +371,45 @@ def test_composed_attention_padded_bf16_vs_fp32():
         assert relmax(fz, ref) < 3e-2
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("dot", [False, True])
+def test_attention_node_matches_primitive_composition_through_double_backward(dot, dtype, tol):
+    """gradient-penalty attention as ONE any-order node (ops.ComposedAttnFn: K-concatenated products, deferred rank-d
+    gradient of the probabilities, softmax backward with on-the-fly addend) against the composition from closed
+    primitives, on a penalty-shaped objective (first-order term + squared input gradient) at 32x32 tokens, both logit
+    forms (gigagan_pytorch.py:562-592 under :138-155)."""
+    import gigagan_pytorch_b200 as g
+    from gigagan_pytorch_b200 import modules
+    g.set_compute_dtype(dtype)
+    torch.manual_seed(0)
+    blk = g.SelfAttention(64, dim_head=64, heads=2, dot_product=dot).to(dev())
+    x0 = torch.randn(2, 32, 32, 64, device=dev())
+    w = torch.randn(2, 32, 32, 64, device=dev()).to(dtype)
+    res = []
+    for node in (False, True):
+        old = modules._COMPUTE["attention_node"]
+        modules._COMPUTE["attention_node"] = node
+        try:
+            blk.zero_grad(set_to_none=True)
+            x = x0.clone().to(dtype).requires_grad_()
+            o = blk.forward_nhwc(x, fused=False)
+            gx, = torch.autograd.grad(ops_sum(o, w), x, create_graph=True, retain_graph=True)
+            total = ops_sum(o, w) + 10.0 * ops_sum(gx, gx)
+            total.backward()
+            res.append([o.detach(), gx.detach(), x.grad] + [p.grad for p in blk.parameters()])
+        finally:
+            modules._COMPUTE["attention_node"] = old
+    for a, b in zip(res[1], res[0]):
+        assert torch.isfinite(a).all()
+        assert relmax(a, b) < tol, (a.shape, relmax(a, b))
+
+
+def ops_sum(a, b):
+    from gigagan_pytorch_b200 import ops
+    a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
+    return ops.sum_all(ops.dot_sc(a2, b2, a2.shape[0], 1))
+
+
 def test_fused_attention_matches_composed_large():
     """size beyond the oracle's reach: fused (online softmax) vs composed (materialised) on 32x32 tokens."""
     import gigagan_pytorch_b200 as g

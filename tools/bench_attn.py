@@ -9,8 +9,13 @@ dev = torch.device("cuda:0")
 L = _lib.lib()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=dev)
 VARIANTS = (("gen1_8w", 8), ("gen2_8w", 16), ("gen2_16w", 0))
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None        # optional: one shape name, one flag value (ncu captures)
+if len(sys.argv) > 2:
+    VARIANTS = tuple(v for v in VARIANTS if v[1] == int(sys.argv[2]))
 for name, B, n, l2 in (("D_res32_l2", 64, 1024, True), ("D_res16_l2", 128, 256, True), ("G_res32_dot", 16, 1024, False),
                        ("G_res16_dot", 16, 256, False)):
+    if ONLY and name != ONLY:
+        continue
     heads, d = 8, 64
     torch.manual_seed(0)
     qkv = (torch.randn(B, n, 3 * heads * d, device=dev) * 0.5).to(torch.bfloat16).requires_grad_()
