@@ -17,6 +17,11 @@
 // NSW = 8 instantiations exist for A/B measurements (gg_set_flags bit 4).
 #include "attn_tc_common.cuh"
 
+#define ATC2_FWD_KS 4      // key-tile stages of the forward kernel
+#define ATC2_DQ_KS 3       // key-tile stages of the dQ kernel (a key tile is read by S(j) early and by dQ(j) late)
+#define ATC2_DKV_QS 3      // query / dO tile stages of the dK,dV kernel
+#define ATC2_DKV_BARS (32768 + ATC2_DKV_QS * 16384 + 16384 + ATC2_DKV_QS * 16384 + 65536 + 512)   // tiles + |k|^2 row
+
 __device__ __forceinline__ void tc_ld32_nw(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
                "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -71,20 +76,23 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const AtcP p, const float* __restrict__ null_kv,
                  const float* __restrict__ ksq, bf16* __restrict__ o, float* __restrict__ lse2) {
   constexpr int NH = NSW / 4, CW = 128 / NH, NST = NSW * 32, OC = 64 / NH;
-  constexpr uint32_t AUX = 147456;
+  constexpr int KS = ATC2_FWD_KS;                   // key-tile stages: pass A only takes row maxima, i.e. runs at the speed
+                                                    // the key tiles arrive - two stages left it TMA-latency bound
+  constexpr uint32_t AUX = 16384 + KS * 16384 + 32768 + 65536;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // layout: Q 16K | K[2] 32K | V[2] 32K | P[2] 64K | ksq[2][128] 1K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
-  const uint32_t sQ = base, sK = base + 16384, sV = sK + 32768, sP = sV + 32768;
+  // layout: Q 16K | K[KS] | V[2] 32K | P[2] 64K | ksq[2][128] 1K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
+  const uint32_t sQ = base, sK = base + 16384, sV = sK + KS * 16384, sP = sV + 32768;
   float* ksq_sm = (float*)(gbase + AUX);
   float* null_sm = (float*)(gbase + AUX + 1024);
   float* xchg = (float*)(gbase + AUX + 1536);
   const uint32_t bars = base + AUX + 3584;
-  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13, P_EMPTY = 15, O_FULL = 17 };
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + 2, S_FULL = V_EMPTY + 2,
+         S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, O_FULL = P_EMPTY + 2, NBAR = O_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 3584 + 8 * 18);
+  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 3584 + 8 * NBAR);
 
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
@@ -93,8 +101,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
   if (threadIdx.x == 0) {
     mbar_init(bar(Q_FULL), 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
       mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
       mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), NSW);
       mbar_init(bar(P_FULL + i), NSW); mbar_init(bar(P_EMPTY + i), 1);
@@ -126,8 +134,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     int kc = 0, vc = 0;
     for (int pass = 0; pass < 2; ++pass)
       for (int j = 0; j < T; ++j) {
-        int s = kc & 1;
-        mbar_wait(bar(K_EMPTY + s), ((kc >> 1) & 1) ^ 1u);
+        int s = kc % KS;
+        mbar_wait(bar(K_EMPTY + s), ((kc / KS) & 1) ^ 1u);
         mbar_expect_tx_el(bar(K_FULL + s), 16384, el);
         tma_load_4d_el(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b, el);
         ++kc;
@@ -144,8 +152,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t el = tc_elect_one();
     int kc = 0, sc = 0, pc = 0;
     auto issue_S = [&]() {
-      int ks = kc & 1, ss = sc & 1;
-      mbar_wait(bar(K_FULL + ks), (kc >> 1) & 1);
+      int ks = kc % KS, ss = sc & 1;
+      mbar_wait(bar(K_FULL + ks), (kc / KS) & 1);
       mbar_wait(bar(S_EMPTY + ss), ((sc >> 1) & 1) ^ 1u);
       tc_fence_after();
       {
@@ -191,8 +199,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int cb = hsel * CW;                         // first column of this thread's slab
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r; // global token row
-    float kq = 0.f;                                   // |k|^2 * kb2 of the NEXT tile (threads 0..127 of the group)
-    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2; };
+    float kq = 0.f;                                   // |k|^2 of the NEXT tile (threads 0..127 of the group), raw: nothing
+                                                      // may consume the register before the tile boundary
+    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = __ldg(ksq + ((long)bh * p.n) + j * ATC_T + st); };
     ksq_fetch(0);
     float t_null = -INFINITY;
     mbar_wait(bar(Q_FULL), 0);
@@ -219,7 +228,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       int ss = sc & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[ss * 128 + st] = kq;
+        if (st < 128) ksq_sm[ss * 128 + st] = kq * p.kb2;
         named_bar_sync(1, NST);
         ksq_fetch(j + 1 < T ? j + 1 : 0);             // the tile after the last one of pass A is tile 0 of pass B
       }
@@ -255,7 +264,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       int ss = sc & 1, ps = pc & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[ss * 128 + st] = kq;
+        if (st < 128) ksq_sm[ss * 128 + st] = kq * p.kb2;
         named_bar_sync(1, NST);
         if (j + 1 < T) ksq_fetch(j + 1);
       }
@@ -339,19 +348,22 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const float* __restrict__ lse2, bf16* __restrict__ dq, float* __restrict__ delta,
                     float* __restrict__ nullrow) {
   constexpr int NH = NSW / 4, CW = 128 / NH, NST = NSW * 32, OC = 64 / NH, CPT = 8 / NH;
-  constexpr uint32_t AUX = 163840;
+  constexpr int KS = ATC2_DQ_KS;                    // a key tile is released only by dQ(j): with two stages the refill of
+                                                    // tile j+2 (and with it S(j+2)) waited for a TMA round trip after dQ(j)
+  constexpr uint32_t AUX = 32768 + KS * 16384 + 32768 + 65536;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // Q 16K | dO 16K | K[2] 32K | V[2] 32K | dS[2] 64K | ksq[2][128] 1K | null 512B | exchange [4][NH][128] <=8K | barriers
-  const uint32_t sQ = base, sDO = base + 16384, sK = base + 32768, sV = base + 65536, sDS = base + 98304;
+  // Q 16K | dO 16K | K[KS] | V[2] 32K | dS[2] 64K | ksq[2][128] 1K | null 512B | exchange [4][NH][128] <=8K | barriers
+  const uint32_t sQ = base, sDO = base + 16384, sK = base + 32768, sV = sK + KS * 16384, sDS = sV + 32768;
   float* ksq_sm = (float*)(gbase + AUX);
   float* null_sm = (float*)(gbase + AUX + 1024);
   float* xchg = (float*)(gbase + AUX + 1536);
   const uint32_t bars = base + AUX + 9728;
-  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, DP_FULL = 13, DP_EMPTY = 14,
-         DS_FULL = 15, DS_EMPTY = 17, DQ_FULL = 19, NBAR = 20 };
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + 2, S_FULL = V_EMPTY + 2,
+         S_EMPTY = S_FULL + 2, DP_FULL = S_EMPTY + 2, DP_EMPTY = DP_FULL + 1, DS_FULL = DP_EMPTY + 1, DS_EMPTY = DS_FULL + 2,
+         DQ_FULL = DS_EMPTY + 2, NBAR = DQ_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 9728 + 8 * NBAR);
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
@@ -360,8 +372,8 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int T = p.tiles;
   if (threadIdx.x == 0) {
     mbar_init(bar(Q_FULL), 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1);
       mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
       mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), NSW);
       mbar_init(bar(DS_FULL + i), NSW); mbar_init(bar(DS_EMPTY + i), 1);
@@ -391,11 +403,11 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_load_4d_el(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
     tma_load_4d_el(sDO, &tmDO, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
     for (int j = 0; j < T; ++j) {
-      int s = j & 1;
+      int s = j & 1, ks = j % KS;
       uint32_t par = ((j >> 1) & 1) ^ 1u;
-      mbar_wait(bar(K_EMPTY + s), par);
-      mbar_expect_tx_el(bar(K_FULL + s), 16384, el);
-      tma_load_4d_el(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b, el);
+      mbar_wait(bar(K_EMPTY + ks), ((j / KS) & 1) ^ 1u);
+      mbar_expect_tx_el(bar(K_FULL + ks), 16384, el);
+      tma_load_4d_el(sK + ks * 16384, &tmK, bar(K_FULL + ks), 0, j * ATC_T, h, b, el);
       mbar_wait(bar(V_EMPTY + s), par);
       mbar_expect_tx_el(bar(V_FULL + s), 16384, el);
       tma_load_4d_el(sV + s * 16384, &tmV, bar(V_FULL + s), 0, j * ATC_T, h, b, el);
@@ -403,12 +415,12 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 1) {
     const uint32_t el = tc_elect_one();
     auto issue_S = [&](int j) {
-      int s = j & 1;
-      mbar_wait(bar(K_FULL + s), (j >> 1) & 1);
+      int s = j & 1, ks = j % KS;
+      mbar_wait(bar(K_FULL + ks), (j / KS) & 1);
       mbar_wait(bar(S_EMPTY + s), ((j >> 1) & 1) ^ 1u);
       tc_fence_after();
       {
-        uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + s * 16384, 1024, 2);
+        uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + ks * 16384, 1024, 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16_el(tS + s * 128, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
         tc_commit_el(bar(S_FULL + s), el);
@@ -436,18 +448,18 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // the next tile's products first: the softmax warps release S / dP as soon as they hold them in registers, so these
       // run underneath tile j's exponentials; only then wait for tile j's dS
       if (j + 1 < T) { issue_S(j + 1); issue_dP(j + 1); }
-      int s = j & 1;
+      int s = j & 1, ks = j % KS;
       mbar_wait(bar(DS_FULL + s), (j >> 1) & 1);
       tc_fence_after();
       {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t da = make_smem_desc(sDS + s * 32768 + (k >> 2) * 16384, 1024, 2) + (uint64_t)(2 * (k & 3));
-          uint64_t db = make_smem_desc_mn(sK + s * 16384 + k * 2048, 0, 1024);
+          uint64_t db = make_smem_desc_mn(sK + ks * 16384 + k * 2048, 0, 1024);
           tc_mma_f16_el(tDQ, da, db, idesc_dq, (j | k) ? 1u : 0u, el);
         }
         tc_commit_el(bar(DS_EMPTY + s), el);
-        tc_commit_el(bar(K_EMPTY + s), el);
+        tc_commit_el(bar(K_EMPTY + ks), el);
         if (j == T - 1) tc_commit_el(bar(DQ_FULL), el);
       }
       __syncwarp();
@@ -460,10 +472,16 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r;
     const long srow = (long)bh * p.n + qt * ATC_T + r;
-    float kq = 0.f;
-    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = ksq[((long)bh * p.n) + j * ATC_T + st] * p.kb2; };
+    float kq = 0.f;                                    // raw |k|^2 of the next tile (scaled when it is staged)
+    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = __ldg(ksq + ((long)bh * p.n) + j * ATC_T + st); };
     ksq_fetch(0);
     const float L2 = lse2[srow];
+    uint4 ovr[CPT];                                    // this thread's chunks of the O row: in flight while Q / dO arrive
+    {
+      const bf16* orow = o + grow * p.o_rs + h * ATC_D;
+#pragma unroll
+      for (int cc = 0; cc < CPT; ++cc) ovr[cc] = __ldg(reinterpret_cast<const uint4*>(orow) + hsel * CPT + cc);
+    }
     mbar_wait(bar(Q_FULL), 0);
     // streaming pass over this row of Q, dO (smem tiles) and O (global): delta = dO.O, q.k_null, dO.v_null - the NH threads
     // of a row take CPT 16-byte chunks each and exchange the partial sums
@@ -471,13 +489,12 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     {
       const uint8_t* qr = gbase + (sQ - base) + r * 128;
       const uint8_t* dr = gbase + (sDO - base) + r * 128;
-      const bf16* orow = o + grow * p.o_rs + h * ATC_D;
 #pragma unroll
       for (int cc = 0; cc < CPT; ++cc) {
         const int c = hsel * CPT + cc;
         uint4 qv = *reinterpret_cast<const uint4*>(qr + ((c ^ (r & 7)) << 4));
         uint4 dv = *reinterpret_cast<const uint4*>(dr + ((c ^ (r & 7)) << 4));
-        uint4 ov = __ldg(reinterpret_cast<const uint4*>(orow) + c);
+        uint4 ov = ovr[cc];
         const __nv_bfloat162* qh = reinterpret_cast<const __nv_bfloat162*>(&qv);
         const __nv_bfloat162* dh = reinterpret_cast<const __nv_bfloat162*>(&dv);
         const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&ov);
@@ -523,7 +540,7 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < T; ++j) {
       int s = j & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[s * 128 + st] = kq;
+        if (st < 128) ksq_sm[s * 128 + st] = kq * p.kb2;
         named_bar_sync(1, NST);
         if (j + 1 < T) ksq_fetch(j + 1);
       }
@@ -597,20 +614,26 @@ attn2_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // K 16K | V 16K | [Q 16K | ones 16K] x2 | dO x2 | P 32K | dS 32K
-  const uint32_t sK = base, sV = base + 16384, sQO = base + 32768, sDO = base + 98304, sP = base + 131072, sDS = base + 163840;
-  float* ksq_sm = (float*)(gbase + 196608);
-  const uint32_t bars = base + 197120;
-  enum { KV_FULL = 0, QO_FULL = 1, QO_EMPTY = 3, SDP_FULL = 5, SDP_EMPTY = 6, PDS_FULL = 7, PDS_EMPTY = 8, OUT_FULL = 9, NBAR = 10 };
+  constexpr int QS = ATC2_DKV_QS;                   // query / dO stages: a stage is released only by dV/dK(i); with two stages
+                                                    // S/dP(i+2) waited for a TMA round trip behind them (28 % of the softmax
+                                                    // warps' samples in ncu).  The block of ones (columns 64..79 of the dK
+                                                    // product's B operand, reached through the descriptor's LBO) is shared.
+  // K 16K | V 16K | Q[QS] | ones 16K | dO[QS] | P 32K | dS 32K | ksq 512B | barriers
+  const uint32_t sK = base, sV = base + 16384, sQ = base + 32768, sOnes = sQ + QS * 16384, sDO = sOnes + 16384,
+                 sP = sDO + QS * 16384, sDS = sP + 32768;
+  float* ksq_sm = (float*)(gbase + ATC2_DKV_BARS - 512);
+  const uint32_t bars = base + ATC2_DKV_BARS;
+  enum { KV_FULL = 0, QO_FULL = 1, QO_EMPTY = QO_FULL + QS, SDP_FULL = QO_EMPTY + QS, SDP_EMPTY = SDP_FULL + 1,
+         PDS_FULL = SDP_EMPTY + 1, PDS_EMPTY = PDS_FULL + 1, OUT_FULL = PDS_EMPTY + 1, NBAR = OUT_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(gbase + 197120 + 8 * NBAR);
+  uint32_t* tmem_slot = (uint32_t*)(gbase + ATC2_DKV_BARS + 8 * NBAR);
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int kt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
   const int b = bh / p.heads, h = bh % p.heads;
   const int T = p.tiles;
   if (threadIdx.x == 0) {
     mbar_init(bar(KV_FULL), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(bar(QO_FULL + i), 1); mbar_init(bar(QO_EMPTY + i), 1); }
+    for (int i = 0; i < QS; ++i) { mbar_init(bar(QO_FULL + i), 1); mbar_init(bar(QO_EMPTY + i), 1); }
     mbar_init(bar(SDP_FULL), 1); mbar_init(bar(SDP_EMPTY), NSW);
     mbar_init(bar(PDS_FULL), NSW); mbar_init(bar(PDS_EMPTY), 1); mbar_init(bar(OUT_FULL), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -619,12 +642,10 @@ attn2_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  {   // the two "ones" slabs (bf16 1.0 everywhere; swizzle-invariant)
+  {   // the "ones" slab (bf16 1.0 everywhere; swizzle-invariant)
     uint4 one4 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    for (int i = threadIdx.x; i < 2 * 1024; i += 64 + NSW * 32) {
-      int buf = i >> 10, off = (i & 1023) << 4;
-      *reinterpret_cast<uint4*>(gbase + (sQO - base) + buf * 32768 + 16384 + off) = one4;
-    }
+    for (int i = threadIdx.x; i < 1024; i += 64 + NSW * 32)
+      *reinterpret_cast<uint4*>(gbase + (sOnes - base) + (i << 4)) = one4;
     fence_async_smem();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 192 && L2M) ksq_sm[threadIdx.x - 64] = ksq[(long)bh * p.n + kt * ATC_T + (threadIdx.x - 64)] * p.kb2;
@@ -643,21 +664,21 @@ attn2_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     tma_load_4d_el(sK, &tmK, bar(KV_FULL), 0, kt * ATC_T, h, b, el);
     tma_load_4d_el(sV, &tmV, bar(KV_FULL), 0, kt * ATC_T, h, b, el);
     for (int i = 0; i < T; ++i) {
-      int s = i & 1;
-      mbar_wait(bar(QO_EMPTY + s), ((i >> 1) & 1) ^ 1u);
+      int s = i % QS;
+      mbar_wait(bar(QO_EMPTY + s), ((i / QS) & 1) ^ 1u);
       mbar_expect_tx_el(bar(QO_FULL + s), 32768, el);
-      tma_load_4d_el(sQO + s * 32768, &tmQ, bar(QO_FULL + s), 0, i * ATC_T, h, b, el);
+      tma_load_4d_el(sQ + s * 16384, &tmQ, bar(QO_FULL + s), 0, i * ATC_T, h, b, el);
       tma_load_4d_el(sDO + s * 16384, &tmDO, bar(QO_FULL + s), 0, i * ATC_T, h, b, el);
     }
   } else if (warp == 1) {
     const uint32_t el = tc_elect_one();
     auto issue_SdP = [&](int i) {
-      int s = i & 1;
-      mbar_wait(bar(QO_FULL + s), (i >> 1) & 1);
+      int s = i % QS;
+      mbar_wait(bar(QO_FULL + s), (i / QS) & 1);
       mbar_wait(bar(SDP_EMPTY), (i & 1) ^ 1u);
       tc_fence_after();
       {
-        uint64_t dq_ = make_smem_desc(sQO + s * 32768, 1024, 2), dk_ = make_smem_desc(sK, 1024, 2);
+        uint64_t dq_ = make_smem_desc(sQ + s * 16384, 1024, 2), dk_ = make_smem_desc(sK, 1024, 2);
         uint64_t do_ = make_smem_desc(sDO + s * 16384, 1024, 2), dv_ = make_smem_desc(sV, 1024, 2);
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16_el(tS, dq_ + (uint64_t)(2 * k), dk_ + (uint64_t)(2 * k), idesc_kk, k ? 1u : 0u, el);
@@ -671,7 +692,7 @@ attn2_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     issue_SdP(0);
     for (int i = 0; i < T; ++i) {
       if (i + 1 < T) issue_SdP(i + 1);      // needs only the early release of S / dP by the softmax warps of tile i
-      int s = i & 1;
+      int s = i % QS;
       mbar_wait(bar(PDS_FULL), i & 1);
       tc_fence_after();
       {
@@ -684,7 +705,7 @@ attn2_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           uint64_t as_ = make_smem_desc_mn(sDS + k * 2048, 16384, 1024);
-          uint64_t bq = make_smem_desc_mn(sQO + s * 32768 + k * 2048, 16384, 1024);
+          uint64_t bq = make_smem_desc_mn(sQ + s * 16384 + k * 2048, (uint32_t)(QS - s) * 16384u, 1024);   // LBO -> the ones
           tc_mma_f16_el(tDK, as_, bq, idesc_dk, (i | k) ? 1u : 0u, el);
         }
         tc_commit_el(bar(PDS_EMPTY), el);
@@ -806,7 +827,7 @@ static int atc2_launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
     cudaFuncSetAttribute(attn2_fwd_kernel<NSW, L2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  size_t smem = 1024 + 147456 + 3584 + 8 * 18 + 16;
+  size_t smem = 1024 + (16384 + ATC2_FWD_KS * 16384 + 32768 + 65536) + 3584 + 8 * (2 * ATC2_FWD_KS + 12) + 16;
   attn2_fwd_kernel<NSW, L2M><<<p.B * p.heads * p.tiles, 64 + NSW * 32, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
   return gg_check_launch("attn2_fwd");
 }
@@ -846,7 +867,8 @@ static int atc2_launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
     attr_set = true;
   }
   const int grid = p.B * p.heads * p.tiles, threads = 64 + NSW * 32;
-  size_t smem1 = 1024 + 163840 + 9728 + 8 * 20 + 16, smem2 = 1024 + 197120 + 8 * 10 + 16;
+  size_t smem1 = 1024 + (32768 + ATC2_DQ_KS * 16384 + 32768 + 65536) + 9728 + 8 * (2 * ATC2_DQ_KS + 16) + 16;
+  size_t smem2 = 1024 + ATC2_DKV_BARS + 8 * (2 * ATC2_DKV_QS + 6) + 16;
   float* nullrow = delta_ws + (size_t)p.B * p.heads * p.n;
   attn2_bwd_dq_kernel<NSW, L2M><<<grid, threads, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);
   if (p.has_null) atc_launch_null_grad(q, go, nullrow, null_kv, dnull_kv, p.B, p.n, p.heads, q_rs, p.mode, st);

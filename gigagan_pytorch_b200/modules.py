@@ -228,8 +228,9 @@ class SelfAttention(nn.Module):
         16-byte aligned rows for the TMA-fed tcgen05 batched GEMMs; padded columns get probability exactly 0."""
         L = seq + 1
         Lp = (L + 63) // 64 * 64 if (q.dtype == torch.bfloat16 and seq >= 64 and d % 16 == 0) else L
-        parts_k = [self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d), k.view(n, seq, heads, d)]
-        parts_v = [self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d), v.view(n, seq, heads, d)]
+        # (the broadcast null rows are materialised: a stride-0 input sends the whole cat down ATen's generic gather path)
+        parts_k = [self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d).contiguous(), k.view(n, seq, heads, d)]
+        parts_v = [self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d).contiguous(), v.view(n, seq, heads, d)]
         if Lp > L:
             z = torch.zeros((n, Lp - L, heads, d), dtype=q.dtype, device=q.device)
             parts_k.append(z)
@@ -245,7 +246,8 @@ class SelfAttention(nn.Module):
         node = _COMPUTE["attention_node"]                                  # one any-order node instead of primitives
         if self.dot_product:
             if node:
-                return ops.composed_attention(q4, kf.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3), mask, self.scale)
+                return ops.composed_attention(q4, kf.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3), mask,
+                                              self.scale).permute(0, 2, 1, 3)
             s = ops.bmm(q4, kt, alpha=self.scale)
             p = ops.softmax(s, mask, s.numel() // Lp, 1) if mask is not None else ops.softmax(s)
         else:
@@ -275,7 +277,7 @@ class SelfAttention(nn.Module):
             qa = torch.cat(qx, dim=-1)
             if node:
                 return ops.composed_attention(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 1, 3), vf.permute(0, 2, 1, 3),
-                                              None, 2.0 * self.scale)
+                                              None, 2.0 * self.scale).permute(0, 2, 1, 3)
             s = ops.bmm(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 3, 1), alpha=2.0 * self.scale)
             p = ops.softmax(s)
         o = ops.bmm(p, vf.permute(0, 2, 1, 3), out_bmhn=True)             # physical (n, seq, heads, d)
