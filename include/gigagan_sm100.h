@@ -29,7 +29,8 @@ int gg_has_tcgen05(void);
  * bit 1: disable the thin-layer ring kernels (conv_thin_tc.cu) so those shapes take the generic tcgen05 kernels;
  * bit 2: disable only the thin-layer weight-gradient kernel.
  * bit 3: fused attention on the first-generation kernels (8 softmax warps, chunked TMEM reads; attn_tc.cu);
- * bit 4: second-generation attention kernels (attn_tc2.cu) with 8 instead of 16 softmax warps (A/B measurements).
+ * bit 4: second-generation attention kernels (attn_tc2.cu) with 8 softmax warps in every kernel, bit 5: with 16 in every
+ *        kernel (default: forward 8, backward 16; A/B measurements).
  * Returns old flags. */
 int gg_set_flags(int flags);
 
