@@ -70,7 +70,10 @@ __device__ __forceinline__ void load_ksq_slab(const float* src, float* kk) {
 }
 
 // ================================================================================================= forward
-template <int NSW, bool L2M>
+// ONEP (shared-QK L2-distance form only, k == q): the logits are -s |q_i - k_j|^2 <= 0 with equality at j = i (and the null
+// key's logit is <= 0 as well), so the row maximum is known before any product is formed - in the reduced form used here
+// (the -s |q_i|^2 term dropped) it is s |q_i|^2 - and pass A disappears: half of the Q K^T products and key-tile loads.
+template <int NSW, bool L2M, bool ONEP>
 __global__ void __launch_bounds__(64 + NSW * 32, 1)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AtcP p, const float* __restrict__ null_kv,
@@ -83,16 +86,16 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // layout: Q 16K | K[KS] | V[2] 32K | P[2] 64K | ksq[2][128] 1K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
+  // layout: Q 16K | K[KS] | V[2] 32K | P[2] 64K | |k|^2 slabs [NSW][CW] 2K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
   const uint32_t sQ = base, sK = base + 16384, sV = sK + KS * 16384, sP = sV + 32768;
   float* ksq_sm = (float*)(gbase + AUX);
-  float* null_sm = (float*)(gbase + AUX + 1024);
-  float* xchg = (float*)(gbase + AUX + 1536);
-  const uint32_t bars = base + AUX + 3584;
+  float* null_sm = (float*)(gbase + AUX + 2048);
+  float* xchg = (float*)(gbase + AUX + 2560);
+  const uint32_t bars = base + AUX + 4608;
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + 2, S_FULL = V_EMPTY + 2,
          S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, O_FULL = P_EMPTY + 2, NBAR = O_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 3584 + 8 * NBAR);
+  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 4608 + 8 * NBAR);
 
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
@@ -132,7 +135,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     mbar_expect_tx_el(bar(Q_FULL), 16384, el);
     tma_load_4d_el(sQ, &tmQ, bar(Q_FULL), 0, qt * ATC_T, h, b, el);
     int kc = 0, vc = 0;
-    for (int pass = 0; pass < 2; ++pass)
+    for (int pass = ONEP ? 1 : 0; pass < 2; ++pass)
       for (int j = 0; j < T; ++j) {
         int s = kc % KS;
         mbar_wait(bar(K_EMPTY + s), ((kc / KS) & 1) ^ 1u);
@@ -167,7 +170,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       ++kc; ++sc;
     };
     mbar_wait(bar(Q_FULL), 0);
-    for (int j = 0; j < T; ++j) issue_S();           // pass A: row maxima
+    if (!ONEP)
+      for (int j = 0; j < T; ++j) issue_S();         // pass A: row maxima
     issue_S();                                        // pass B, S_0
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) issue_S();
@@ -199,9 +203,19 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int cb = hsel * CW;                         // first column of this thread's slab
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r; // global token row
-    float kq = 0.f;                                   // |k|^2 of the NEXT tile (threads 0..127 of the group), raw: nothing
-                                                      // may consume the register before the tile boundary
-    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = __ldg(ksq + ((long)bh * p.n) + j * ATC_T + st); };
+    // |k|^2 of a key tile: every WARP stages its own CW-column slab (lanes < CW/4 fetch one float4 a tile ahead, raw -
+    // nothing may consume the register before the tile boundary - and store it scaled; __syncwarp instead of a barrier
+    // over all softmax warps, which cost 18 % of the samples as a convoy point in front of every tile)
+    float* kslab = ksq_sm + (warp - 2) * CW;
+    float4 kq4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ksq_fetch = [&](int j) {
+      if (L2M && lane < CW / 4) kq4 = __ldg(reinterpret_cast<const float4*>(ksq + ((long)bh * p.n) + j * ATC_T + cb) + lane);
+    };
+    auto ksq_stage = [&]() {
+      __syncwarp();                                   // the previous tile's reads of the slab are done
+      if (lane < CW / 4) reinterpret_cast<float4*>(kslab)[lane] = make_float4(kq4.x * p.kb2, kq4.y * p.kb2, kq4.z * p.kb2, kq4.w * p.kb2);
+      __syncwarp();
+    };
     ksq_fetch(0);
     float t_null = -INFINITY;
     mbar_wait(bar(Q_FULL), 0);
@@ -224,12 +238,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     float m = t_null;
     int sc = 0, pc = 0;
+    if (ONEP) m = -p.kb2 * __ldg(ksq + (long)bh * p.n + qt * ATC_T + r);      // s log2(e) |q_r|^2: the diagonal logit
     // ---------------- pass A: row maximum (each thread over its CW columns)
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < (ONEP ? 0 : T); ++j) {
       int ss = sc & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[ss * 128 + st] = kq * p.kb2;
-        named_bar_sync(1, NST);
+        ksq_stage();
         ksq_fetch(j + 1 < T ? j + 1 : 0);             // the tile after the last one of pass A is tile 0 of pass B
       }
       mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
@@ -242,7 +256,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (lane == 0) mbar_arrive(bar(S_EMPTY + ss));  // accumulator handed back before the arithmetic
       if (L2M) {
         float kk[CW];
-        load_ksq_slab<CW>(ksq_sm + ss * 128 + cb, kk);
+        load_ksq_slab<CW>(kslab, kk);
 #pragma unroll
         for (int e = 0; e < CW; ++e) m = fmaxf(m, fmaf(__uint_as_float(v[e]), p.c2, kk[e]));
       } else {
@@ -253,10 +267,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       ++sc;
     }
-    xchg[hsel * 128 + r] = m;
-    named_bar_sync(2, NST);
+    if (!ONEP) {
+      xchg[hsel * 128 + r] = m;
+      named_bar_sync(2, NST);
 #pragma unroll
-    for (int hh = 0; hh < NH; ++hh) m = fmaxf(m, xchg[hh * 128 + r]);
+      for (int hh = 0; hh < NH; ++hh) m = fmaxf(m, xchg[hh * 128 + r]);
+    }
     // ---------------- pass B: probabilities, partial row sums, this thread's slab of P
     const float p_null = p.has_null ? fast_exp2(t_null - m) : 0.f;
     const float negm = -m;
@@ -264,8 +280,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       int ss = sc & 1, ps = pc & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[ss * 128 + st] = kq * p.kb2;
-        named_bar_sync(1, NST);
+        ksq_stage();
         if (j + 1 < T) ksq_fetch(j + 1);
       }
       mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
@@ -279,7 +294,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       uint32_t pk[CW / 2];
       if (L2M) {
         float kk[CW];
-        load_ksq_slab<CW>(ksq_sm + ss * 128 + cb, kk);
+        load_ksq_slab<CW>(kslab, kk);
 #pragma unroll
         for (int e = 0; e < CW; e += 2) {
           float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), p.c2, kk[e]) + negm);
@@ -355,17 +370,17 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // Q 16K | dO 16K | K[KS] | V[2] 32K | dS[2] 64K | ksq[2][128] 1K | null 512B | exchange [4][NH][128] <=8K | barriers
+  // Q 16K | dO 16K | K[KS] | V[2] 32K | dS[2] 64K | |k|^2 slabs [NSW][CW] 2K | null 512B | exchange [4][NH][128] <=8K | barriers
   const uint32_t sQ = base, sDO = base + 16384, sK = base + 32768, sV = sK + KS * 16384, sDS = sV + 32768;
   float* ksq_sm = (float*)(gbase + AUX);
-  float* null_sm = (float*)(gbase + AUX + 1024);
-  float* xchg = (float*)(gbase + AUX + 1536);
-  const uint32_t bars = base + AUX + 9728;
+  float* null_sm = (float*)(gbase + AUX + 2048);
+  float* xchg = (float*)(gbase + AUX + 2560);
+  const uint32_t bars = base + AUX + 10752;
   enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + 2, S_FULL = V_EMPTY + 2,
          S_EMPTY = S_FULL + 2, DP_FULL = S_EMPTY + 2, DP_EMPTY = DP_FULL + 1, DS_FULL = DP_EMPTY + 1, DS_EMPTY = DS_FULL + 2,
          DQ_FULL = DS_EMPTY + 2, NBAR = DQ_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
-  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 9728 + 8 * NBAR);
+  uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 10752 + 8 * NBAR);
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
   const int b = bh / p.heads, h = bh % p.heads;
@@ -472,8 +487,11 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r;
     const long srow = (long)bh * p.n + qt * ATC_T + r;
-    float kq = 0.f;                                    // raw |k|^2 of the next tile (scaled when it is staged)
-    auto ksq_fetch = [&](int j) { if (L2M && st < 128) kq = __ldg(ksq + ((long)bh * p.n) + j * ATC_T + st); };
+    float* kslab = ksq_sm + (warp - 2) * CW;           // per-warp slab of the key tile's |k|^2 (see the forward kernel)
+    float4 kq4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto ksq_fetch = [&](int j) {
+      if (L2M && lane < CW / 4) kq4 = __ldg(reinterpret_cast<const float4*>(ksq + ((long)bh * p.n) + j * ATC_T + cb) + lane);
+    };
     ksq_fetch(0);
     const float L2 = lse2[srow];
     uint4 ovr[CPT];                                    // this thread's chunks of the O row: in flight while Q / dO arrive
@@ -540,8 +558,9 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < T; ++j) {
       int s = j & 1;
       if (L2M) {
-        if (st < 128) ksq_sm[s * 128 + st] = kq * p.kb2;
-        named_bar_sync(1, NST);
+        __syncwarp();
+        if (lane < CW / 4) reinterpret_cast<float4*>(kslab)[lane] = make_float4(kq4.x * p.kb2, kq4.y * p.kb2, kq4.z * p.kb2, kq4.w * p.kb2);
+        __syncwarp();
         if (j + 1 < T) ksq_fetch(j + 1);
       }
       mbar_wait(bar(S_FULL + s), (j >> 1) & 1);
@@ -558,7 +577,7 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t pk[CW / 2];
       if (L2M) {
         float kk[CW];
-        load_ksq_slab<CW>(ksq_sm + s * 128 + cb, kk);
+        load_ksq_slab<CW>(kslab, kk);
 #pragma unroll
         for (int e = 0; e < CW; e += 2) {
           float p0 = fast_exp2(fmaf(__uint_as_float(sv[e]), p.c2, kk[e]) + negL2);
@@ -819,16 +838,16 @@ static bool atc2_eligible(int nq, int nk, int d, long q_rs, long k_rs, long v_rs
   return d == ATC_D && nq == nk && nq % ATC_T == 0 && nq >= ATC_T && !(q_rs % 8) && !(k_rs % 8) && !(v_rs % 8);
 }
 
-template <int NSW, bool L2M>
+template <int NSW, bool L2M, bool ONEP>
 static int atc2_launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AtcP& p,
                            const float* null_kv, const float* ksq_ws, void* o, float* lse, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn2_fwd_kernel<NSW, L2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn2_fwd_kernel<NSW, L2M, ONEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  size_t smem = 1024 + (16384 + ATC2_FWD_KS * 16384 + 32768 + 65536) + 3584 + 8 * (2 * ATC2_FWD_KS + 12) + 16;
-  attn2_fwd_kernel<NSW, L2M><<<p.B * p.heads * p.tiles, 64 + NSW * 32, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
+  size_t smem = 1024 + (16384 + ATC2_FWD_KS * 16384 + 32768 + 65536) + 4608 + 8 * (2 * ATC2_FWD_KS + 12) + 16;
+  attn2_fwd_kernel<NSW, L2M, ONEP><<<p.B * p.heads * p.tiles, 64 + NSW * 32, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
   return gg_check_launch("attn2_fwd");
 }
 
@@ -849,10 +868,14 @@ int ggi_tc2_attn_fwd(const void* q, const void* k, const void* v, const float* n
   CUtensorMap tmQ, tmK, tmV;
   if (make_qkv_map(&tmQ, q, B, nq, heads, q_rs) || make_qkv_map(&tmK, k, B, nk, heads, k_rs) || make_qkv_map(&tmV, v, B, nk, heads, v_rs)) return -1;
   if (mode == 1) atc_launch_ksq(k, ksq_ws, B, nk, heads, k_rs, st);
-  if (nsw == 8) return mode == 1 ? atc2_launch_fwd<8, true>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
-                                 : atc2_launch_fwd<8, false>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st);
-  return mode == 1 ? atc2_launch_fwd<16, true>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
-                   : atc2_launch_fwd<16, false>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st);
+  // the single-pass form needs the keys to BE the queries (the discriminator's shared-QK attention); gg_set_flags bit 6
+  // (passed in as nsw + 64) keeps the two-pass kernel for A/B measurements
+  const bool onep = mode == 1 && q == k && q_rs == k_rs && !(nsw & 64);
+  nsw &= 63;
+#define ATC2_FWD(NSW_, L2_, ONEP_) atc2_launch_fwd<NSW_, L2_, ONEP_>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
+  if (nsw == 8) return mode != 1 ? ATC2_FWD(8, false, false) : onep ? ATC2_FWD(8, true, true) : ATC2_FWD(8, true, false);
+  return mode != 1 ? ATC2_FWD(16, false, false) : onep ? ATC2_FWD(16, true, true) : ATC2_FWD(16, true, false);
+#undef ATC2_FWD
 }
 
 template <int NSW, bool L2M>
@@ -867,7 +890,7 @@ static int atc2_launch_bwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const
     attr_set = true;
   }
   const int grid = p.B * p.heads * p.tiles, threads = 64 + NSW * 32;
-  size_t smem1 = 1024 + (32768 + ATC2_DQ_KS * 16384 + 32768 + 65536) + 9728 + 8 * (2 * ATC2_DQ_KS + 16) + 16;
+  size_t smem1 = 1024 + (32768 + ATC2_DQ_KS * 16384 + 32768 + 65536) + 10752 + 8 * (2 * ATC2_DQ_KS + 16) + 16;
   size_t smem2 = 1024 + ATC2_DKV_BARS + 8 * (2 * ATC2_DKV_QS + 6) + 16;
   float* nullrow = delta_ws + (size_t)p.B * p.heads * p.n;
   attn2_bwd_dq_kernel<NSW, L2M><<<grid, threads, smem1, st>>>(tmQ, tmK, tmV, tmDO, p, null_kv, ksq_ws, (const bf16*)o, lse2, (bf16*)dq, delta_ws, nullrow);

@@ -31,6 +31,8 @@ int gg_has_tcgen05(void);
  * bit 3: fused attention on the first-generation kernels (8 softmax warps, chunked TMEM reads; attn_tc.cu);
  * bit 4: second-generation attention kernels (attn_tc2.cu) with 8 softmax warps in every kernel, bit 5: with 16 in every
  *        kernel (default: forward 8, backward 16; A/B measurements).
+ * bit 6: keep the two-pass forward for the shared-QK L2 attention (default: single pass, the row maximum of
+ *        -|q_i - k_j|^2 is the diagonal).
  * Returns old flags. */
 int gg_set_flags(int flags);
 

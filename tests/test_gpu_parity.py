@@ -503,9 +503,12 @@ def test_patch_select_matches_rearrange(dtype):
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("n", [256, 1024])
-def test_tcgen05_fused_attention(mode, n):
+@pytest.mark.parametrize("variant", [0, 8, 16, 32, 64])
+def test_tcgen05_fused_attention(mode, n, variant):
     """tcgen05 fused attention forward + backward (TMEM accumulators, softmax out of TMEM, P/dS through swizzled
-    smem) vs the FFMA flash kernels on identical bf16 inputs (strided q/k/v views, null key/value, dot and L2)."""
+    smem) vs the FFMA flash kernels on identical bf16 inputs (strided q/k/v views, null key/value, dot and L2).
+    variant = gg_set_flags bits: 0 default (second generation; single-pass forward for the shared-QK L2 form),
+    8 first generation, 16 / 32 second generation with 8 / 16 softmax warps everywhere, 64 two-pass L2 forward."""
     from gigagan_pytorch_b200 import _lib, ops
     B, heads, d = 3, 2, 64
     dt = torch.bfloat16
@@ -517,7 +520,7 @@ def test_tcgen05_fused_attention(mode, n):
         qkv = (rn(1, B, n, 3 * heads * d) * 0.7).to(dev()).to(dt).requires_grad_()
         nk = null_kv.clone().requires_grad_()
         q, k, v = qkv[..., : heads * d], qkv[..., heads * d: 2 * heads * d], qkv[..., 2 * heads * d:]
-        old = L.gg_set_flags(force_ffma)
+        old = L.gg_set_flags(1 if force_ffma else variant)
         try:
             o = ops.fused_attention(q, q if mode == 1 else k, v, nk, heads, d ** -0.5, l2=(mode == 1))
             g1, g2 = torch.autograd.grad(o, (qkv, nk), go)
