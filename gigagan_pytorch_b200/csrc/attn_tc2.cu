@@ -73,29 +73,33 @@ __device__ __forceinline__ void load_ksq_slab(const float* src, float* kk) {
 // ONEP (shared-QK L2-distance form only, k == q): the logits are -s |q_i - k_j|^2 <= 0 with equality at j = i (and the null
 // key's logit is <= 0 as well), so the row maximum is known before any product is formed - in the reduced form used here
 // (the -s |q_i|^2 term dropped) it is s |q_i|^2 - and pass A disappears: half of the Q K^T products and key-tile loads.
-template <int NSW, bool L2M, bool ONEP>
-__global__ void __launch_bounds__(64 + NSW * 32, 1)
+// OCC = 2: two CTAs per SM (one buffer each for S, V and P, two key stages, 256 TMEM columns, <= 113 KB): a CTA spends ~6 us
+// of un-overlapped prologue/epilogue around 8-16 tile steps of ~0.5-0.8 us; a second resident CTA fills it.
+template <int NSW, bool L2M, bool ONEP, int OCC>
+__global__ void __launch_bounds__(64 + NSW * 32, OCC)
 attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AtcP p, const float* __restrict__ null_kv,
                  const float* __restrict__ ksq, bf16* __restrict__ o, float* __restrict__ lse2) {
   constexpr int NH = NSW / 4, CW = 128 / NH, NST = NSW * 32, OC = 64 / NH;
-  constexpr int KS = ATC2_FWD_KS;                   // key-tile stages: pass A only takes row maxima, i.e. runs at the speed
+  constexpr int KS = OCC == 2 ? 2 : ATC2_FWD_KS;    // key-tile stages: pass A only takes row maxima, i.e. runs at the speed
                                                     // the key tiles arrive - two stages left it TMA-latency bound
-  constexpr uint32_t AUX = 16384 + KS * 16384 + 32768 + 65536;
+  constexpr int NB = OCC == 2 ? 1 : 2;              // buffers of S (TMEM), V and P (shared memory)
+  constexpr uint32_t AUX = 16384 + KS * 16384 + NB * 16384 + NB * 32768;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  // layout: Q 16K | K[KS] | V[2] 32K | P[2] 64K | |k|^2 slabs [NSW][CW] 2K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
-  const uint32_t sQ = base, sK = base + 16384, sV = sK + KS * 16384, sP = sV + 32768;
+  // layout: Q 16K | K[KS] | V[NB] | P[NB] | |k|^2 slabs [NSW][CW] 2K | null k,v 512B | exchange [NH][128] <=2K | barriers | tmem slot
+  const uint32_t sQ = base, sK = base + 16384, sV = sK + KS * 16384, sP = sV + NB * 16384;
   float* ksq_sm = (float*)(gbase + AUX);
   float* null_sm = (float*)(gbase + AUX + 2048);
   float* xchg = (float*)(gbase + AUX + 2560);
   const uint32_t bars = base + AUX + 4608;
-  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + 2, S_FULL = V_EMPTY + 2,
-         S_EMPTY = S_FULL + 2, P_FULL = S_EMPTY + 2, P_EMPTY = P_FULL + 2, O_FULL = P_EMPTY + 2, NBAR = O_FULL + 1 };
+  enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + NB, S_FULL = V_EMPTY + NB,
+         S_EMPTY = S_FULL + NB, P_FULL = S_EMPTY + NB, P_EMPTY = P_FULL + NB, O_FULL = P_EMPTY + NB, NBAR = O_FULL + 1 };
   auto bar = [&](int i) { return bars + 8u * i; };
   uint32_t* tmem_slot = (uint32_t*)(gbase + AUX + 4608 + 8 * NBAR);
+  constexpr uint32_t TMEM_COLS = NB == 2 ? 512 : 256;
 
   const int warp = tc_warp_idx(), lane = threadIdx.x & 31;
   const int qt = blockIdx.x % p.tiles, bh = blockIdx.x / p.tiles;
@@ -105,7 +109,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   if (threadIdx.x == 0) {
     mbar_init(bar(Q_FULL), 1);
     for (int i = 0; i < KS; ++i) { mbar_init(bar(K_FULL + i), 1); mbar_init(bar(K_EMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NB; ++i) {
       mbar_init(bar(V_FULL + i), 1); mbar_init(bar(V_EMPTY + i), 1);
       mbar_init(bar(S_FULL + i), 1); mbar_init(bar(S_EMPTY + i), NSW);
       mbar_init(bar(P_FULL + i), NSW); mbar_init(bar(P_EMPTY + i), 1);
@@ -114,7 +118,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x >= 64 && threadIdx.x < 192 && p.has_null) {
@@ -125,7 +129,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 256;       // S[2] at columns 0 / 128, O at 256 (64 columns)
+  const uint32_t tS = tmem, tO = tmem + NB * 128;  // S[NB] at columns 0 (/ 128), O behind them (64 columns)
   const uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -143,8 +147,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tma_load_4d_el(sK + s * 16384, &tmK, bar(K_FULL + s), 0, j * ATC_T, h, b, el);
         ++kc;
         if (pass == 1) {
-          int sv = vc & 1;
-          mbar_wait(bar(V_EMPTY + sv), ((vc >> 1) & 1) ^ 1u);
+          int sv = vc % NB;
+          mbar_wait(bar(V_EMPTY + sv), ((vc / NB) & 1) ^ 1u);
           mbar_expect_tx_el(bar(V_FULL + sv), 16384, el);
           tma_load_4d_el(sV + sv * 16384, &tmV, bar(V_FULL + sv), 0, j * ATC_T, h, b, el);
           ++vc;
@@ -155,9 +159,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t el = tc_elect_one();
     int kc = 0, sc = 0, pc = 0;
     auto issue_S = [&]() {
-      int ks = kc % KS, ss = sc & 1;
+      int ks = kc % KS, ss = sc % NB;
       mbar_wait(bar(K_FULL + ks), (kc / KS) & 1);
-      mbar_wait(bar(S_EMPTY + ss), ((sc >> 1) & 1) ^ 1u);
+      mbar_wait(bar(S_EMPTY + ss), ((sc / NB) & 1) ^ 1u);
       tc_fence_after();
       {
         uint64_t da = make_smem_desc(sQ, 1024, 2), db = make_smem_desc(sK + ks * 16384, 1024, 2);
@@ -175,9 +179,9 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     issue_S();                                        // pass B, S_0
     for (int j = 0; j < T; ++j) {
       if (j + 1 < T) issue_S();
-      int ps = pc & 1;
-      mbar_wait(bar(P_FULL + ps), (pc >> 1) & 1);
-      mbar_wait(bar(V_FULL + ps), (pc >> 1) & 1);
+      int ps = pc % NB;
+      mbar_wait(bar(P_FULL + ps), (pc / NB) & 1);
+      mbar_wait(bar(V_FULL + ps), (pc / NB) & 1);
       tc_fence_after();
       {
 #pragma unroll
@@ -241,12 +245,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     if (ONEP) m = -p.kb2 * __ldg(ksq + (long)bh * p.n + qt * ATC_T + r);      // s log2(e) |q_r|^2: the diagonal logit
     // ---------------- pass A: row maximum (each thread over its CW columns)
     for (int j = 0; j < (ONEP ? 0 : T); ++j) {
-      int ss = sc & 1;
+      int ss = sc % NB;
       if (L2M) {
         ksq_stage();
         ksq_fetch(j + 1 < T ? j + 1 : 0);             // the tile after the last one of pass A is tile 0 of pass B
       }
-      mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
+      mbar_wait(bar(S_FULL + ss), (sc / NB) & 1);
       tc_fence_after();
       uint32_t v[CW];
       tc_ld_cols<CW>(tS + ss * 128 + lane_addr + cb, v);
@@ -278,12 +282,12 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float negm = -m;
     float l = hsel == 0 ? p_null : 0.f;
     for (int j = 0; j < T; ++j) {
-      int ss = sc & 1, ps = pc & 1;
+      int ss = sc % NB, ps = pc % NB;
       if (L2M) {
         ksq_stage();
         if (j + 1 < T) ksq_fetch(j + 1);
       }
-      mbar_wait(bar(S_FULL + ss), (sc >> 1) & 1);
+      mbar_wait(bar(S_FULL + ss), (sc / NB) & 1);
       tc_fence_after();
       uint32_t v[CW];
       tc_ld_cols<CW>(tS + ss * 128 + lane_addr + cb, v);
@@ -311,7 +315,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           pk[e >> 1] = pack_bf16x2(p0, p1);
         }
       }
-      mbar_wait(bar(P_EMPTY + ps), ((pc >> 1) & 1) ^ 1u);
+      mbar_wait(bar(P_EMPTY + ps), ((pc / NB) & 1) ^ 1u);
       uint8_t* ptile = gbase + (sP - base) + ps * 32768;
 #pragma unroll
       for (int g = 0; g < CW / 16; ++g) write_tile16_packed(ptile, r, cb + 16 * g, pk + 8 * g);
@@ -350,7 +354,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -838,16 +842,17 @@ static bool atc2_eligible(int nq, int nk, int d, long q_rs, long k_rs, long v_rs
   return d == ATC_D && nq == nk && nq % ATC_T == 0 && nq >= ATC_T && !(q_rs % 8) && !(k_rs % 8) && !(v_rs % 8);
 }
 
-template <int NSW, bool L2M, bool ONEP>
+template <int NSW, bool L2M, bool ONEP, int OCC>
 static int atc2_launch_fwd(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AtcP& p,
                            const float* null_kv, const float* ksq_ws, void* o, float* lse, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attn2_fwd_kernel<NSW, L2M, ONEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn2_fwd_kernel<NSW, L2M, ONEP, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
-  size_t smem = 1024 + (16384 + ATC2_FWD_KS * 16384 + 32768 + 65536) + 4608 + 8 * (2 * ATC2_FWD_KS + 12) + 16;
-  attn2_fwd_kernel<NSW, L2M, ONEP><<<p.B * p.heads * p.tiles, 64 + NSW * 32, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
+  constexpr int KS = OCC == 2 ? 2 : ATC2_FWD_KS, NB = OCC == 2 ? 1 : 2;
+  size_t smem = 1024 + (16384 + KS * 16384 + NB * 16384 + NB * 32768) + 4608 + 8 * (2 * KS + 6 * NB + 2) + 16;
+  attn2_fwd_kernel<NSW, L2M, ONEP, OCC><<<p.B * p.heads * p.tiles, 64 + NSW * 32, smem, st>>>(tmQ, tmK, tmV, p, null_kv, ksq_ws, (bf16*)o, lse);
   return gg_check_launch("attn2_fwd");
 }
 
@@ -871,10 +876,12 @@ int ggi_tc2_attn_fwd(const void* q, const void* k, const void* v, const float* n
   // the single-pass form needs the keys to BE the queries (the discriminator's shared-QK attention); gg_set_flags bit 6
   // (passed in as nsw + 64) keeps the two-pass kernel for A/B measurements
   const bool onep = mode == 1 && q == k && q_rs == k_rs && !(nsw & 64);
+  const bool occ2 = (nsw & 128) != 0;              // gg_set_flags bit 7: two CTAs per SM (8 softmax warps)
   nsw &= 63;
-#define ATC2_FWD(NSW_, L2_, ONEP_) atc2_launch_fwd<NSW_, L2_, ONEP_>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
-  if (nsw == 8) return mode != 1 ? ATC2_FWD(8, false, false) : onep ? ATC2_FWD(8, true, true) : ATC2_FWD(8, true, false);
-  return mode != 1 ? ATC2_FWD(16, false, false) : onep ? ATC2_FWD(16, true, true) : ATC2_FWD(16, true, false);
+#define ATC2_FWD(NSW_, L2_, ONEP_, OCC_) atc2_launch_fwd<NSW_, L2_, ONEP_, OCC_>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
+  if (occ2) return mode != 1 ? ATC2_FWD(8, false, false, 2) : onep ? ATC2_FWD(8, true, true, 2) : ATC2_FWD(8, true, false, 2);
+  if (nsw == 8) return mode != 1 ? ATC2_FWD(8, false, false, 1) : onep ? ATC2_FWD(8, true, true, 1) : ATC2_FWD(8, true, false, 1);
+  return mode != 1 ? ATC2_FWD(16, false, false, 1) : onep ? ATC2_FWD(16, true, true, 1) : ATC2_FWD(16, true, false, 1);
 #undef ATC2_FWD
 }
 

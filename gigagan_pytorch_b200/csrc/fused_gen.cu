@@ -1,6 +1,7 @@
 // Small fused kernels of the generator / discriminator glue (HBM- or latency-bound; one launch replaces a chain of
 // pointwise / reduction launches of the composed operators).  extern "C" surface declared in include/gigagan_sm100.h.
 #include "../../include/gigagan_sm100.h"
+#include <cstdlib>
 #include "gg_common.cuh"
 
 #define ST ((cudaStream_t)stream)
@@ -17,10 +18,10 @@ template <typename T, int NK>
 __global__ void __launch_bounds__(512)
 sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod, const float* __restrict__ kmod,
                   const T* __restrict__ x, T* __restrict__ xs, float* __restrict__ attn, float* __restrict__ dinv, int B,
-                  int n, int O, int I, int KK, int HW, int demod, float eps, long ldm, long ldk, int XB, int use_ssm) {
+                  int n, int O, int I, int KK, int HW, int demod, float eps, long ldm, long ldk, int XB, int use_ssm, int ob) {
   __shared__ float sa[SB_BCH * 8];
   __shared__ float red[16][SB_BCH];
-  const int OBL = (O + SB_OB - 1) / SB_OB;
+  const int OBL = (O + ob - 1) / ob;
   if ((int)blockIdx.x >= OBL) {
     const long per = (long)HW * I, tot = per * B;
     for (long e = (long)(blockIdx.x - OBL) * blockDim.x + threadIdx.x; e < tot; e += (long)XB * blockDim.x) {
@@ -47,8 +48,8 @@ sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod,
       if (blockIdx.x == 0) for (int j = 0; j < n; ++j) attn[b * n + j] = sa[threadIdx.x * 8 + j];
     }
     __syncthreads();
-    for (int oo = 0; oo < SB_OB; ++oo) {
-      const int o = blockIdx.x * SB_OB + oo;
+    for (int oo = 0; oo < ob; ++oo) {
+      const int o = blockIdx.x * ob + oo;
       if (o >= O) break;
       if (!demod) { if ((int)threadIdx.x < nb) dinv[(long)(b0 + threadIdx.x) * O + o] = 1.f; continue; }
       float ss[SB_BCH];
@@ -297,9 +298,11 @@ int gg_sbank_prep(const float* bank, const float* mod, const float* kmod, const 
   size_t smem = sizeof(float) * (size_t)SB_BCH * I;
   int use_ssm = smem <= 40 * 1024;
   if (!use_ssm) smem = 0;
-  const int OBL = gg_cdiv(O, SB_OB);
+  static int ob = 0;                               // output channels per block (GG_SB_OB: tuning sweeps)
+  if (!ob) { const char* e = getenv("GG_SB_OB"); ob = e ? atoi(e) : SB_OB; if (ob < 1) ob = 1; }
+  const int OBL = gg_cdiv(O, ob);
 #define SB_GO(NK) sbank_prep_kernel<T, NK><<<OBL + XB, 512, smem, ST>>>(bank, mod, kmod, (const T*)x, (T*)xs, attn, dinv, B, n, O, I, \
-                                                                       KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB, use_ssm)
+                                                                       KK, HW, demod, eps, (long)mod_ld, (long)kmod_ld, XB, use_ssm, ob)
   GG_DISPATCH(dtype, (n <= 1 ? SB_GO(1) : n <= 2 ? SB_GO(2) : n <= 4 ? SB_GO(4) : SB_GO(8)));
 #undef SB_GO
   return gg_check_launch("sbank_prep");

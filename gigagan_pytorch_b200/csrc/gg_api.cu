@@ -173,7 +173,7 @@ int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_k
     // groups), the backward 16; flag 16 forces 8 everywhere, flag 32 forces 16 everywhere (A/B measurements).
     int r = (g_flags & 8) ? ggi_tc_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST)
                           : ggi_tc2_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode,
-                                             ((g_flags & 32) ? 16 : 8) | (g_flags & 64), ST);
+                                             ((g_flags & 32) ? 16 : 8) | (g_flags & 192), ST);
     if (r <= 0) return r;
   }
 #endif

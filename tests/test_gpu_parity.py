@@ -503,12 +503,13 @@ def test_patch_select_matches_rearrange(dtype):
 
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("n", [256, 1024])
-@pytest.mark.parametrize("variant", [0, 8, 16, 32, 64])
+@pytest.mark.parametrize("variant", [0, 8, 16, 32, 64, 128])
 def test_tcgen05_fused_attention(mode, n, variant):
     """tcgen05 fused attention forward + backward (TMEM accumulators, softmax out of TMEM, P/dS through swizzled
     smem) vs the FFMA flash kernels on identical bf16 inputs (strided q/k/v views, null key/value, dot and L2).
     variant = gg_set_flags bits: 0 default (second generation; single-pass forward for the shared-QK L2 form),
-    8 first generation, 16 / 32 second generation with 8 / 16 softmax warps everywhere, 64 two-pass L2 forward."""
+    8 first generation, 16 / 32 second generation with 8 / 16 softmax warps everywhere, 64 two-pass L2 forward,
+    128 forward with two CTAs per SM."""
     from gigagan_pytorch_b200 import _lib, ops
     B, heads, d = 3, 2, 64
     dt = torch.bfloat16

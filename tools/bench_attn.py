@@ -8,7 +8,7 @@ from gigagan_pytorch_b200 import ops, _lib
 dev = torch.device("cuda:0")
 L = _lib.lib()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=dev)
-VARIANTS = (("gen1_8w", 8), ("gen2_8w", 16), ("gen2_16w", 32), ("gen2_2pass", 64), ("gen2_default", 0))
+VARIANTS = (("gen1_8w", 8), ("gen2_8w", 16), ("gen2_16w", 32), ("gen2_2pass", 64), ("gen2_occ2", 128), ("gen2_default", 0))
 ONLY = sys.argv[1] if len(sys.argv) > 1 else None        # optional: one shape name, one flag value (ncu captures)
 if len(sys.argv) > 2:
     VARIANTS = tuple(v for v in VARIANTS if v[1] == int(sys.argv[2]))
