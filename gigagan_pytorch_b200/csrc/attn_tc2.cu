@@ -876,7 +876,9 @@ int ggi_tc2_attn_fwd(const void* q, const void* k, const void* v, const float* n
   // the single-pass form needs the keys to BE the queries (the discriminator's shared-QK attention); gg_set_flags bit 6
   // (passed in as nsw + 64) keeps the two-pass kernel for A/B measurements
   const bool onep = mode == 1 && q == k && q_rs == k_rs && !(nsw & 64);
-  const bool occ2 = (nsw & 128) != 0;              // gg_set_flags bit 7: two CTAs per SM (8 softmax warps)
+  // default: two CTAs per SM with 8 softmax warps each (1.3x the one-CTA forms at every measured shape); gg_set_flags
+  // bits 4 / 5 / 7 select the one-CTA-per-SM kernels with 8 / 16 / 8 softmax warps (A/B measurements)
+  const bool occ2 = !(nsw & 128) && !(nsw & 256);
   nsw &= 63;
 #define ATC2_FWD(NSW_, L2_, ONEP_, OCC_) atc2_launch_fwd<NSW_, L2_, ONEP_, OCC_>(tmQ, tmK, tmV, p, null_kv, ksq_ws, o, lse, st)
   if (occ2) return mode != 1 ? ATC2_FWD(8, false, false, 2) : onep ? ATC2_FWD(8, true, true, 2) : ATC2_FWD(8, true, false, 2);

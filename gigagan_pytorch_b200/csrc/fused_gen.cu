@@ -13,7 +13,7 @@
 // size), every bank row [n][I*KK] is read once and reused for all images.  The remaining blocks write xs = x * (mod + 1)
 // over a slice of the whole batch.  attn = softmax over the n <= 8 kernel logits.
 #define SB_BCH 16
-#define SB_OB 4
+#define SB_OB 2       // measured (7 launches of the README-256 generator): 1 -> 0.276 ms, 2 -> 0.271, 4 -> 0.394
 template <typename T, int NK>
 __global__ void __launch_bounds__(512)
 sbank_prep_kernel(const float* __restrict__ bank, const float* __restrict__ mod, const float* __restrict__ kmod,

@@ -168,12 +168,12 @@ int gg_attn_fwd(const void* q, const void* k, const void* v, const float* null_k
                 int mode, int dtype, gg_stream_t stream) {
 #ifndef GG_NO_TC
   if (dtype == GG_BF16 && !(g_flags & 1)) {
-    // flag 8: first-generation kernels (8 softmax warps, chunked TMEM reads).  Second generation: the forward runs 8
-    // softmax warps (measured 5 % faster than 16 on the L2-distance form: it exchanges row maxima / sums between column
-    // groups), the backward 16; flag 16 forces 8 everywhere, flag 32 forces 16 everywhere (A/B measurements).
+    // flag 8: first-generation kernels (8 softmax warps, chunked TMEM reads).  Second generation: the forward runs two
+    // CTAs per SM with 8 softmax warps each, the backward 16 warps; flags 16 / 32: one CTA per SM with 8 / 16 warps in every
+    // kernel, flag 128: one-CTA forward with 8 warps, flag 64: two-pass L2 forward (A/B measurements).
     int r = (g_flags & 8) ? ggi_tc_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode, ST)
                           : ggi_tc2_attn_fwd(q, k, v, null_kv, o, lse, ksq_ws, B, heads, nq, nk, d, q_rs, k_rs, v_rs, o_rs, scale, mode,
-                                             ((g_flags & 32) ? 16 : 8) | (g_flags & 192), ST);
+                                             ((g_flags & 32) ? 16 : 8) | (g_flags & 192) | ((g_flags & 48) ? 256 : 0), ST);
     if (r <= 0) return r;
   }
 #endif

@@ -162,19 +162,61 @@ class FlatAdamW:
             yield off
             off += p.numel()
 
-    def step(self, grad_scale=1.0):
+    def _begin_step(self):
         ops.clear_weight_cache()
         if getattr(self, "bank", None) is not None:
             self.bank.dirty = True
         if self.flat.device.type != "cuda":
             raise RuntimeError("FlatAdamW.step needs the parameters on the GPU (no CPU path)")
         call("gg_incr", _p(self.step_t), _st())
-        call("gg_adamw", _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), _p(self.chunks), self.chunks.shape[0],
+
+    def _adamw(self, c0, c1, grad_scale):
+        """fused AdamW over chunk-table rows [c0, c1) (rows hold absolute offsets, so any sub-table is a valid launch)"""
+        call("gg_adamw", _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), self.chunks.data_ptr() + 16 * c0, c1 - c0,
              _p(self.step_t), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, float(grad_scale), _st())
+
+    def step(self, grad_scale=1.0):
+        self._begin_step()
+        self._adamw(0, self.chunks.shape[0], grad_scale)
 
     def all_reduce_grads(self, group=None):
         """SUM all-reduce of the flat gradient; the 1/world scaling is folded into the AdamW kernel."""
         dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+
+    def _part_bounds(self, parts):
+        """the chunk table cut into <= parts contiguous runs of about equal size: [(chunk0, chunk1, elem_lo, elem_hi)]"""
+        if getattr(self, "_bounds", (None, None))[0] != parts:
+            rows = self.chunks.tolist()
+            total = self.flat.numel()
+            target, out, c0 = total / max(parts, 1), [], 0
+            for k in range(1, parts + 1):
+                c1 = len(rows) if k == parts else c0
+                while k < parts and c1 < len(rows) and (rows[c1][0] + (rows[c1][3] << 31) + rows[c1][1]) <= k * target:
+                    c1 += 1
+                if c1 > c0:
+                    lo = rows[c0][0] + (rows[c0][3] << 31)
+                    hi = rows[c1 - 1][0] + (rows[c1 - 1][3] << 31) + rows[c1 - 1][1]
+                    out.append((c0, c1, lo, hi))
+                    c0 = c1
+            self._bounds = (parts, out)
+        return self._bounds[1]
+
+    def all_reduce_grads_pipelined(self, group=None, parts=4):
+        """the same SUM all-reduce as `parts` slices issued back to back (async): -> [(work, (chunk0, chunk1, lo, hi))].
+        A consumer that waits for slice i only (AdamW of that slice) runs under the reduction of slice i+1."""
+        bounds = self._part_bounds(parts)
+        return [(dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=group, async_op=True), (c0, c1, lo, hi))
+                for c0, c1, lo, hi in bounds]
+
+    def reduce_and_step(self, world_size, group=None, parts=4):
+        """gradient all-reduce pipelined with the fused AdamW update (data-parallel step, ref gigagan_pytorch.py:2426,
+        :2578 through accelerate's DDP): the update of a slice is launched as soon as ITS reduction is done and overlaps
+        the next slice's reduction on NCCL's stream; at 8 GPUs the update (0.36 ms for D) disappears under the exchange."""
+        pending = self.all_reduce_grads_pipelined(group, parts)
+        self._begin_step()
+        for work, (c0, c1, _, _) in pending:
+            work.wait()                                   # the current stream waits for this slice's reduction
+            self._adamw(c0, c1, 1.0 / world_size)
 
     # ---- checkpoint interchange: the state_dict is the one torch.optim.AdamW produces for the reference's optimiser
     # (optimizer.py:10-34: group 0 = parameters with ndim >= 2 (weight decay), group 1 = the rest, weight_decay 0;
@@ -832,8 +874,9 @@ class GigaGAN(nn.Module):
                 parts = [p.detach() / grad_accum_every for p in parts]
                 acc = parts if acc is None else [a + p for a, p in zip(acc, parts)]
         if self.is_distributed:
-            self.D_opt.all_reduce_grads()
-        self.D_opt.step(grad_scale=1.0 / self.world_size)
+            self.D_opt.reduce_and_step(self.world_size)
+        else:
+            self.D_opt.step()
         div, ms, gp, aux = acc
         return TrainDiscrLosses(div, ms if calc_multiscale_loss else None, 0., 0., gp, aux)
 
@@ -885,8 +928,9 @@ class GigaGAN(nn.Module):
             for p in frozen:                 # only the flags that were set before
                 p.requires_grad_(True)
         if self.is_distributed:
-            self.G_opt.all_reduce_grads()
-        self.G_opt.step(grad_scale=1.0 / self.world_size)
+            self.G_opt.reduce_and_step(self.world_size)
+        else:
+            self.G_opt.step()
         if self.is_main and self.has_ema_generator:
             self._ema_update()
         div, msd = acc

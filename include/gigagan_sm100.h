@@ -33,7 +33,8 @@ int gg_has_tcgen05(void);
  *        kernel (default: forward 8, backward 16; A/B measurements).
  * bit 6: keep the two-pass forward for the shared-QK L2 attention (default: single pass, the row maximum of
  *        -|q_i - k_j|^2 is the diagonal).
- * bit 7: attention forward with two CTAs per SM (single S / V / P buffers, 256 TMEM columns each).
+ * bit 7: attention forward with ONE CTA per SM (default: two CTAs per SM, single S / V / P buffers, 256 TMEM columns
+ *        each; bits 4 and 5 also select one-CTA forwards).
  * Returns old flags. */
 int gg_set_flags(int flags);
 

@@ -46,6 +46,19 @@ def _worker(rank, world, port, q):
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     ok = torch.allclose(opt.grad, sum(gathered)) and bool((net[0].weight.grad != 0).any())
+    # the pipelined form (slices reduced back to back, consumed one by one) gives the same buffer and covers it exactly
+    FlatAdamW.CHUNK = 16                                       # small chunks: several slices even for this toy model
+    opt2 = FlatAdamW(net)
+    opt2.grad.copy_(local)
+    pending = opt2.all_reduce_grads_pipelined(parts=3)
+    cover = torch.zeros(off, dtype=torch.int32)
+    rows = opt2.chunks.tolist()
+    for work, (c0, c1, lo, hi) in pending:
+        work.wait()
+        cover[lo:hi] += 1
+        ok = ok and lo == rows[c0][0] and hi == rows[c1 - 1][0] + rows[c1 - 1][1]
+    ok = ok and len(pending) >= 2 and int(cover.min()) == 1 and int(cover.max()) == 1
+    ok = ok and torch.allclose(opt2.grad, sum(gathered))
     q.put((rank, ok, opt.flat.clone()))
     dist.barrier()
     dist.destroy_process_group()

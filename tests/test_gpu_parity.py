@@ -509,7 +509,7 @@ def test_tcgen05_fused_attention(mode, n, variant):
     smem) vs the FFMA flash kernels on identical bf16 inputs (strided q/k/v views, null key/value, dot and L2).
     variant = gg_set_flags bits: 0 default (second generation; single-pass forward for the shared-QK L2 form),
     8 first generation, 16 / 32 second generation with 8 / 16 softmax warps everywhere, 64 two-pass L2 forward,
-    128 forward with two CTAs per SM."""
+    128 forward with one CTA per SM (the default runs two)."""
     from gigagan_pytorch_b200 import _lib, ops
     B, heads, d = 3, 2, 64
     dt = torch.bfloat16

@@ -1,6 +1,7 @@
 """Fused attention (tcgen05) timing at the discriminator's / generator's shapes: forward and backward, CUDA events, for the
 kernel variants (gg_set_flags 8: first generation; 16 / 32: second generation with 8 / 16 softmax warps everywhere;
-0: the default - second generation, forward 8 and backward 16 warps).  Also prints the largest deviation of every output/gradient from the first generation."""
+64: two-pass L2 forward; 128: forward with one CTA per SM;
+0: the default - second generation, forward two CTAs per SM x 8 warps, backward 16 warps).  Also prints the largest deviation of every output/gradient from the first generation."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,7 +9,7 @@ from gigagan_pytorch_b200 import ops, _lib
 dev = torch.device("cuda:0")
 L = _lib.lib()
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.int8, device=dev)
-VARIANTS = (("gen1_8w", 8), ("gen2_8w", 16), ("gen2_16w", 32), ("gen2_2pass", 64), ("gen2_occ2", 128), ("gen2_default", 0))
+VARIANTS = (("gen1_8w", 8), ("gen2_8w", 16), ("gen2_16w", 32), ("gen2_2pass", 64), ("gen2_fwd_1cta", 128), ("gen2_default", 0))
 ONLY = sys.argv[1] if len(sys.argv) > 1 else None        # optional: one shape name, one flag value (ncu captures)
 if len(sys.argv) > 2:
     VARIANTS = tuple(v for v in VARIANTS if v[1] == int(sys.argv[2]))

@@ -9,8 +9,8 @@ python tools/ncu_summarize.py gpurun_out/launches_$R.csv gpurun_out/${R}_ncu_ste
 head -30 gpurun_out/launches_${R}_summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_fprop_tc -c 3 -o gpurun_out/prof_conv_fprop_$R \
     python tools/bench_conv.py > gpurun_out/ncu_conv.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_ -c 6 -o gpurun_out/prof_attn_$R \
-    python tools/bench_attn.py > gpurun_out/ncu_attn.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn2_ -c 3 -o gpurun_out/prof_attn_$R \
+    python tools/bench_attn.py D_res32_l2 0 > gpurun_out/ncu_attn.log 2>&1
 for f in prof_conv_fprop_$R prof_attn_$R; do
   ncu -i gpurun_out/$f.ncu-rep --page raw --csv > gpurun_out/$f.raw.csv 2>/dev/null
 done
