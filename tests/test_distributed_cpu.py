@@ -64,16 +64,30 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_flat_bucket_allreduce_world2():
+def _run_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    try:
+        res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    except Exception:
+        for p in procs:
+            p.kill()
+        return None
     for p in procs:
         p.join(timeout=60)
-        assert p.exitcode == 0
+        if p.exitcode != 0:
+            return None
+    return res
+
+
+def test_flat_bucket_allreduce_world2():
+    res = _run_world2()
+    if res is None:                      # rendezvous trouble (the probed port was taken meanwhile, a slow first import): once more
+        res = _run_world2()
+    assert res is not None, "the two gloo ranks did not finish"
     assert all(ok for _, ok, _ in res)
     assert torch.equal(res[0][2], res[1][2]), "ranks must start from identical (broadcast) weights"
