@@ -2,19 +2,19 @@
 // tiles and the same maths as attn_tc.cu; replaces gigagan_pytorch.py:562-592 and its autograd backward).
 //
 // ncu on the first generation (profiles/r02_ncu_attention_tc.md): tensor pipe 16-23 % active, issue slots 32 % busy with
-// two softmax warps per scheduler - the softmax warps were LATENCY bound, not throughput bound:
-//   * every 16-column chunk paid one tcgen05.ld round trip before its arithmetic could start (four to eight per tile);
-//   * the L2-distance form fetched |k|^2 of the tile from global memory at the top of every tile (a full L2 round trip
-//     in front of the tile's first instruction), the dK/dV kernel fetched log-sum-exp and delta the same way;
-//   * in the backward kernels the next tile's S / dP products were only issued after the current tile's dQ (dK, dV)
-//     products, i.e. after the softmax warps had finished - their start-up latency was exposed once per tile.
-// Here:
-//   * NSW = 16 softmax warps (4 per scheduler), each thread owns 32 of the 128 tile columns; the thread pulls its whole
-//     slab of S (and dP) out of TMEM with ONE round trip and immediately hands the accumulator back to the MMA warp
-//     ("early release"), so the next tile's products run underneath this tile's exponentials;
-//   * the MMA warp issues S(j+1) / dP(j+1) BEFORE it waits for dS(j);
-//   * per-tile scalars (|k|^2, lse, delta) are prefetched one tile ahead into registers.
-// NSW = 8 instantiations exist for A/B measurements (gg_set_flags bit 4).
+// two softmax warps per scheduler - the softmax warps were LATENCY bound, not throughput bound.  The source page
+// (tools/ncu_source_regions.py) located the waits; what changed, in the order measured:
+//   * a softmax thread pulls its whole column slab of S (and dP) out of TMEM with ONE round trip and immediately hands the
+//     accumulator back to the MMA warp ("early release"); the MMA warp issues S(j+1) / dP(j+1) BEFORE it waits for dS(j);
+//   * per-tile scalars (|k|^2, lse, delta) are prefetched one tile ahead into registers, with no consumer behind the load;
+//   * stage depth follows the release point: 3 key stages in dQ (a key tile is released by dQ(j), not by S(j)), 3 query/dO
+//     stages with one shared block of ones in dK/dV, 4 key stages in the one-CTA forward;
+//   * |k|^2 of a key tile is staged per WARP (__syncwarp) instead of for all softmax warps behind a 512-thread barrier;
+//   * the shared-QK L2 form needs no max pass (ONEP): the row maximum of -s |q_i - k_j|^2 is the diagonal;
+//   * the forward runs two CTAs per SM (OCC = 2): ~6 us of prologue/epilogue per CTA around 8-16 short tile steps.
+// Template parameters: NSW softmax warps (8: each thread owns 64 of the 128 tile columns, 16: 32), L2M shared-QK L2-distance
+// logits, ONEP / OCC forward only.  Defaults: forward <8, *, *, 2>, backward <16, *>; gg_set_flags bits 3-7 select the
+// other instantiations (and the first generation) for A/B measurements and the parity tests.
 #include "attn_tc_common.cuh"
 
 #define ATC2_FWD_KS 4      // key-tile stages of the forward kernel
@@ -203,7 +203,6 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     const int r = q * 32 + lane;                      // row inside the tile
-    const int st = threadIdx.x - 64;                  // index among the softmax threads
     const int cb = hsel * CW;                         // first column of this thread's slab
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r; // global token row
@@ -487,7 +486,6 @@ attn2_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int q = warp & 3;                            // TMEM lane quarter
     const int hsel = (warp - 2) >> 2, cb = hsel * CW;  // column slab of this thread
     const int r = q * 32 + lane;
-    const int st = threadIdx.x - 64;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const long grow = (long)b * p.n + qt * ATC_T + r;
     const long srow = (long)bh * p.n + qt * ATC_T + r;

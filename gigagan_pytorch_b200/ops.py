@@ -750,12 +750,19 @@ class AxpbyFn(Function):
         out = torch.empty_like(x)
         call("gg_pw_axpby", float(alpha), _p(x), float(beta), _p(y), _p(out), x.numel(), _dt(x), _st())
         ctx.alpha, ctx.beta = alpha, beta
+        ctx.yshape = None if y is None else y.shape
         return out
 
     @staticmethod
     def backward(ctx, g):
-        gx = AxpbyFn.apply(ctx.alpha, g, 0.0, None) if ctx.needs_input_grad[1] else None
-        gy = AxpbyFn.apply(ctx.beta, g, 0.0, None) if ctx.needs_input_grad[3] else None
+        # a unit coefficient passes the gradient through as it is (x + y is the common case: two full copies of g otherwise)
+        gx = gy = None
+        if ctx.needs_input_grad[1]:
+            gx = g if ctx.alpha == 1.0 else AxpbyFn.apply(ctx.alpha, g, 0.0, None)
+        if ctx.needs_input_grad[3]:
+            gy = g if ctx.beta == 1.0 else AxpbyFn.apply(ctx.beta, g, 0.0, None)
+            if gy.shape != ctx.yshape:
+                gy = gy.reshape(ctx.yshape)
         return None, gx, None, gy
 
 
