@@ -742,6 +742,9 @@ def mul(a, b):
     return MulFn.apply(a, b)
 
 
+_AXPBY_PASS = os.environ.get("GG_AXPBY_PASS", "1") != "0"      # diagnostics: 0 restores the copying backward
+
+
 class AxpbyFn(Function):
     @staticmethod
     def forward(ctx, alpha, x, beta, y):
@@ -758,9 +761,9 @@ class AxpbyFn(Function):
         # a unit coefficient passes the gradient through as it is (x + y is the common case: two full copies of g otherwise)
         gx = gy = None
         if ctx.needs_input_grad[1]:
-            gx = g if ctx.alpha == 1.0 else AxpbyFn.apply(ctx.alpha, g, 0.0, None)
+            gx = g if (ctx.alpha == 1.0 and _AXPBY_PASS) else AxpbyFn.apply(ctx.alpha, g, 0.0, None)
         if ctx.needs_input_grad[3]:
-            gy = g if ctx.beta == 1.0 else AxpbyFn.apply(ctx.beta, g, 0.0, None)
+            gy = g if (ctx.beta == 1.0 and _AXPBY_PASS) else AxpbyFn.apply(ctx.beta, g, 0.0, None)
             if gy.shape != ctx.yshape:
                 gy = gy.reshape(ctx.yshape)
         return None, gx, None, gy

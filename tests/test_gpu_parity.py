@@ -648,7 +648,10 @@ def test_trainer_steps_run_and_cuda_graph_replay_matches_eager(upsampler, amp):
         gans.append(gan)
         its.append(cycle(Pool()))
     eager, graph = gans
-    tol_loss, tol_grad = (1e-2, 2e-2) if amp else (1e-4, 1e-3)
+    # fp32 is the check of the replay logic.  bf16: both trainers sum through fp32 atomics in arbitrary order and every
+    # difference passes bf16 roundings and LeakyReLU slopes; typical deviation 2e-3, one run in ~15 full-suite runs exceeded
+    # the former 2e-2 gradient bound, hence the margin
+    tol_loss, tol_grad = (2e-2, 5e-2) if amp else (1e-4, 1e-3)
     p_start = torch.cat([eager.G_opt.flat, eager.D_opt.flat]).clone()
     for step in range(1, 7):        # plain variant: eager warm-up, capture, replay; then the same for the penalty variant
         gp = step > 3
