@@ -22,7 +22,9 @@ from .ops import U_GELU, U_INVNORM, U_RSQRT_EPS8, U_SIGMOID, U_SILU
 _COMPUTE = {"dtype": torch.float32, "fused_attention": True,
             # gradient-penalty attention as one any-order autograd node (ops.ComposedAttnFn); GG_ATTN_NODE=0 keeps the
             # composition from primitives (A/B measurements, parity cross-checks)
-            "attention_node": os.environ.get("GG_ATTN_NODE", "1") != "0"}
+            "attention_node": os.environ.get("GG_ATTN_NODE", "1") != "0",
+            # ... and its augmented operands (shared-QK L2 form) from one kernel; GG_ATTN_AUGMENT=0: concatenations
+            "attention_augment": os.environ.get("GG_ATTN_AUGMENT", "1") != "0"}
 
 
 def set_compute_dtype(dtype):
@@ -228,6 +230,13 @@ class SelfAttention(nn.Module):
         16-byte aligned rows for the TMA-fed tcgen05 batched GEMMs; padded columns get probability exactly 0."""
         L = seq + 1
         Lp = (L + 63) // 64 * 64 if (q.dtype == torch.bfloat16 and seq >= 64 and d % 16 == 0) else L
+        if (_COMPUTE["attention_node"] and _COMPUTE["attention_augment"] and not self.dot_product and k is q
+                and q.dtype == torch.bfloat16 and d == 64 and Lp % 64 == 0):
+            # shared-QK L2 form on the benchmarked path: the augmented operands (see the composition below) come from one
+            # kernel, and one for each of their derivatives, instead of reductions, casts, fills and concatenations
+            qa, ka, va = ops.attn_augment(q.view(n, seq, heads, d), v.view(n, seq, heads, d), self.null_kv, Lp)
+            return ops.composed_attention(qa.permute(0, 2, 1, 3), ka.permute(0, 2, 1, 3), va.permute(0, 2, 1, 3), None,
+                                          2.0 * self.scale).permute(0, 2, 1, 3)
         # (the broadcast null rows are materialised: a stride-0 input sends the whole cat down ATen's generic gather path)
         parts_k = [self.null_kv[0].to(q.dtype)[None, None].expand(n, 1, heads, d).contiguous(), k.view(n, seq, heads, d)]
         parts_v = [self.null_kv[1].to(q.dtype)[None, None].expand(n, 1, heads, d).contiguous(), v.view(n, seq, heads, d)]

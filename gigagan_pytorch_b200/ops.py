@@ -1124,6 +1124,81 @@ class ComposedAttnBwdFn(Function):
         return g_qa, g_ka, g_v, g_p, g_go, None, None
 
 
+# ---- operand builder of that node for the shared-QK L2 form (bf16, dim_head 64): one kernel each for the forward, the
+# first and the second derivative instead of row reductions, casts, zero fills and three concatenations (and, backwards,
+# strided slice copies and gradient accumulations of the key-sized tensors).
+def _k_aug_fwd(q4, v4, null_kv, Lp):
+    n, seq, h, d = q4.shape
+    qa = torch.empty((n, seq, h, d + 16), dtype=q4.dtype, device=q4.device)
+    ka = torch.empty((n, Lp, h, d + 16), dtype=q4.dtype, device=q4.device)
+    vf = torch.empty((n, Lp, h, d), dtype=q4.dtype, device=q4.device)
+    call("gg_attn_augment_fwd", _p(q4), _p(v4), _p(null_kv), _p(qa), _p(ka), _p(vf), n, seq, Lp, h, d, _st())
+    return qa, ka, vf
+
+
+def _k_aug_bwd(dqa, dka, dvf, q4, null_kv):
+    n, seq, h, d = q4.shape
+    dq, dv = torch.empty_like(q4), torch.empty_like(q4)
+    dnull = torch.empty((2, h, d), dtype=torch.float32, device=q4.device)
+    call("gg_attn_augment_bwd", _p(dqa), _p(dka), _p(dvf), _p(q4), _p(null_kv), _p(dq), _p(dv), _p(dnull), n, seq, dka.shape[1],
+         h, d, _st())
+    return dq, dv, dnull
+
+
+def _k_aug_bwd2(wq, wv, wnull, q4, null_kv, dka):
+    n, seq, h, d = q4.shape
+    Lp = dka.shape[1]
+    g_dqa = torch.empty((n, seq, h, d + 16), dtype=q4.dtype, device=q4.device)
+    g_dka, g_dvf = torch.empty_like(dka), torch.empty((n, Lp, h, d), dtype=q4.dtype, device=q4.device)
+    g_q = torch.empty_like(q4)
+    g_null = torch.empty((2, h, d), dtype=torch.float32, device=q4.device)
+    call("gg_attn_augment_bwd2", _p(wq), _p(wv), _p(wnull), _p(q4), _p(null_kv), _p(dka), _p(g_dqa), _p(g_dka), _p(g_dvf), _p(g_q),
+         _p(g_null), n, seq, Lp, h, d, _st())
+    return g_dqa, g_dka, g_dvf, g_q, g_null
+
+
+class AttnAugmentFn(Function):
+    """(qa, ka, vf) of the shared-QK L2 attention from q (= k) and v, both (n, seq, h, 64) contiguous, and the null
+    key/value parameter (2, h, 64) fp32; see csrc/attn_augment.cu for the layouts."""
+
+    @staticmethod
+    def forward(ctx, q4, v4, null_kv, Lp):
+        q4, v4, null_kv = _c(q4), _c(v4), _c(null_kv)
+        ctx.save_for_backward(q4, null_kv)
+        return _k_aug_fwd(q4, v4, null_kv, Lp)
+
+    @staticmethod
+    def backward(ctx, dqa, dka, dvf):
+        q4, null_kv = ctx.saved_tensors
+        if torch.is_grad_enabled():
+            dq, dv, dnull = AttnAugmentBwdFn.apply(dqa, dka, dvf, q4, null_kv)
+        else:
+            dq, dv, dnull = _k_aug_bwd(_c(dqa), _c(dka), _c(dvf), q4, null_kv)
+        return dq, dv, dnull, None
+
+
+class AttnAugmentBwdFn(Function):
+    """first derivative of AttnAugmentFn as a node (linear in the gradients, bilinear in (dka[..., 64], q)); its backward
+    is terminal"""
+
+    @staticmethod
+    def forward(ctx, dqa, dka, dvf, q4, null_kv):
+        dqa, dka, dvf = _c(dqa), _c(dka), _c(dvf)
+        ctx.save_for_backward(q4, null_kv, dka)
+        return _k_aug_bwd(dqa, dka, dvf, q4, null_kv)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, wq, wv, wnull):
+        q4, null_kv, dka = ctx.saved_tensors
+        g_dqa, g_dka, g_dvf, g_q, g_null = _k_aug_bwd2(_c(wq), _c(wv), _c(wnull), q4, null_kv, dka)
+        return g_dqa, g_dka, g_dvf, g_q, g_null
+
+
+def attn_augment(q4, v4, null_kv, Lp):
+    return AttnAugmentFn.apply(q4, v4, null_kv, Lp)
+
+
 def composed_attention(qa, ka, v, mask, alpha):
     o, _ = ComposedAttnFn.apply(qa, ka, v, mask, alpha, {})
     return o

@@ -175,6 +175,20 @@ int gg_attn_bwd(const void* q, const void* k, const void* v, const float* null_k
                 int B, int heads, int nq, int nk, int d, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
                 float scale, int mode, int dtype, gg_stream_t stream);
 
+/* ---- operand builder of the gradient-penalty attention node (shared-QK L2-distance form, bf16, dim_head 64; replaces the
+ * concatenations / casts / row reductions around gigagan_pytorch.py:574-586 on that path and their autograd):
+ *   fwd:  qa [n,seq,h,80] = [q, 1, 1, 0..], ka [n,Lp,h,80] = [k, hi, lo, 0..] (k_0 = null key, k_j = q_{j-1}, padding rows 0
+ *         with hi = -1e30; hi + lo = -|k|^2/2), vf [n,Lp,h,64] = [null value; v; 0]
+ *   bwd:  dq = dqa[:, :64] + dka[1:seq+1, :64] - dka[1:seq+1, 64] * q,  dv = dvf[1:seq+1],  dnull [2,h,64] fp32 (j = 0 rows)
+ *   bwd2: the adjoint of bwd for the cotangents (wq, wv, wnull (nullable)): g_dqa, g_dka, g_dvf, g_q = -dka[.,64] * wq, g_null */
+int gg_attn_augment_fwd(const void* q, const void* v, const float* null_kv, void* qa, void* ka, void* vf, int n, int seq, int Lp,
+                        int heads, int d, gg_stream_t stream);
+int gg_attn_augment_bwd(const void* dqa, const void* dka, const void* dvf, const void* q, const float* null_kv, void* dq, void* dv,
+                        float* dnull, int n, int seq, int Lp, int heads, int d, gg_stream_t stream);
+int gg_attn_augment_bwd2(const void* wq, const void* wv, const float* wnull, const void* q, const float* null_kv, const void* dka,
+                         void* g_dqa, void* g_dka, void* g_dvf, void* g_q, float* g_null, int n, int seq, int Lp, int heads, int d,
+                         gg_stream_t stream);
+
 /* ---- AdamW on a flat fp32 parameter buffer (optimizer.py:10-34 as GigaGAN configures it: betas (0.5,0.9),
  * decoupled wd on ndim>=2 tensors).  chunks: int4 {offset_lo31, len, wd_flag, offset_hi}. */
 int gg_adamw(float* p, const float* g, float* m, float* v, const void* chunks, int nchunks, const int* step_ptr,

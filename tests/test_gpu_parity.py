@@ -386,9 +386,9 @@ def test_attention_node_matches_primitive_composition_through_double_backward(do
     x0 = torch.randn(2, 32, 32, 64, device=dev())
     w = torch.randn(2, 32, 32, 64, device=dev()).to(dtype)
     res = []
-    for node in (False, True):
-        old = modules._COMPUTE["attention_node"]
-        modules._COMPUTE["attention_node"] = node
+    for node in (False, True, "concat"):                      # "concat": the node fed by concatenations (no operand-builder kernel)
+        old = modules._COMPUTE["attention_node"], modules._COMPUTE["attention_augment"]
+        modules._COMPUTE["attention_node"], modules._COMPUTE["attention_augment"] = bool(node), node is True
         try:
             blk.zero_grad(set_to_none=True)
             x = x0.clone().to(dtype).requires_grad_()
@@ -398,16 +398,67 @@ def test_attention_node_matches_primitive_composition_through_double_backward(do
             total.backward()
             res.append([o.detach(), gx.detach(), x.grad] + [p.grad for p in blk.parameters()])
         finally:
-            modules._COMPUTE["attention_node"] = old
-    for a, b in zip(res[1], res[0]):
-        assert torch.isfinite(a).all()
-        assert relmax(a, b) < tol, (a.shape, relmax(a, b))
+            modules._COMPUTE["attention_node"], modules._COMPUTE["attention_augment"] = old
+    for other in res[1:]:
+        for a, b in zip(other, res[0]):
+            assert torch.isfinite(a).all()
+            assert relmax(a, b) < tol, (a.shape, relmax(a, b))
 
 
 def ops_sum(a, b):
     from gigagan_pytorch_b200 import ops
     a2, b2 = a.reshape(-1, a.shape[-1]), b.reshape(-1, b.shape[-1])
     return ops.sum_all(ops.dot_sc(a2, b2, a2.shape[0], 1))
+
+
+def test_attn_augment_kernels_match_formulas():
+    """csrc/attn_augment.cu (operand builder of the gradient-penalty attention node, its first and second derivative)
+    against the plain formulas on identical bf16 inputs: layouts, the hi/lo split of -|k|^2/2, the padding rows, the null
+    key/value rows and gradients."""
+    from gigagan_pytorch_b200 import ops
+    torch.manual_seed(0)
+    n, seq, h, d, Lp = 3, 100, 2, 64, 128
+    bf = torch.bfloat16
+    q4 = (torch.randn(n, seq, h, d, device=dev()) * 0.5).to(bf)
+    v4 = torch.randn(n, seq, h, d, device=dev()).to(bf)
+    nk = torch.randn(2, h, d, device=dev())
+    nkr = nk.to(bf).float()                                   # the key / value rows hold the bf16-rounded parameter
+    qa, ka, vf = ops._k_aug_fwd(q4, v4, nk, Lp)
+    kf = torch.cat([nkr[0][None, None].expand(n, 1, h, d), q4.float(), torch.zeros(n, Lp - seq - 1, h, d, device=dev())], 1)
+    t = -0.5 * (kf * kf).sum(-1)
+    assert torch.equal(qa[..., :64], q4) and torch.equal(ka[:, 1:seq + 1, :, :64], q4)
+    assert (qa[..., 64:66].float() == 1).all() and (qa[..., 66:] == 0).all() and (ka[..., 66:] == 0).all()
+    assert torch.equal(ka[:, 0, :, :64].float(), nkr[0][None].expand(n, h, d)) and (ka[:, seq + 1:, :, :64] == 0).all()
+    hl = ka[..., 64].float() + ka[..., 65].float()
+    assert ((hl[:, :seq + 1] - t[:, :seq + 1]).abs() <= 2.0 ** -15 * t[:, :seq + 1].abs() + 1e-6).all()
+    assert (ka[:, seq + 1:, :, 64].float() < -1e29).all()
+    assert torch.equal(vf[:, 1:seq + 1], v4) and (vf[:, seq + 1:] == 0).all()
+    assert torch.equal(vf[:, 0].float(), nkr[1][None].expand(n, h, d))
+    # first derivative
+    dqa = torch.randn(n, seq, h, 80, device=dev()).to(bf)
+    dka = torch.randn(n, Lp, h, 80, device=dev()).to(bf)
+    dvf = torch.randn(n, Lp, h, d, device=dev()).to(bf)
+    dq, dv, dnull = ops._k_aug_bwd(dqa, dka, dvf, q4, nk)
+    ghi = dka[:, 1:seq + 1, :, 64:65].float()
+    ref_dq = dqa[..., :64].float() + dka[:, 1:seq + 1, :, :64].float() - ghi * q4.float()
+    assert relmax(dq, ref_dq) < 1e-2 and torch.equal(dv, dvf[:, 1:seq + 1])
+    ref_dn = torch.stack([(dka[:, 0, :, :64].float() - dka[:, 0, :, 64:65].float() * nkr[0][None]).sum(0), dvf[:, 0].float().sum(0)])
+    assert relmax(dnull, ref_dn) < 1e-5
+    # second derivative
+    wq = torch.randn(n, seq, h, d, device=dev()).to(bf)
+    wv = torch.randn(n, seq, h, d, device=dev()).to(bf)
+    wn = torch.randn(2, h, d, device=dev())
+    g_dqa, g_dka, g_dvf, g_q, g_null = ops._k_aug_bwd2(wq, wv, wn, q4, nk, dka)
+    assert torch.equal(g_dqa[..., :64], wq) and (g_dqa[..., 64:] == 0).all()
+    assert torch.equal(g_dka[:, 1:seq + 1, :, :64], wq) and (g_dka[:, seq + 1:] == 0).all() and (g_dka[..., 65:] == 0).all()
+    assert relmax(g_dka[:, 1:seq + 1, :, 64], -(wq.float() * q4.float()).sum(-1)) < 1e-2
+    assert relmax(g_dka[:, 0, :, :64], wn[0][None].expand(n, h, d)) < 1e-2
+    assert relmax(g_dka[:, 0, :, 64], -(wn[0] * nkr[0]).sum(-1)[None].expand(n, h)) < 1e-2
+    assert torch.equal(g_dvf[:, 1:seq + 1], wv) and (g_dvf[:, seq + 1:] == 0).all()
+    assert relmax(g_dvf[:, 0], wn[1][None].expand(n, h, d)) < 1e-2
+    assert relmax(g_q, -ghi * wq.float()) < 1e-2
+    ref_gn = torch.stack([-(dka[:, 0, :, 64:65].float() * wn[0][None]).sum(0), torch.zeros(h, d, device=dev())])
+    assert relmax(g_null, ref_gn) < 1e-5
 
 
 def test_fused_attention_matches_composed_large():
