@@ -182,6 +182,7 @@ __global__ void attn_aug_null_kernel(const bf16* __restrict__ dka, const bf16* _
 static int aug_check(int d, int Lp, int seq, const void* a, const void* b) {
   if (d != AUG_D) return gg_fail("attn_augment: dim_head %d != 64", d);
   if (Lp < seq + 1) return gg_fail("attn_augment: Lp %d < seq + 1", Lp);
+  if (Lp % 4) return gg_fail("attn_augment: Lp %d must be a multiple of 4 (four 8-lane rows per warp reduce together)", Lp);
   if (((uintptr_t)a | (uintptr_t)b) & 15) return gg_fail("attn_augment: operands must be 16-byte aligned");
   return 0;
 }
