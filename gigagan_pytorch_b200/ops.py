@@ -1106,15 +1106,17 @@ class ComposedAttnBwdFn(Function):
             g_p, g_dP = _k_softmax_bwd2(p, dP, G)
             del G
             g_v = _k_bmm(_t(g_dP), go, 1.0, v if _dense_like(v) else False)          # dP = go v^T
-            g_go = _k_bmm(g_dP, v)
+            g_go = _k_bmm(g_dP, v, 1.0, True)      # physical (b, n, h, d): what the out-projection's convolutions read
             del g_dP
             if uk is not None:
                 g_qa = _k_bmm(dS, uk, alpha, qa if _dense_like(qa) else False)       # dka = alpha dS^T qa
             if uq is not None:
                 g_ka = _k_bmm(_t(dS), uq, alpha, ka if _dense_like(ka) else False)   # dqa = alpha dS ka
         if uv is not None:                                                             # dv = p^T go
-            t = _k_bmm(p, uv)
-            g_go = t if g_go is None else axpby(1.0, g_go, 1.0, t)
+            t = _k_bmm(p, uv, 1.0, True)
+            if g_go is not None:                   # summed in the physical layout (contiguous there: no staging copies)
+                t = axpby(1.0, g_go.permute(0, 2, 1, 3), 1.0, t.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+            g_go = t
             if g_p is None:
                 g_p = _k_bmm(go, _t(uv))
             else:
