@@ -262,3 +262,27 @@ def test_ema_decay_warmup_matches_ema_pytorch_formula():
     assert abs(ema_current_decay(102, 100, 0.995) - (1 - 2 ** (-2 / 3))) < 1e-12
     assert abs(ema_current_decay(111, 100, 0.995) - (1 - 11 ** (-2 / 3))) < 1e-12
     assert ema_current_decay(10 ** 6, 100, 0.995) == 0.995
+
+
+def test_flat_adamw_slices_cover_the_buffer_exactly():
+    """FlatAdamW._part_bounds (the slices of the pipelined all-reduce + AdamW): contiguous, ordered, every element once, cut on
+    chunk-table rows - also when there are fewer chunks than parts or one parameter dominates"""
+    import torch
+    from gigagan_pytorch_b200.trainer import FlatAdamW
+    old = FlatAdamW.CHUNK
+    try:
+        for chunk, layers in ((8, [(3, 5), (7,)]), (1 << 16, [(3, 5)]), (4, [(100,), (2,), (3,)])):
+            FlatAdamW.CHUNK = chunk
+            net = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s)) for s in layers])
+            opt = FlatAdamW(net)
+            rows = opt.chunks.tolist()
+            for parts in (1, 2, 4, 7):
+                b = opt._part_bounds(parts)
+                assert 1 <= len(b) <= parts
+                assert b[0][0] == 0 and b[0][2] == 0 and b[-1][1] == len(rows) and b[-1][3] == opt.flat.numel()
+                for (c0, c1, lo, hi), nxt in zip(b, b[1:] + [None]):
+                    assert c0 < c1 and lo == rows[c0][0] and hi == rows[c1 - 1][0] + rows[c1 - 1][1]
+                    if nxt is not None:
+                        assert nxt[0] == c1 and nxt[2] == hi
+    finally:
+        FlatAdamW.CHUNK = old

@@ -35,7 +35,8 @@ def near(lines, mnemonic, what, window=8):
 pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not available")
 
 
-@pytest.mark.parametrize("obj,max_r2ur_mma", [("conv_tc.o", 0), ("conv_thin_tc.o", 0), ("bmm_tc.o", 0), ("attn_tc.o", 11)])
+@pytest.mark.parametrize("obj,max_r2ur_mma", [("conv_tc.o", 0), ("conv_thin_tc.o", 0), ("bmm_tc.o", 0), ("attn_tc.o", 11),
+                                              ("attn_tc2.o", 60)])      # 392 UTCHMMA in 21 instantiations, 43 near an R2UR
 def test_tcgen05_mma_is_issued_from_uniform_registers(obj, max_r2ur_mma):
     lines = sass(obj)
     n_mma, r2ur_mma = near(lines, "UTCHMMA", "R2UR")
@@ -45,12 +46,19 @@ def test_tcgen05_mma_is_issued_from_uniform_registers(obj, max_r2ur_mma):
     assert any("LDTM" in l for l in lines), f"{obj}: no tcgen05.ld (LDTM)"
 
 
-@pytest.mark.parametrize("obj", ["conv_tc.o", "bmm_tc.o", "attn_tc.o"])
+@pytest.mark.parametrize("obj", ["conv_tc.o", "bmm_tc.o", "attn_tc.o", "attn_tc2.o"])
 def test_tma_loads_present(obj):
     lines = sass(obj)
     assert any("UTMALDG" in l for l in lines), f"{obj}: no TMA tensor load (UTMALDG)"
 
 
 def test_epilogues_use_256_bit_stores():
-    for obj in ("conv_tc.o", "conv_thin_tc.o", "attn_tc.o"):
+    for obj in ("conv_tc.o", "conv_thin_tc.o", "attn_tc.o", "attn_tc2.o"):
         assert any("STG.E.ENL2.256" in l for l in sass(obj)), f"{obj}: no 256-bit global store"
+
+
+def test_second_generation_attention_reads_tmem_in_whole_slabs():
+    """attn_tc2.cu: a softmax thread pulls its column slab of S / dP out of TMEM with 32-column loads (one round trip per
+    tile), not in 16-column chunks"""
+    lines = sass("attn_tc2.o")
+    assert sum("LDTM.x32" in l for l in lines) >= 20
